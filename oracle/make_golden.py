@@ -1,0 +1,228 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run HERE (needs /root/reference; the GPU box only sees the committed .npz files):
+
+    python -m oracle.make_golden
+
+The reference's `MPV.MPMeshVid`, `utils_vid.Patch3DGPNN*Loss`, `utils_mpi.overcompose` etc. are
+imported verbatim behind `oracle/ref_shims` (see its README for the "parity unpinned" caveat on
+the pytorch3d rasteriser).  Inputs are seeded and stored together with the outputs, so tests can
+replay them through the oracle restatement (CPU) and through the CUDA path (GPU).
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import ref_env  # noqa: E402
+from oracle import mpv_oracle as MO  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _np(d):
+    out = {}
+    for k, v in d.items():
+        if torch.is_tensor(v):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    return out
+
+
+def _view(seed, H, W, rot=0.05, trans=(0.08, -0.03, 0.02)):
+    g = torch.Generator().manual_seed(seed)
+    c, s = np.cos(rot), np.sin(rot)
+    ext = torch.eye(4)
+    ext[:3, :3] = torch.tensor([[c, 0, s], [0, 1, 0], [-s, 0, c]], dtype=torch.float32)
+    ext[:3, 3] = torch.tensor(trans)
+    f = 0.8 * W
+    intr = torch.tensor([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1.]])
+    intr[:2, 2] += torch.rand(2, generator=g) - 0.5          # train_3dvid.py:222-225
+    return ext[None], intr[None]
+
+
+def _load_state_into_reference(m, st):
+    """Overwrite a reference MPMeshVid's tensors with an MPVState (same names, MPV.py:95-104)."""
+    import torch.nn as nn
+    m._verts.data = st.verts.clone()
+    m.planedepth.data = st.planedepth.clone()
+    m.ref_extrin.data = st.ref_extrin.clone()
+    m.ref_intrin.data = st.ref_intrin.clone()
+    m.uvs.data = st.uvs.clone()
+    m.uvs_dyn.data = st.uvs_dyn.clone()
+    m.uvfaces = st.uvfaces.clone()
+    m.uvfaces_dyn = st.uvfaces_dyn.clone()
+    m.faces = st.faces.clone()
+    m.faces_dyn = st.faces_dyn.clone()
+    m.register_parameter("atlas", nn.Parameter(st.atlas.clone()))
+    m.register_parameter("atlas_dyn", nn.Parameter(st.atlas_dyn.clone()))
+    m.frm_num = st.atlas_dyn.shape[0]
+    m.is_sparse = True
+    m.has_dyn = True
+
+
+def _state_arrays(st):
+    return dict(verts=st.verts, planedepth=st.planedepth, faces=st.faces, faces_dyn=st.faces_dyn, uvs=st.uvs,
+                uvs_dyn=st.uvs_dyn, uvfaces=st.uvfaces, uvfaces_dyn=st.uvfaces_dyn, atlas=st.atlas,
+                atlas_dyn=st.atlas_dyn, ref_extrin=st.ref_extrin, ref_intrin=st.ref_intrin,
+                mpi_d=st.mpi_d, hv=st.hv, wv=st.wv)
+
+
+def make_model(kind, H, W, D, hv, wv, T, seed, **kw):
+    import MPV  # reference
+    args = ref_env.make_args(mpi_d=D, mpi_h_verts=hv, mpi_w_verts=wv, atlas_grid_h=kw.get("grid_h", 2),
+                             mpv_frm_num=T, mpi_h_scale=kw.get("scale", 1.2), mpi_w_scale=kw.get("scale", 1.2),
+                             add_intrin_noise=False)
+    f = 0.8 * W
+    ref_intrin = np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32)
+    torch.manual_seed(seed)
+    m = MPV.MPMeshVid(args, H, W, np.eye(4, dtype=np.float32), ref_intrin, 1.0, 10.0)
+    if kind == "dense":
+        st = MO.dense_state(H, W, D, hv, wv, kw.get("grid_h", 2), T, 1.0, 10.0, kw.get("scale", 1.2),
+                            kw.get("scale", 1.2), seed=seed)
+        # the oracle's constructor must reproduce the reference's own geometry exactly
+        assert torch.allclose(st.verts, m._verts.data) and torch.equal(st.faces_dyn, m.faces_dyn)
+        assert torch.allclose(st.uvs_dyn, m.uvs_dyn.data, atol=1e-7) and torch.allclose(st.planedepth, m.planedepth)
+        st.atlas = st.atlas[:, :, :1, :1].clone()             # like init_from_mpi's dummy static (MPV.py:266)
+    else:
+        st = MO.sparse_state(H, W, D, hv, wv, T, 1.0, 10.0, tile=kw.get("tile", 6), occupancy=kw.get("occ", 0.6),
+                             dyn_frac=0.5, h_scale=kw.get("scale", 1.2), w_scale=kw.get("scale", 1.2), seed=seed)
+    _load_state_into_reference(m, st)
+    return m, st, args
+
+
+def golden_render(name, kind, H=24, W=40, D=4, hv=5, wv=7, T=3, seed=0, **kw):
+    m, st, args = make_model(kind, H, W, D, hv, wv, T, seed, **kw)
+    ext, intr = _view(seed, H, W)
+    m.eval()
+    ts = list(range(T))
+    with torch.no_grad():
+        extr = ext @ m.ref_extrin[None].inverse()
+        rgb, var = m.render(H, W, extr, intr, ts)
+        rgb_eval, _ = m(H, W, ext, intr, ts=[T - 1, 0])
+    out = dict(H=H, W=W, T=T, tar_extrin=ext, tar_intrin=intr, rgb=rgb, mpi=var["mpi"], alpha=var["alpha"],
+               blend_weight=var["blend_weight"], pix_to_face=var["pix_to_face"], K=var["mpi"].shape[-2],
+               rgb_eval_ts=rgb_eval, **_state_arrays(st))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(out))
+    print(name, "K =", var["mpi"].shape[-2], "rgb mean", float(rgb.mean()))
+
+
+LOSS_CFG_REF = dict(loss_name="gpnn_lm", loss_gain=3.5, patch_size=5, patcht_size=3, stride=2, stridet=1,
+                    alpha=0.0, rou="-2", scaling=0.1, dist_fn="mse", macro_block=15, factor=1)
+LOSS_CFG_OTHER = dict(loss_name="gpnn_lm", patch_size=3, patcht_size=3, stride=2, stridet=1,
+                      alpha=10000.0, rou="-2", scaling=0.1, dist_fn="mse", macro_block=15, factor=1)
+
+
+def _batched(cfg):
+    """What the DataLoader hands to forward (MPV.py:494 un-batches with v[0])."""
+    return {k: ([v] if isinstance(v, str) else torch.tensor([v])) for k, v in cfg.items()}
+
+
+def golden_step(name, kind, cfg, H=24, W=40, D=4, hv=5, wv=7, T=6, F=9, seed=1, lr=0.05, **kw):
+    m, st, args = make_model(kind, H, W, D, hv, wv, T, seed, **kw)
+    ext, intr = _view(seed, H, W)
+    g = torch.Generator().manual_seed(seed + 7)
+    res = torch.rand(1, F, 3, H, W, generator=g)
+    res = (res + res.roll(1, 1) + res.roll(2, 1)) / 3          # temporally smooth-ish
+    m.train()
+    params = [m.atlas, m.atlas_dyn]
+    opt = torch.optim.Adam(params, lr=lr, betas=(0.9, 0.999), eps=6e-8)   # MPV.py:213
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, extra = m(H, W, ext, intr, res=res, losscfg=_batched(cfg))
+    extra_v = {k: v.detach().clone() for k, v in extra.items()}
+    swd = extra.pop("swd").mean()                               # train_3dvid.py:230-244
+    loss = swd
+    for k, v in extra.items():
+        w = getattr(args, f"{k}_loss_weight")
+        if w > 0:
+            loss = loss + v.mean() * w
+    opt.zero_grad()
+    loss.backward()
+    g_atlas = m.atlas.grad.clone() if m.atlas.grad is not None else torch.zeros_like(m.atlas)
+    g_dyn = m.atlas_dyn.grad.clone()
+    opt.step()
+    lossobj = m.losses[cfg["loss_name"]]
+    out = dict(H=H, W=W, T=T, F=F, tar_extrin=ext, tar_intrin=intr, res=res, lr=lr, loss=loss.detach(),
+               grad_atlas=g_atlas, grad_atlas_dyn=g_dyn, new_atlas=m.atlas.data, new_atlas_dyn=m.atlas_dyn.data,
+               y2x=lossobj.last_y2x, weight=lossobj.last_weight,
+               rgb_smooth_w=args.rgb_smooth_loss_weight, a_smooth_w=args.a_smooth_loss_weight,
+               **{"extra_" + k: v for k, v in extra_v.items()},
+               **{"cfg_" + k: v for k, v in cfg.items()}, **_state_arrays(st))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(out))
+    print(name, {k: float(v) for k, v in extra_v.items()}, "loss", float(loss))
+
+
+def golden_loss(name, cls, t=8, F=12, h=23, w=31, seed=3, smooth=False, **cfg):
+    import utils_vid  # reference
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(1, 3, t, h, w, generator=g)
+    y = torch.rand(1, 3, F, h, w, generator=g)
+    if smooth:
+        y = (y + y.roll(1, 2) + y.roll(2, 2)) / 3
+        x = (y[:, :, :t] * 0.8 + 0.2 * x).contiguous()
+    x.requires_grad_(True)
+    lossobj = getattr(utils_vid, cls)()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        loss = lossobj(x, y, **cfg)
+    loss.backward()
+    # NN indices of the global problem, straight from the reference's search (utils_vid.py:122-142)
+    p, pt, s, st = cfg["patch_size"], cfg["patcht_size"], cfg["stride"], cfg["stridet"]
+    hh, ww, tt = lossobj.last_y2x.shape[-2], lossobj.last_y2x.shape[-1], lossobj.last_y2x.shape[-3]
+    with torch.no_grad():
+        px = utils_vid.extract_3Dpatches(x[..., :tt, :hh, :ww], p, pt, s, st)
+        b, c, d, ho, wo = px.shape
+        px = px.permute(0, 3, 4, 2, 1).reshape(ho * wo, -1, 3, pt, p, p)
+        py = utils_vid.extract_3Dpatches(y[..., :hh, :ww], p, pt, s, st)
+        py = py.permute(0, 3, 4, 2, 1).reshape(ho * wo, -1, 3, pt, p, p)
+        alpha = cfg.get("alpha", 1e10)
+        nn = utils_vid.get_NN_indices_low_memory(px, py, None if alpha > 100 else alpha, 1024)
+    out = dict(x=x.detach(), y=y, loss=loss.detach(), y2x=lossobj.last_y2x, weight=lossobj.last_weight,
+               grad_x=x.grad, nn=nn.reshape(ho, wo, -1), cls=cls, **{"cfg_" + k: v for k, v in cfg.items()})
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(out))
+    print(name, "loss", float(loss))
+
+
+def golden_pointwise(name):
+    """overcompose (utils_mpi.py:92-107) + robust_lossfun (utils_vid.py:10-26) known answers."""
+    import utils_mpi
+    import utils_vid
+    g = torch.Generator().manual_seed(5)
+    alpha = torch.rand(2, 3, 4, 6, generator=g)
+    content = torch.rand(2, 3, 4, 6, 3, generator=g)
+    rgb, bw = utils_mpi.overcompose(alpha, content)
+    r = torch.randn(257, generator=g) * 0.3
+    out = dict(alpha=alpha, content=content, rgb=rgb, bw=bw, r=r, depths=utils_mpi.make_depths(8, 1.0, 10.0))
+    for rou in ("mse", "abs", "0", "2", "-2", "1"):
+        out["rho_" + rou] = utils_vid.robust_lossfun(r, rou, 0.1)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(out))
+    print(name)
+
+
+def main():
+    assert ref_env.reference_available(), "needs /root/reference"
+    ref_env.enable()
+    os.makedirs(OUT, exist_ok=True)
+    golden_pointwise("pointwise")
+    golden_render("render_dense", "dense", seed=0)
+    golden_render("render_sparse", "sparse", seed=1, D=6, hv=6, wv=9, T=2)
+    golden_step("step_dense_refcfg", "dense", LOSS_CFG_REF, seed=2)
+    golden_step("step_sparse_othercfg", "sparse", LOSS_CFG_OTHER, seed=3, D=6, hv=6, wv=9)
+    golden_loss("loss_lm_alpha0", "Patch3DGPNNLowMemLoss", macro_block=15, patch_size=5, stride=2, patcht_size=3,
+                stridet=1, rou="-2", scaling=0.1, alpha=0.0)
+    golden_loss("loss_lm_noalpha", "Patch3DGPNNLowMemLoss", macro_block=11, patch_size=3, stride=2, patcht_size=3,
+                stridet=1, rou="-2", scaling=0.1, alpha=10000.0, smooth=True)
+    golden_loss("loss_direct_p7", "Patch3DGPNNDirectLoss", patch_size=7, stride=4, patcht_size=2, stridet=2,
+                rou="0", scaling=0.2, alpha=0.5, t=9, h=23, w=27)
+    golden_loss("loss_lm_abs", "Patch3DGPNNLowMemLoss", macro_block=64, patch_size=3, stride=1, patcht_size=1,
+                stridet=1, rou="abs", scaling=0.2, alpha=10000.0, t=4, F=5, h=9, w=10)
+
+
+if __name__ == "__main__":
+    main()
