@@ -1,0 +1,148 @@
+/*
+ * vl3d.h — C ABI of libvl3d.so: the B200 (sm_100a) kernels behind VideoLoop3D's stage-2 hot path.
+ *
+ * The reference (limacv/VideoLoop3D) is pure Python and has no FFI / plugin registry: the boundary
+ * it offers is the Python operator surface (`MPMeshVid.render` / `forward`, the loop-loss callables,
+ * `run_iter`).  This header is the thin C boundary underneath our drop-in Python mirror of that
+ * surface (`videoloop3d_b200/`); each entry point cites the reference code it replaces.
+ * `INTEGRATION.md` shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named `*_host` or it is
+ *     a `const vl3d_*` descriptor struct (host memory, copied into the launch);
+ *   - the caller allocates every input, output and workspace; the library never allocates, frees or
+ *     keeps state between calls (except the last-error string);
+ *   - stream-ordered on `stream` (a cudaStream_t passed as void*), no host synchronisation inside,
+ *     CUDA-graph capturable;
+ *   - return 0 on success, a negative `VL3D_E*` for argument errors (validated before any launch),
+ *     a positive value = cudaError_t from the launch; `vl3d_last_error_string()` describes the last
+ *     failure on the calling thread.  Never throws, never aborts.
+ *   - fp32 arithmetic throughout (the reference's `fp16` flag is marked "do NOT use",
+ *     config_parser.py:32-33); NN indices are int32.
+ *   - texel layout: atlases are RGBA-interleaved, i.e. a torch tensor of logical shape (T,4,Hd,Wd)
+ *     in `channels_last` memory format == physical (T,Hd,Wd,4).  Rendered video / targets are
+ *     frame-major channel-planar (T,3,H,W).
+ */
+#ifndef VL3D_H_
+#define VL3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VL3D_VERSION 100
+#define VL3D_MAX_PLANES 32
+
+#define VL3D_EINVAL   (-1)  /* bad argument / shape */
+#define VL3D_ENULL    (-2)  /* required pointer is NULL */
+#define VL3D_ERANGE   (-3)  /* size outside the supported range (e.g. D > 32, patch too large) */
+#define VL3D_EALIGN   (-4)  /* pointer not 16-byte aligned where float4 access is required */
+
+/* One quad ("tile") of the MPV mesh: where its texels live in the atlas.
+ * Built on the host from faces(_dyn)[::2,0] and uvs(_dyn) (MPV.py:66-81, MPI.py:385-418).
+ * Atlas pixel coordinate of a point with in-quad fractions (a, b):
+ *     x = x0i + (x0f + a * sx),   y = y0i + (y0f + b * sy)      (align_corners=True pixels)
+ * kind: 0 = culled / absent, 1 = static atlas, 2 = dynamic atlas. */
+typedef struct vl3d_quad {
+    float   x0f, y0f, sx, sy;
+    int32_t x0i, y0i, kind, reserved;
+} vl3d_quad;
+
+/* Per-call view descriptor (host memory).  Replaces the no_grad geometry block of
+ * MPMeshVid.render (MPV.py:353-405: NDC transform, pytorch3d rasterize_meshes, get_uvs):
+ * for plane d, target pixel centre (c+0.5, r+0.5) maps to quad-grid coordinates
+ *     [gx*w, gy*w, w] = hom[d] * [c + 0.5 - cx, r + 0.5 - cy, 1],
+ * gx in (0,qw), gy in (0,qh); the homography is pre-multiplied so that a valid (in front of the
+ * camera) intersection has w > 0.  Planes are ordered nearest first (MPV.py:51). */
+typedef struct vl3d_view {
+    int32_t H, W;            /* rendered patch size */
+    int32_t D;               /* planes, 1..VL3D_MAX_PLANES */
+    int32_t qh, qw;          /* quads per plane = (mpi_h_verts-1, mpi_w_verts-1) */
+    int32_t dyn_h, dyn_w;    /* dynamic atlas size in texels */
+    int32_t sta_h, sta_w;    /* static atlas size in texels */
+    float   cx, cy;
+    float   hom[VL3D_MAX_PLANES * 9];
+} vl3d_view;
+
+/* Looping-loss problem descriptor (fitted crop; utils_vid.py:305-320).
+ * x = rendered (looped, scaled) video, frames tx in [0, t); y = target video, frames in [0, F).
+ * Both are channel-planar with explicit element strides (frame, channel, row); pixels contiguous. */
+typedef struct vl3d_loss_desc {
+    int32_t t, F;            /* frames used of x (fitted) and y */
+    int32_t h, w;            /* fitted spatial crop */
+    int32_t p, pt, s, st;    /* patch size, temporal patch size, stride, temporal stride */
+    int32_t n1, n2;          /* query / candidate temporal positions */
+    int32_t ho, wo;          /* patch positions per column / row */
+    int64_t x_sf, x_sc, x_sr;/* x strides in elements: frame, channel, row */
+    int64_t y_sf, y_sc, y_sr;
+    int32_t use_alpha;       /* 0: alpha=None (alpha > 100, utils_vid.py:208) */
+    float   alpha;
+} vl3d_loss_desc;
+
+int         vl3d_version(void);
+const char* vl3d_last_error_string(void);
+
+/* ---- composite (MPV.py:413-475 render_masked_rgba + masked_scatter + utils_mpi.overcompose,
+ *      and the slot-wise smoothness regularisers MPV.py:517-531) -------------------------------
+ * ts:        T int32 frame ids into atlas_dyn, or NULL for 0..T-1 (MPV.py:480-481).
+ * rgb_out:   (T + pad, 3, H, W); frames t < pad are also written at T + t (loop pad, MPV.py:490-492).
+ * alpha_out: (T, H, W) or NULL  (MPV.py:454).
+ * smooth_sums: 4 doubles, ACCUMULATED: sum|dx rgb|, sum|dy rgb|, sum|dx a|, sum|dy a| over slot-indexed
+ *            values (missing slots read as 0), or NULL to skip the regulariser pass.
+ * mpi_out:   (T, H, W, D, 4) slot-indexed activated RGBA (variables['mpi'], MPV.py:441-449) or NULL.
+ * hits_out:  (H, W) int32 number of occupied slots per pixel (K = max, utils.py:64-69) or NULL. */
+int vl3d_composite_fwd(const vl3d_view* view, const vl3d_quad* quads, const float* atlas_dyn,
+                       const float* atlas_sta, const int32_t* ts, int32_t T, int32_t pad,
+                       float* rgb_out, float* alpha_out, double* smooth_sums, float* mpi_out,
+                       int32_t* hits_out, void* stream);
+
+/* Hand-written backward of the above (replaces autograd through MPV.py:413-451, utils_mpi.py:92-107
+ * and MPV.py:517-531).  grad_rgb: (T + pad, 3, H, W) = dL/d rgb_out (pad frames folded in-kernel).
+ * rgb: the forward's rgb_out.  w_smooth: 4 DEVICE floats dL/d(smooth_sums[i]), or NULL when the forward
+ * ran without the regulariser pass (no host round trip of upstream scalars).
+ * grad_dyn (Tall,Hd,Wd,4) and grad_sta (Hs,Ws,4) are ACCUMULATED into (caller zeroes them). */
+int vl3d_composite_bwd(const vl3d_view* view, const vl3d_quad* quads, const float* atlas_dyn,
+                       const float* atlas_sta, const int32_t* ts, int32_t T, int32_t pad,
+                       const float* grad_rgb, const float* rgb, const float* w_smooth,
+                       float* grad_dyn, float* grad_sta, void* stream);
+
+/* ---- scale-invariant gain (MPV.py:499-504):
+ *      out[0] = (exp(mean_{c,h,w} log((mean_F res + .01)/(mean_T rgb + .01))) + 3) / 4
+ * rgb (T,3,H,W) contiguous, res (F,3,H,W) contiguous. partials: workspace of >= vl3d_scale_partials()
+ * doubles. */
+int vl3d_scale_partials(void);
+int vl3d_scale_invariant(const float* rgb, int32_t T, const float* res, int32_t F, int32_t H, int32_t W,
+                         double* partials, float* out, void* stream);
+
+/* ---- looping loss (utils_vid.py) ---------------------------------------------------------------
+ * vl3d_patchnn_search: extract_3Dpatches + efficient_compute_distances + get_col_mins_efficient +
+ *   get_NN_indices_low_memory (utils_vid.py:60-142) fused; distances are direct sums of squared
+ *   differences in fp32.  x values are multiplied by *xscale (device scalar, NULL = 1).
+ *   nn_out: (ho, wo, n1) int32, first-minimum tie rule.  Only patch rows [row_begin, row_end) are
+ *   searched and written (patch positions are independent: this is how ranks split the search).
+ * vl3d_vote_loss: gather + FoldNd votes / counts + robust_lossfun + its derivative
+ *   (utils_vid.py:217-229, 344-348, 10-26).  rou_kind: 0 general float rou, 1 'mse', 2 'abs'.
+ *   y2x_out (3,t,h,w)/weight_out (t,h,w) optional (last_y2x / last_weight caches).
+ *   grad_out: (Tx_full, 3, Hfull, Wfull) = gcoef * xscale * rho'(x*xscale - y2x) / N inside the
+ *   fitted crop, 0 outside (optional).  loss_out[0] = mean rho (1 float). partials: workspace of
+ *   >= vl3d_vote_partials(Tx_full, Hfull, Wfull) doubles. */
+int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, const float* xscale, const float* y,
+                        int32_t row_begin, int32_t row_end, int32_t* nn_out, void* stream);
+int vl3d_vote_partials(int32_t Tx_full, int32_t Hfull, int32_t Wfull);
+int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const float* xscale, const float* y,
+                   const int32_t* nn, int32_t rou_kind, float rou, float scaling, float gcoef,
+                   int32_t Tx_full, int32_t Hfull, int32_t Wfull,
+                   float* y2x_out, float* weight_out, float* grad_out, double* partials, float* loss_out,
+                   void* stream);
+
+/* ---- optimiser (MPV.py:200-218: torch.optim.Adam(betas=(0.9,0.999), eps=6e-8), one tensor) ------
+ * p, g, m, v: n floats each; step >= 1.  lr etc. are host scalars. */
+int vl3d_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr,
+                   float beta1, float beta2, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VL3D_H_ */

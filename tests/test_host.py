@@ -1,0 +1,127 @@
+"""CPU: host-side logic (quad table, homographies, loss descriptors, args) and the C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mpv_oracle as MO
+from util import load_golden, state_from_golden
+from videoloop3d_b200 import _lib, build, ops, tiles
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _emulate_kernel_geometry(st, table, homs, cx, cy, H, W):
+    """float32 re-statement of composite.cu's plane_grid()/make_taps() address maths (test only)."""
+    D, qh, qw = st.mpi_d, st.hv - 1, st.wv - 1
+    r, c = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    u = (c + 0.5 - cx).astype(np.float32).reshape(-1)
+    v = (r + 0.5 - cy).astype(np.float32).reshape(-1)
+    out = []
+    for d in range(D):
+        h = homs[d]
+        w_ = h[6] * u + h[7] * v + h[8]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            gx = (h[0] * u + h[1] * v + h[2]) / w_
+            gy = (h[3] * u + h[4] * v + h[5]) / w_
+        ok = (w_ > 0) & (gx > 0) & (gx < qw) & (gy > 0) & (gy < qh)
+        qx = np.clip(np.nan_to_num(gx).astype(np.int32), 0, qw - 1)
+        qy = np.clip(np.nan_to_num(gy).astype(np.int32), 0, qh - 1)
+        e = table[(d * qh + qy) * qw + qx]
+        ok &= e["kind"] != 0
+        ax = e["x0i"] + (e["x0f"] + (gx - qx) * e["sx"])
+        ay = e["y0i"] + (e["y0f"] + (gy - qy) * e["sy"])
+        out.append((ok, e["kind"], ax, ay))
+    return out
+
+
+@pytest.mark.parametrize("name", ["render_dense", "render_sparse"])
+def test_quad_table_and_homographies_match_oracle_geometry(name):
+    g = load_golden(name)
+    st = state_from_golden(g)
+    H, W, D, hv, wv = int(g["H"]), int(g["W"]), st.mpi_d, st.hv, st.wv
+    grids = tiles.plane_grids(st.verts.numpy(), D, hv, wv)
+    table = tiles.build_quad_table(D, hv, wv, st.faces.numpy(), st.uvs.numpy(), st.uvfaces.numpy(),
+                                   tuple(st.atlas.shape[-2:]), st.faces_dyn.numpy(), st.uvs_dyn.numpy(),
+                                   st.uvfaces_dyn.numpy(), tuple(st.atlas_dyn.shape[-2:]))
+    assert table.dtype.itemsize == ctypes.sizeof(_lib.Quad) == 32
+    ext = g["tar_extrin"].reshape(4, 4).astype(np.float64) @ np.linalg.inv(st.ref_extrin.numpy().astype(np.float64))
+    homs, cx, cy = tiles.view_homographies(grids, hv - 1, wv - 1, ext, g["tar_intrin"], np.eye(4), H, W)
+    geo = MO.geometry(st, H, W, torch.as_tensor(g["tar_extrin"]), torch.as_tensor(g["tar_intrin"]))
+    for d, (ok, kind, ax, ay) in enumerate(_emulate_kernel_geometry(st, table, homs, cx, cy, H, W)):
+        oh = geo["hit"][:, d].numpy()
+        assert np.array_equal(ok, oh)
+        assert np.array_equal(kind[oh], geo["kind"][:, d].numpy()[oh])
+        assert np.abs(ax[oh] - geo["ax"][:, d].numpy()[oh]).max(initial=0) < 1e-4
+        assert np.abs(ay[oh] - geo["ay"][:, d].numpy()[oh]).max(initial=0) < 1e-4
+
+
+def test_geometry_errors():
+    st = MO.dense_state(16, 24, 2, 3, 4, 1, 1, 1.0, 10.0)
+    v = st.verts.numpy().copy()
+    v[5, 0] += 0.3
+    with pytest.raises(tiles.GeometryError):
+        tiles.plane_grids(v, 2, 3, 4)
+    grids = tiles.plane_grids(st.verts.numpy(), 2, 3, 4)
+    behind = np.eye(4)
+    behind[2, 3] = -5.0          # camera origin at z = +5: inside the plane stack
+    with pytest.raises(tiles.GeometryError):
+        tiles.view_homographies(grids, 2, 3, behind, np.array([[20., 0, 12], [0, 20, 8], [0, 0, 1]]), np.eye(4), 16, 24)
+    bad_faces = st.faces_dyn.numpy().copy()
+    bad_faces[0, 1] += 1
+    with pytest.raises(tiles.GeometryError):
+        tiles.build_quad_table(2, 3, 4, st.faces.numpy(), st.uvs.numpy(), st.uvfaces.numpy(), (4, 4), bad_faces,
+                               st.uvs_dyn.numpy(), st.uvfaces_dyn.numpy(), tuple(st.atlas_dyn.shape[-2:]))
+
+
+def test_loss_desc_fitting_matches_reference_rules():
+    d = ops.make_loss_desc((50, 3, 180, 320), (1, 1, 1), (258, 3, 180, 320), (1, 1, 1), 11, 3, 4, 1, 0.0)
+    assert (d.t, d.h, d.w) == (50, 179, 319) and (d.n1, d.n2, d.ho, d.wo) == (48, 256, 43, 78)
+    assert d.use_alpha == 1 and d.alpha == 0.0
+    d = ops.make_loss_desc((50, 3, 180, 320), (1, 1, 1), (64, 3, 180, 320), (1, 1, 1), 3, 3, 2, 1, 10000.0)
+    assert (d.h, d.w, d.ho, d.wo) == (179, 319, 89, 159) and d.use_alpha == 0
+    d = ops.make_loss_desc((9, 3, 23, 27), (1, 1, 1), (12, 3, 23, 27), (1, 1, 1), 7, 2, 4, 2, 0.5, fit=False)
+    assert (d.t, d.h, d.w, d.n1, d.n2, d.ho, d.wo) == (9, 23, 27, 4, 6, 5, 6)
+    with pytest.raises(ValueError):
+        ops.make_loss_desc((2, 3, 23, 27), (1, 1, 1), (12, 3, 23, 27), (1, 1, 1), 7, 3, 4, 1, 0.5)
+    assert ops.parse_rou("-2") == (0, -2.0) and ops.parse_rou("mse")[0] == 1 and ops.parse_rou("abs")[0] == 2
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads (no GPU needed) and exports exactly what include/vl3d.h declares."""
+    build.build()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "vl3d.h")).read()
+    declared = set(re.findall(r"\b(vl3d_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.vl3d_version() == 100
+    assert ctypes.sizeof(_lib.View) == 4 * 9 + 4 * 2 + 4 * 32 * 9
+    assert ctypes.sizeof(_lib.LossDesc) == 4 * 12 + 8 * 6 + 8
+
+
+def test_argument_validation_happens_before_any_launch():
+    lib = _lib.load()
+    v = _lib.View()
+    v.D = 64
+    with pytest.raises(_lib.Vl3dError, match="D=64"):
+        _lib.call("vl3d_composite_fwd", ctypes.byref(v), ctypes.c_void_p(16), None, None, None, 1, 0,
+                  ctypes.c_void_p(16), None, None, None, None, None)
+    d = ops.make_loss_desc((50, 3, 180, 320), (1, 1, 1), (258, 3, 180, 320), (1, 1, 1), 11, 3, 4, 1, 0.0)
+    with pytest.raises(_lib.Vl3dError, match="NULL"):
+        _lib.call("vl3d_patchnn_search", ctypes.byref(d), None, None, None, 0, 1, None, None)
+    with pytest.raises(_lib.Vl3dError, match="step"):
+        _lib.call("vl3d_adam_step", ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16),
+                  8, 0, 0.1, 0.9, 0.999, 6e-8, None)
+    assert b"step" in lib.vl3d_last_error_string()
+
+
+def test_product_refuses_cpu_tensors():
+    from videoloop3d_b200 import Patch3DGPNNLowMemLoss, Vl3dError
+    x, y = torch.rand(1, 3, 5, 9, 9), torch.rand(1, 3, 6, 9, 9)
+    with pytest.raises(Vl3dError):
+        Patch3DGPNNLowMemLoss()(x, y, patch_size=3, stride=2, patcht_size=3, stridet=1)

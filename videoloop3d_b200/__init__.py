@@ -1,0 +1,16 @@
+"""videoloop3d_b200 — B200-native (sm_100a) hot path of VideoLoop3D's stage-2 optimisation step.
+
+Public surface mirrors the reference's Python operators:
+    MPMeshVid                    (reference MPV.py)       render / forward / lod / get_optimizer / ...
+    Patch3DGPNNLowMemLoss, ...   (reference utils_vid.py) loop-loss callables
+    make_run_iter, FusedLoopStep (reference train_3dvid.py:214-255) the optimisation step
+The numerical work is done by hand-written CUDA kernels in libvl3d.so (C ABI: include/vl3d.h).
+"""
+from ._lib import Vl3dError, load as load_library  # noqa: F401
+from .loop_loss import (Patch3DAvg, Patch3DGPNNDirectLoss, Patch3DGPNNLowMemDownSampleLoss,  # noqa: F401
+                        Patch3DGPNNLowMemLoss, Patch3DMSE)
+from .mpv import MPMeshVid, get_new_intrin, make_depths, gen_mpi_vertices, pose2extrin_torch  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
+from .train_step import FusedLoopStep, make_run_iter, default_args  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,102 @@
+"""ctypes binding of libvl3d.so (C ABI in include/vl3d.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or fails to load, every product
+entry point raises.  (The CPU oracle lives under oracle/ and is test infrastructure only.)
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+MAX_PLANES = 32
+
+
+class Quad(C.Structure):
+    _fields_ = [("x0f", C.c_float), ("y0f", C.c_float), ("sx", C.c_float), ("sy", C.c_float),
+                ("x0i", C.c_int32), ("y0i", C.c_int32), ("kind", C.c_int32), ("reserved", C.c_int32)]
+
+
+class View(C.Structure):
+    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("D", C.c_int32), ("qh", C.c_int32), ("qw", C.c_int32),
+                ("dyn_h", C.c_int32), ("dyn_w", C.c_int32), ("sta_h", C.c_int32), ("sta_w", C.c_int32),
+                ("cx", C.c_float), ("cy", C.c_float), ("hom", C.c_float * (MAX_PLANES * 9))]
+
+
+class LossDesc(C.Structure):
+    _fields_ = [("t", C.c_int32), ("F", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("p", C.c_int32), ("pt", C.c_int32), ("s", C.c_int32), ("st", C.c_int32),
+                ("n1", C.c_int32), ("n2", C.c_int32), ("ho", C.c_int32), ("wo", C.c_int32),
+                ("x_sf", C.c_int64), ("x_sc", C.c_int64), ("x_sr", C.c_int64),
+                ("y_sf", C.c_int64), ("y_sc", C.c_int64), ("y_sr", C.c_int64),
+                ("use_alpha", C.c_int32), ("alpha", C.c_float)]
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    "vl3d_version": (C.c_int, []),
+    "vl3d_last_error_string": (C.c_char_p, []),
+    "vl3d_composite_fwd": (C.c_int, [C.POINTER(View), _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "vl3d_composite_bwd": (C.c_int, [C.POINTER(View), _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "vl3d_scale_partials": (C.c_int, []),
+    "vl3d_scale_invariant": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
+    "vl3d_patchnn_search": (C.c_int, [C.POINTER(LossDesc), _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "vl3d_vote_partials": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    "vl3d_vote_loss": (C.c_int, [C.POINTER(LossDesc), _P, _P, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_float,
+                                 C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "vl3d_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
+}
+EXPORTS = tuple(_SIGNATURES)
+
+_lib = None
+LAUNCHES = 0          # kernels launched through this binding (bench.py's gpu_launches)
+_LAUNCHES_PER_CALL = {"vl3d_composite_fwd": 1, "vl3d_composite_bwd": 1, "vl3d_scale_invariant": 2,
+                      "vl3d_patchnn_search": 1, "vl3d_vote_loss": 2, "vl3d_adam_step": 1}
+
+
+class Vl3dError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load libvl3d.so (built in-tree by videoloop3d_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.isfile(path):
+        raise Vl3dError(f"{path} not found: build it with `python -m videoloop3d_b200.build` "
+                        f"(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here == header / library mismatch
+        fn.restype, fn.argtypes = res, args
+    if lib.vl3d_version() != 100:
+        raise Vl3dError(f"libvl3d version {lib.vl3d_version()} != 100")
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise Vl3dError on a non-zero status."""
+    global LAUNCHES
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.vl3d_last_error_string().decode(errors="replace")
+        raise Vl3dError(f"{name} failed ({rc}): {msg}")
+    LAUNCHES += _LAUNCHES_PER_CALL.get(name, 0)
+    return rc
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

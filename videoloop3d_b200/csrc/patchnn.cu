@@ -1,0 +1,423 @@
+// Looping loss for sm_100a: temporal patch nearest-neighbour search, vote/merge, robust loss.
+//
+// Replaces (reference file:line): utils_vid.py:60-69 extract_3Dpatches (unfoldNd im2col),
+// :72-86 efficient_compute_distances (bmm), :109-119 get_col_mins_efficient, :122-142
+// get_NN_indices_low_memory, :206-229 FindNNpatchAndMerge (gather + FoldNd), :289-349 the macro-block
+// loop of Patch3DGPNNLowMemLoss (a memory trick that does not change results), :10-26 robust_lossfun,
+// and MPV.py:499-504 (scale-invariant gain).
+//
+// Search: the unfold -> GEMM pipeline is, per spatial patch position, a frame-pair distance matrix
+// G[tx][ty] = sum over the p x p x 3 window of (x[tx] - y[ty])^2 followed by a pt-long diagonal sum
+// D[i][j] = sum_dt G[i*st+dt][j*st+dt].  One CTA owns one patch position; it streams the window one
+// pixel row (3 channels) at a time through shared memory, every thread keeps a 4x4 (tx,ty) register
+// tile of G, and candidates are consumed in chunks of 64 frames so the GPNN column-min normaliser
+// (min over all queries) and the running first-min argmin never need the whole matrix.
+// Distances are direct fp32 sums of squared differences (no |x|^2+|y|^2-2xy cancellation, no
+// tensor cores): index parity with an fp64 search is limited only by exact near-ties.
+#include "vl3d_common.cuh"
+
+namespace vl3d {
+
+constexpr int NN_THREADS = 256;
+constexpr int NN_CF = 64;      // frames per chunk (both x block and y chunk)
+constexpr int NN_R = 4;        // register tile edge
+constexpr int NN_MAX_N1 = 256;
+
+struct SearchParams {
+    vl3d_loss_desc d;
+    const float* x;
+    const float* xscale;
+    const float* y;
+    int* nn;
+    int groups;     // float4 groups per slab = ceil(3p/4)
+    int row0;       // first patch row handled by this launch
+};
+
+// smem carve-up (floats): xs4[2][groups][64][4], ys4[2][groups][64][4], Gs[64][65], Ds[n1][64],
+// colmin[64], best_val[n1], best_idx[n1]
+__global__ void __launch_bounds__(NN_THREADS) patchnn_search_kernel(const __grid_constant__ SearchParams P) {
+    extern __shared__ __align__(16) float smem[];
+    const vl3d_loss_desc& L = P.d;
+    const int G4 = P.groups;
+    float4* xs4 = reinterpret_cast<float4*>(smem);                  // [2][G4][64]
+    float4* ys4 = xs4 + 2 * G4 * NN_CF;                             // [2][G4][64]
+    float* Gs = reinterpret_cast<float*>(ys4 + 2 * G4 * NN_CF);     // [64][65]
+    float* Ds = Gs + NN_CF * (NN_CF + 1);                           // [n1][64]
+    float* colmin = Ds + (size_t)L.n1 * NN_CF;                      // [64]
+    float* best_val = colmin + NN_CF;                               // [n1]
+    int* best_idx = reinterpret_cast<int*>(best_val + L.n1);        // [n1]
+
+    const int tid = threadIdx.x;
+    const int pxi = blockIdx.x, pyi = P.row0 + blockIdx.y;                   // patch position on the stride-s grid
+    const int x0 = pxi * L.s, y0 = pyi * L.s;
+    const int p = L.p, pt = L.pt, st = L.st;
+    const float xsc = P.xscale ? __ldg(P.xscale) : 1.f;
+    const float inv_d = 1.f / (float)(3 * pt * p * p);              // dist /= d (utils_vid.py:83-84)
+    const int tb = tid & 15, ta = tid >> 4;                         // thread tile: x frames ta+16*i, y frames tb+16*j
+
+    for (int i = tid; i < L.n1; i += NN_THREADS) { best_val[i] = INFINITY; best_idx[i] = 0; }
+
+    const int tx_used = (L.n1 - 1) * st + pt, ty_used = (L.n2 - 1) * st + pt;
+    // candidate chunks: y frames [c0, c0+64); candidates j in [j0, j1) fully inside the chunk
+    for (int j0 = 0; j0 < L.n2;) {
+        const int c0 = j0 * st;
+        int j1 = (c0 + NN_CF - pt) / st + 1;                        // last j with j*st+pt-1 <= c0+63, exclusive
+        if (j1 > L.n2) j1 = L.n2;
+        const int cj = j1 - j0;
+        // query blocks: x frames [a0, a0+64)
+        for (int i0 = 0; i0 < L.n1;) {
+            const int a0 = i0 * st;
+            int i1 = (a0 + NN_CF - pt) / st + 1;
+            if (i1 > L.n1) i1 = L.n1;
+
+            float acc[NN_R][NN_R];
+#pragma unroll
+            for (int i = 0; i < NN_R; ++i)
+#pragma unroll
+                for (int j = 0; j < NN_R; ++j) acc[i][j] = 0.f;
+
+            // stage one slab (pixel row `row` of the window, 3 channels) into buffer `buf`
+            auto stage = [&](int row, int buf) {
+                // rows of p contiguous pixels: id -> (which, channel, frame)
+                for (int id = tid; id < 2 * 3 * NN_CF; id += NN_THREADS) {
+                    const int fr = id & (NN_CF - 1);
+                    const int c = (id >> 6) % 3;
+                    const int which = id / (3 * NN_CF);               // 0: x, 1: y
+                    float* dst = reinterpret_cast<float*>((which ? ys4 : xs4) + (size_t)buf * G4 * NN_CF);
+                    const int gf = (which ? c0 : a0) + fr;            // global frame
+                    const bool ok = gf < (which ? ty_used : tx_used);
+                    const float* src = which ? P.y + (size_t)gf * L.y_sf + (size_t)c * L.y_sc + (size_t)(y0 + row) * L.y_sr + x0
+                                             : P.x + (size_t)gf * L.x_sf + (size_t)c * L.x_sc + (size_t)(y0 + row) * L.x_sr + x0;
+                    const float mul = which ? 1.f : xsc;
+                    for (int dx = 0; dx < p; ++dx) {
+                        const int e = c * p + dx;
+                        const float val = ok ? __ldg(src + dx) * mul : 0.f;
+                        dst[((e >> 2) * NN_CF + fr) * 4 + (e & 3)] = val;
+                    }
+                }
+                // zero the padding lanes of the last float4 group (3p..4*G4)
+                const int npad = 4 * G4 - 3 * p;
+                for (int id = tid; id < 2 * npad * NN_CF; id += NN_THREADS) {
+                    const int fr = id & (NN_CF - 1);
+                    const int e = 3 * p + (id >> 6) % npad;
+                    const int which = id / (npad * NN_CF);
+                    float* dst = reinterpret_cast<float*>((which ? ys4 : xs4) + (size_t)buf * G4 * NN_CF);
+                    dst[((e >> 2) * NN_CF + fr) * 4 + (e & 3)] = 0.f;
+                }
+            };
+
+            __syncthreads();            // previous users of the staging buffers / Gs are done
+            stage(0, 0);
+            __syncthreads();
+            for (int row = 0; row < p; ++row) {
+                const int buf = row & 1;
+                if (row + 1 < p) stage(row + 1, buf ^ 1);
+                const float4* xb = xs4 + (size_t)buf * G4 * NN_CF;
+                const float4* yb = ys4 + (size_t)buf * G4 * NN_CF;
+                for (int g = 0; g < G4; ++g) {
+                    float4 xa[NN_R], ya[NN_R];
+#pragma unroll
+                    for (int i = 0; i < NN_R; ++i) xa[i] = xb[g * NN_CF + ta + 16 * i];
+#pragma unroll
+                    for (int j = 0; j < NN_R; ++j) ya[j] = yb[g * NN_CF + tb + 16 * j];
+#pragma unroll
+                    for (int i = 0; i < NN_R; ++i)
+#pragma unroll
+                        for (int j = 0; j < NN_R; ++j) {
+                            float dlt;
+                            dlt = xa[i].x - ya[j].x; acc[i][j] = fmaf(dlt, dlt, acc[i][j]);
+                            dlt = xa[i].y - ya[j].y; acc[i][j] = fmaf(dlt, dlt, acc[i][j]);
+                            dlt = xa[i].z - ya[j].z; acc[i][j] = fmaf(dlt, dlt, acc[i][j]);
+                            dlt = xa[i].w - ya[j].w; acc[i][j] = fmaf(dlt, dlt, acc[i][j]);
+                        }
+                }
+                __syncthreads();
+            }
+            // G tile -> shared
+#pragma unroll
+            for (int i = 0; i < NN_R; ++i)
+#pragma unroll
+                for (int j = 0; j < NN_R; ++j) Gs[(ta + 16 * i) * (NN_CF + 1) + tb + 16 * j] = acc[i][j];
+            __syncthreads();
+            // D[i][j] = sum_dt G[i*st+dt-a0][j*st+dt-c0] / d      (3-D patch = pt stacked 2-D windows)
+            const int ni = i1 - i0;
+            for (int id = tid; id < ni * cj; id += NN_THREADS) {
+                const int il = id / cj, jl = id - il * cj;
+                const int gx = (i0 + il) * st - a0, gy = (j0 + jl) * st - c0;
+                float sum = 0.f;
+                for (int dt = 0; dt < pt; ++dt) sum += Gs[(gx + dt) * (NN_CF + 1) + gy + dt];
+                Ds[(size_t)(i0 + il) * NN_CF + jl] = sum * inv_d;
+            }
+            i0 = i1;
+        }
+        __syncthreads();
+        // GPNN normaliser: D[i][j] / (alpha + min_i D[i][j])   (utils_vid.py:118,133-141)
+        if (L.use_alpha) {
+            for (int jl = tid; jl < cj; jl += NN_THREADS) {
+                float m = INFINITY;
+                for (int i = 0; i < L.n1; ++i) {
+                    const float vv = Ds[(size_t)i * NN_CF + jl];
+                    m = (vv < m || vv != vv) ? vv : m;               // NaN propagates like torch.min
+                }
+                colmin[jl] = L.alpha + m;
+            }
+            __syncthreads();
+        }
+        // running first-min argmin over candidates (torch.argmin: first minimal index; NaN counts as min)
+        for (int i = tid; i < L.n1; i += NN_THREADS) {
+            float bv = best_val[i];
+            int bi = best_idx[i];
+            for (int jl = 0; jl < cj; ++jl) {
+                float vv = Ds[(size_t)i * NN_CF + jl];
+                if (L.use_alpha) vv = vv / colmin[jl];
+                const bool better = (vv < bv) || (vv != vv && bv == bv);
+                if (better) { bv = vv; bi = j0 + jl; }
+            }
+            best_val[i] = bv; best_idx[i] = bi;
+        }
+        j0 = j1;
+    }
+    __syncthreads();
+    int* out = P.nn + ((size_t)pyi * L.wo + pxi) * L.n1;
+    for (int i = tid; i < L.n1; i += NN_THREADS) out[i] = best_idx[i];
+}
+
+static size_t search_smem_bytes(const vl3d_loss_desc* L) {
+    const int G4 = (3 * L->p + 3) / 4;
+    size_t fl = (size_t)4 * 4 * G4 * NN_CF + (size_t)NN_CF * (NN_CF + 1) + (size_t)L->n1 * NN_CF + NN_CF + 2 * (size_t)L->n1;
+    return fl * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------------
+// vote / merge + robust loss + its derivative: one thread per pixel of the full x buffer.
+//   y2x[c,t',py,px] = mean over covering patches (i,j,k) of y[c, NN_ij[k]*st + t'-k*st, py, px]
+// ------------------------------------------------------------------------------------------------
+struct VoteParams {
+    vl3d_loss_desc d;
+    const float* x; const float* xscale; const float* y; const int* nn;
+    int rou_kind; float rou, scaling, gcoef;
+    int Tx_full, Hfull, Wfull;
+    float* y2x; float* weight; float* grad; double* partials; float* loss;
+};
+
+__device__ __forceinline__ void robust(float r, int kind, float rou, float scale, float& val, float& der) {
+    if (kind == 1) { val = r * r; der = 2.f * r; return; }
+    if (kind == 2) { val = fabsf(r); der = signf(r); return; }
+    const float q = r / scale, sq = q * q;
+    if (rou == 0.f) { val = log1pf(0.5f * sq); der = (q / scale) / (1.f + 0.5f * sq); return; }
+    if (rou == 2.f) { val = 0.5f * sq; der = q / scale; return; }
+    const float b = fabsf(rou - 2.f) + 1e-6f;
+    const float dd = rou >= 0.f ? rou + 1e-6f : rou - 1e-6f;
+    const float base = sq / b + 1.f;
+    val = (b / dd) * (powf(base, 0.5f * dd) - 1.f) * (scale * 10.f);
+    der = 10.f * q * powf(base, 0.5f * dd - 1.f);
+}
+
+constexpr int VOTE_THREADS = 256;
+
+__global__ void __launch_bounds__(VOTE_THREADS) vote_loss_kernel(const __grid_constant__ VoteParams P) {
+    const vl3d_loss_desc& L = P.d;
+    const int px = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int py = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int tf = blockIdx.z;
+    float lsum = 0.f;
+    if (px < P.Wfull && py < P.Hfull) {
+        const bool inside = px < L.w && py < L.h && tf < L.t;
+        float g[3] = {0.f, 0.f, 0.f};
+        if (inside) {
+            const int p = L.p, s = L.s, pt = L.pt, st = L.st;
+            int iy0 = (py - p + s) / s; if (py - p + 1 <= 0) iy0 = 0;         // ceil((py-p+1)/s) clipped at 0
+            int ix0 = (px - p + s) / s; if (px - p + 1 <= 0) ix0 = 0;
+            int k0 = (tf - pt + st) / st; if (tf - pt + 1 <= 0) k0 = 0;
+            const int iy1 = min(py / s, L.ho - 1), ix1 = min(px / s, L.wo - 1), k1 = min(tf / st, L.n1 - 1);
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+            int cnt = 0;
+            const float* yb = P.y + (size_t)py * L.y_sr + px;
+            for (int iy = iy0; iy <= iy1; ++iy)
+                for (int ix = ix0; ix <= ix1; ++ix) {
+                    const int* nnp = P.nn + ((size_t)iy * L.wo + ix) * L.n1;
+                    for (int k = k0; k <= k1; ++k) {
+                        const int fr = __ldg(nnp + k) * st + (tf - k * st);
+                        const float* src = yb + (size_t)fr * L.y_sf;
+                        v0 += __ldg(src); v1 += __ldg(src + L.y_sc); v2 += __ldg(src + 2 * L.y_sc);
+                        ++cnt;
+                    }
+                }
+            const float wgt = fmaxf((float)cnt, 1e-10f);                       // clamp_min(1e-10) (utils_vid.py:228)
+            const float m[3] = {v0 / wgt, v1 / wgt, v2 / wgt};
+            const float xsc = P.xscale ? __ldg(P.xscale) : 1.f;
+            const float n_inv = 1.f / ((float)L.t * (float)L.h * (float)L.w * 3.f);
+            const size_t fit_plane = (size_t)L.h * L.w;
+            const size_t fit_pix = (size_t)py * L.w + px;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float xv = __ldg(P.x + (size_t)tf * L.x_sf + (size_t)c * L.x_sc + (size_t)py * L.x_sr + px) * xsc;
+                float val, der;
+                robust(xv - m[c], P.rou_kind, P.rou, P.scaling, val, der);
+                lsum += val;
+                g[c] = P.gcoef * xsc * der * n_inv;
+                if (P.y2x) P.y2x[((size_t)c * L.t + tf) * fit_plane + fit_pix] = m[c];
+            }
+            if (P.weight) P.weight[(size_t)tf * fit_plane + fit_pix] = wgt;
+        }
+        if (P.grad && tf < P.Tx_full) {
+            const size_t plane = (size_t)P.Hfull * P.Wfull;
+            float* gp = P.grad + (size_t)tf * 3 * plane + (size_t)py * P.Wfull + px;
+            gp[0] = g[0]; gp[plane] = g[1]; gp[2 * plane] = g[2];
+        }
+    }
+    __shared__ float s_part[VOTE_THREADS / 32];
+    lsum = warp_sum(lsum);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < VOTE_THREADS / 32; ++i) acc += (double)s_part[i];
+        P.partials[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(1024) finalize_mean_kernel(const double* partials, int n, double denom, float* out) {
+    __shared__ double s[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.0;
+        acc = warp_sum(acc);
+        if (threadIdx.x == 0) out[0] = (float)(acc / denom);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scale-invariant gain (MPV.py:499-504)
+// ------------------------------------------------------------------------------------------------
+constexpr int SCALE_BLOCKS = 1184;   // 8 x 148 SMs
+constexpr int SCALE_THREADS = 256;
+
+__global__ void __launch_bounds__(SCALE_THREADS) scale_partial_kernel(const float* __restrict__ rgb, int T,
+                                                                       const float* __restrict__ res, int F,
+                                                                       size_t chw, double* partials) {
+    float acc = 0.f;
+    for (size_t i = (size_t)blockIdx.x * SCALE_THREADS + threadIdx.x; i < chw; i += (size_t)gridDim.x * SCALE_THREADS) {
+        float sr = 0.f, sx = 0.f;
+        for (int f = 0; f < F; ++f) sr += __ldg(res + (size_t)f * chw + i);
+        for (int t = 0; t < T; ++t) sx += __ldg(rgb + (size_t)t * chw + i);
+        acc += __logf((sr / (float)F + 0.01f) / (sx / (float)T + 0.01f));
+    }
+    __shared__ float s_part[SCALE_THREADS / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < SCALE_THREADS / 32; ++i) a += (double)s_part[i];
+        partials[blockIdx.x] = a;
+    }
+}
+
+__global__ void __launch_bounds__(1024) scale_finalize_kernel(const double* partials, int n, double denom, float* out) {
+    __shared__ double s[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.0;
+        acc = warp_sum(acc);
+        if (threadIdx.x == 0) out[0] = ((float)exp(acc / denom) + 3.f) / 4.f;
+    }
+}
+
+static int validate_desc(const vl3d_loss_desc* L) {
+    VL3D_REQUIRE(L != nullptr, VL3D_ENULL, "loss desc is NULL");
+    VL3D_REQUIRE(L->p >= 1 && L->pt >= 1 && L->s >= 1 && L->st >= 1, VL3D_EINVAL, "bad patch config");
+    VL3D_REQUIRE(L->n1 >= 1 && L->n2 >= 1 && L->ho >= 1 && L->wo >= 1, VL3D_EINVAL, "empty problem");
+    VL3D_REQUIRE((L->n1 - 1) * L->st + L->pt <= L->t && (L->n2 - 1) * L->st + L->pt <= L->F, VL3D_EINVAL,
+                 "n1/n2 exceed the frame counts");
+    VL3D_REQUIRE((L->ho - 1) * L->s + L->p <= L->h && (L->wo - 1) * L->s + L->p <= L->w, VL3D_EINVAL,
+                 "patch grid exceeds the crop");
+    VL3D_REQUIRE(L->pt <= NN_CF / 2, VL3D_ERANGE, "patcht_size %d too large (max %d)", L->pt, NN_CF / 2);
+    VL3D_REQUIRE(L->n1 <= NN_MAX_N1, VL3D_ERANGE, "n1=%d too large (max %d)", L->n1, NN_MAX_N1);
+    return 0;
+}
+
+}  // namespace vl3d
+
+using namespace vl3d;
+
+extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, const float* xscale, const float* y,
+                                   int32_t row_begin, int32_t row_end, int32_t* nn_out, void* stream) {
+    if (int e = validate_desc(desc)) return e;
+    VL3D_REQUIRE(row_begin >= 0 && row_end <= desc->ho && row_begin <= row_end, VL3D_EINVAL, "bad row range [%d,%d)",
+                 row_begin, row_end);
+    if (row_begin == row_end) return 0;
+    VL3D_REQUIRE(x && y && nn_out, VL3D_ENULL, "x / y / nn_out is NULL");
+    const size_t smem = search_smem_bytes(desc);
+    VL3D_REQUIRE(smem <= 200 * 1024, VL3D_ERANGE, "patch_size %d / n1 %d need %zu B of shared memory", desc->p, desc->n1, smem);
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t ce = cudaFuncSetAttribute(patchnn_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce != cudaSuccess) return set_err((int)ce, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
+        configured = smem;
+    }
+    SearchParams P{};
+    P.d = *desc; P.x = x; P.xscale = xscale; P.y = y; P.nn = nn_out; P.groups = (3 * desc->p + 3) / 4;
+    P.row0 = row_begin;
+    dim3 grid(desc->wo, row_end - row_begin);
+    patchnn_search_kernel<<<grid, NN_THREADS, smem, (cudaStream_t)stream>>>(P);
+    return check_launch("patchnn_search");
+}
+
+static dim3 vote_grid(const vl3d_loss_desc* L, int Tx_full, int Hfull, int Wfull) {
+    return dim3((Wfull + 31) / 32, (Hfull + 7) / 8, Tx_full);
+}
+
+extern "C" int vl3d_vote_partials(int32_t Tx_full, int32_t Hfull, int32_t Wfull) {
+    if (Tx_full < 1 || Hfull < 1 || Wfull < 1) return 0;
+    return ((Wfull + 31) / 32) * ((Hfull + 7) / 8) * Tx_full;
+}
+
+extern "C" int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const float* xscale, const float* y,
+                              const int32_t* nn, int32_t rou_kind, float rou, float scaling, float gcoef,
+                              int32_t Tx_full, int32_t Hfull, int32_t Wfull, float* y2x_out, float* weight_out,
+                              float* grad_out, double* partials, float* loss_out, void* stream) {
+    if (int e = validate_desc(desc)) return e;
+    VL3D_REQUIRE(x && y && nn && partials && loss_out, VL3D_ENULL, "required pointer is NULL");
+    VL3D_REQUIRE(Tx_full >= desc->t && Hfull >= desc->h && Wfull >= desc->w, VL3D_EINVAL, "full dims smaller than the crop");
+    VL3D_REQUIRE(rou_kind >= 0 && rou_kind <= 2, VL3D_EINVAL, "rou_kind %d", rou_kind);
+    dim3 grid = vote_grid(desc, Tx_full, Hfull, Wfull);
+    const int nblocks = grid.x * grid.y * grid.z;
+    VoteParams P{};
+    P.d = *desc; P.x = x; P.xscale = xscale; P.y = y; P.nn = nn;
+    P.rou_kind = rou_kind; P.rou = rou; P.scaling = scaling; P.gcoef = gcoef;
+    P.Tx_full = Tx_full; P.Hfull = Hfull; P.Wfull = Wfull;
+    P.y2x = y2x_out; P.weight = weight_out; P.grad = grad_out; P.partials = partials; P.loss = loss_out;
+    cudaStream_t st = (cudaStream_t)stream;
+    vote_loss_kernel<<<grid, VOTE_THREADS, 0, st>>>(P);
+    if (int e = check_launch("vote_loss")) return e;
+    const double denom = (double)desc->t * desc->h * desc->w * 3.0;
+    finalize_mean_kernel<<<1, 1024, 0, st>>>(partials, nblocks, denom, loss_out);
+    return check_launch("vote_finalize");
+}
+
+extern "C" int vl3d_scale_partials(void) { return SCALE_BLOCKS; }
+
+extern "C" int vl3d_scale_invariant(const float* rgb, int32_t T, const float* res, int32_t F, int32_t H, int32_t W,
+                                    double* partials, float* out, void* stream) {
+    VL3D_REQUIRE(rgb && res && partials && out, VL3D_ENULL, "required pointer is NULL");
+    VL3D_REQUIRE(T >= 1 && F >= 1 && H >= 1 && W >= 1, VL3D_EINVAL, "bad sizes");
+    const size_t chw = (size_t)3 * H * W;
+    int blocks = (int)((chw + SCALE_THREADS - 1) / SCALE_THREADS);
+    if (blocks > SCALE_BLOCKS) blocks = SCALE_BLOCKS;
+    cudaStream_t st = (cudaStream_t)stream;
+    scale_partial_kernel<<<blocks, SCALE_THREADS, 0, st>>>(rgb, T, res, F, chw, partials);
+    if (int e = check_launch("scale_partial")) return e;
+    scale_finalize_kernel<<<1, 1024, 0, st>>>(partials, blocks, (double)chw, out);
+    return check_launch("scale_finalize");
+}

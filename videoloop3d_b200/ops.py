@@ -1,0 +1,237 @@
+"""Thin torch-facing wrappers over the C ABI (include/vl3d.h) + the autograd Functions built on them.
+
+PyTorch is only plumbing here: device memory, the current stream and autograd bookkeeping.  Every
+numerical operation of the hot path runs inside libvl3d.so; nothing falls back to eager PyTorch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import tiles
+
+
+def _require_cuda(t, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise _lib.Vl3dError(f"{name} must be a CUDA tensor: the vl3d hot path has no CPU implementation")
+    if t.dtype != torch.float32 and t.dtype not in (torch.int32, torch.float64):
+        raise _lib.Vl3dError(f"{name}: unsupported dtype {t.dtype} (the reference's fp16 flag is 'do NOT use')")
+
+
+def as_texels(atlas):
+    """(B,4,H,W) logical tensor whose memory is RGBA-interleaved (channels_last).  Returns the tensor
+    itself when it already is, else a converted copy (the caller should then re-home the parameter)."""
+    if atlas.dim() != 4 or atlas.shape[1] != 4:
+        raise _lib.Vl3dError(f"atlas must be (B,4,H,W), got {tuple(atlas.shape)} (atlas_cnl must be 4, rgb_mlp_type=direct)")
+    b, c, h, w = atlas.shape
+    want = (h * w * 4, 1, w * 4, 4)
+    if tuple(atlas.stride()) == want:
+        return atlas
+    out = torch.empty_strided((b, c, h, w), want, dtype=atlas.dtype, device=atlas.device)
+    out.copy_(atlas)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# view pack
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class MeshPack:
+    """Device-resident quad table + per-plane vertex grids (rebuilt on lod()/load only)."""
+    quads: torch.Tensor          # uint8 view of the vl3d_quad array, on device
+    grids: np.ndarray            # (D,5) X0,Y0,dX,dY,z (float64, host)
+    D: int
+    qh: int
+    qw: int
+    n_static: int
+    n_dynamic: int
+
+
+def make_mesh_pack(model_tensors, D, hv, wv, device):
+    t = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in model_tensors.items()}
+    grids = tiles.plane_grids(t["verts"], D, hv, wv)
+    table = tiles.build_quad_table(D, hv, wv, t["faces"], t["uvs"], t["uvfaces"], t["atlas_hw"],
+                                   t["faces_dyn"], t["uvs_dyn"], t["uvfaces_dyn"], t["atlas_dyn_hw"])
+    q = torch.from_numpy(table.view(np.uint8).copy()).to(device)
+    return MeshPack(quads=q, grids=grids, D=D, qh=hv - 1, qw=wv - 1,
+                    n_static=int((table["kind"] == 1).sum()), n_dynamic=int((table["kind"] == 2).sum()))
+
+
+def make_view(pack: MeshPack, H, W, tar_extrin, tar_intrin, ref_extrin, dyn_hw, sta_hw):
+    """Host-side vl3d_view for one target camera (float64 maths, see tiles.view_homographies)."""
+    to_np = lambda a: a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    homs, cx, cy = tiles.view_homographies(pack.grids, pack.qh, pack.qw, to_np(tar_extrin), to_np(tar_intrin),
+                                           to_np(ref_extrin), H, W)
+    v = _lib.View()
+    v.H, v.W, v.D, v.qh, v.qw = int(H), int(W), pack.D, pack.qh, pack.qw
+    v.dyn_h, v.dyn_w = int(dyn_hw[0]), int(dyn_hw[1])
+    v.sta_h, v.sta_w = int(sta_hw[0]), int(sta_hw[1])
+    v.cx, v.cy = cx, cy
+    flat = homs.reshape(-1)
+    C.memmove(v.hom, flat.ctypes.data, flat.nbytes)
+    return v
+
+
+# ------------------------------------------------------------------------------------------------
+# raw launches
+# ------------------------------------------------------------------------------------------------
+def composite_fwd(view, pack, atlas_dyn, atlas_sta, ts, T, pad, rgb_out=None, want_alpha=False, smooth_sums=None,
+                  want_mpi=False, want_hits=False):
+    dev = atlas_dyn.device
+    _require_cuda(atlas_dyn, "atlas_dyn"); _require_cuda(atlas_sta, "atlas")
+    H, W = view.H, view.W
+    if rgb_out is None:
+        rgb_out = torch.empty((T + pad, 3, H, W), dtype=torch.float32, device=dev)
+    alpha = torch.empty((T, H, W), dtype=torch.float32, device=dev) if want_alpha else None
+    mpi = torch.zeros((T, H, W, view.D, 4), dtype=torch.float32, device=dev) if want_mpi else None
+    hits = torch.zeros((H, W), dtype=torch.int32, device=dev) if want_hits else None
+    _lib.call("vl3d_composite_fwd", C.byref(view), _lib.ptr(pack.quads), _lib.ptr(atlas_dyn), _lib.ptr(atlas_sta),
+              _lib.ptr(ts), int(T), int(pad), _lib.ptr(rgb_out), _lib.ptr(alpha), _lib.ptr(smooth_sums),
+              _lib.ptr(mpi), _lib.ptr(hits), _lib.stream_ptr())
+    return rgb_out, alpha, mpi, hits
+
+
+def composite_bwd(view, pack, atlas_dyn, atlas_sta, ts, T, pad, grad_rgb, rgb, w_smooth, grad_dyn, grad_sta):
+    _lib.call("vl3d_composite_bwd", C.byref(view), _lib.ptr(pack.quads), _lib.ptr(atlas_dyn), _lib.ptr(atlas_sta),
+              _lib.ptr(ts), int(T), int(pad), _lib.ptr(grad_rgb), _lib.ptr(rgb), _lib.ptr(w_smooth),
+              _lib.ptr(grad_dyn), _lib.ptr(grad_sta), _lib.stream_ptr())
+
+
+def scale_invariant(rgb, T, res, out=None, partials=None):
+    """MPV.py:499-504 on device: rgb (>=T,3,H,W) contiguous, res (F,3,H,W) contiguous -> (1,) float."""
+    _require_cuda(rgb, "rgb"); _require_cuda(res, "res")
+    F_, _, H, W = res.shape
+    if not res.is_contiguous():
+        res = res.contiguous()
+    assert rgb.is_contiguous() and tuple(rgb.shape[1:]) == (3, H, W)
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device=rgb.device)
+    if partials is None:
+        partials = torch.empty(_lib.load().vl3d_scale_partials(), dtype=torch.float64, device=rgb.device)
+    _lib.call("vl3d_scale_invariant", _lib.ptr(rgb), int(T), _lib.ptr(res), int(F_), int(H), int(W),
+              _lib.ptr(partials), _lib.ptr(out), _lib.stream_ptr())
+    return out
+
+
+def _fit(size, p, st, name):
+    """fit_patch of utils_vid.py:307-313."""
+    if size < p:
+        raise ValueError(f"{name}={size} is smaller than the patch size {p}")
+    return (size - p) // st * st + p if (size - p) % st != 0 else size
+
+
+def make_loss_desc(x_tchw_shape, x_strides, y_fchw_shape, y_strides, patch_size, patcht_size, stride, stridet, alpha,
+                   fit=True):
+    """vl3d_loss_desc for x (t,3,h,w)-indexed and y (F,3,h,w)-indexed planar videos.
+    strides: (frame, channel, row) element strides; the pixel stride must be 1."""
+    p, pt, s, st = int(patch_size), int(patcht_size), int(stride), int(stridet)
+    tx, _, h, w = x_tchw_shape
+    F_ = y_fchw_shape[0]
+    d = _lib.LossDesc()
+    if fit:
+        d.t, d.h, d.w = _fit(tx, pt, st, "frame_num"), _fit(h, p, s, "patch_height"), _fit(w, p, s, "patch_width")
+    else:                                            # Patch3DGPNNDirectLoss: unfold's floor semantics
+        if tx < pt or h < p or w < p:
+            raise ValueError("video smaller than the patch")
+        d.t, d.h, d.w = int(tx), int(h), int(w)
+    d.F = int(F_)
+    if F_ < pt:
+        raise ValueError(f"target video has {F_} frames < patcht_size {pt}")
+    d.p, d.pt, d.s, d.st = p, pt, s, st
+    d.n1, d.n2 = (d.t - pt) // st + 1, (F_ - pt) // st + 1
+    d.ho, d.wo = (d.h - p) // s + 1, (d.w - p) // s + 1
+    d.x_sf, d.x_sc, d.x_sr = (int(v) for v in x_strides)
+    d.y_sf, d.y_sc, d.y_sr = (int(v) for v in y_strides)
+    alpha = float(alpha)
+    d.use_alpha = 0 if alpha > 100 else 1            # utils_vid.py:208
+    d.alpha = 0.0 if alpha > 100 else alpha
+    return d
+
+
+def patchnn_search(desc, x, xscale, y, nn_out=None, rows=None):
+    if nn_out is None:
+        nn_out = torch.empty((desc.ho, desc.wo, desc.n1), dtype=torch.int32, device=x.device)
+    r0, r1 = (0, desc.ho) if rows is None else rows
+    _lib.call("vl3d_patchnn_search", C.byref(desc), _lib.ptr(x), _lib.ptr(xscale), _lib.ptr(y), int(r0), int(r1),
+              _lib.ptr(nn_out), _lib.stream_ptr())
+    return nn_out
+
+
+def parse_rou(rou):
+    """robust_lossfun's rou (utils_vid.py:10-16) arrives as str from the config."""
+    if rou == "mse":
+        return 1, 0.0
+    if rou == "abs":
+        return 2, 0.0
+    return 0, float(rou)
+
+
+def vote_loss(desc, x, xscale, y, nn, rou, scaling, gcoef, full_shape, want_cache=False, grad_out=None,
+              want_grad=True, partials=None, loss_out=None):
+    Tx, Hf, Wf = full_shape
+    dev = x.device
+    kind, rouf = parse_rou(rou)
+    y2x = torch.empty((1, 3, desc.t, desc.h, desc.w), dtype=torch.float32, device=dev) if want_cache else None
+    wgt = torch.empty((1, 1, desc.t, desc.h, desc.w), dtype=torch.float32, device=dev) if want_cache else None
+    if want_grad and grad_out is None:
+        grad_out = torch.empty((Tx, 3, Hf, Wf), dtype=torch.float32, device=dev)
+    n_part = _lib.load().vl3d_vote_partials(int(Tx), int(Hf), int(Wf))
+    if partials is None or partials.numel() < n_part:
+        partials = torch.empty(n_part, dtype=torch.float64, device=dev)
+    if loss_out is None:
+        loss_out = torch.empty(1, dtype=torch.float32, device=dev)
+    _lib.call("vl3d_vote_loss", C.byref(desc), _lib.ptr(x), _lib.ptr(xscale), _lib.ptr(y), _lib.ptr(nn),
+              int(kind), float(rouf), float(scaling), float(gcoef), int(Tx), int(Hf), int(Wf),
+              _lib.ptr(y2x), _lib.ptr(wgt), _lib.ptr(grad_out if want_grad else None), _lib.ptr(partials),
+              _lib.ptr(loss_out), _lib.stream_ptr())
+    return loss_out, grad_out, y2x, wgt
+
+
+def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=6e-8):
+    """In-place Adam on tensors that share one dense memory layout (MPV.py:213)."""
+    for t in (g, m, v):
+        if tuple(t.stride()) != tuple(p.stride()) or t.shape != p.shape:
+            raise _lib.Vl3dError("adam_step: p, g, m, v must share shape and strides")
+    _lib.call("vl3d_adam_step", _lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), int(p.numel()), int(step),
+              float(lr), float(beta1), float(beta2), float(eps), _lib.stream_ptr())
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd Functions (the reference-compatible path: loss.backward(); optimizer.step())
+# ------------------------------------------------------------------------------------------------
+class CompositeFn(torch.autograd.Function):
+    """rgb_pad (T+pad,3,H,W), alpha (T,H,W), smooth_sums (4,) float64 = f(atlas_dyn, atlas)."""
+
+    @staticmethod
+    def forward(ctx, atlas_dyn, atlas_sta, view, pack, ts, T, pad, smooth):
+        ctx.set_materialize_grads(False)
+        sums = torch.zeros(4, dtype=torch.float64, device=atlas_dyn.device) if smooth else None
+        rgb, alpha, _, _ = composite_fwd(view, pack, atlas_dyn, atlas_sta, ts, T, pad, want_alpha=True,
+                                         smooth_sums=sums)
+        ctx.save_for_backward(atlas_dyn, atlas_sta, rgb, ts)
+        ctx.view, ctx.pack, ctx.T, ctx.pad, ctx.smooth = view, pack, T, pad, smooth
+        if sums is None:
+            sums = torch.zeros(4, dtype=torch.float64, device=atlas_dyn.device)
+        ctx.mark_non_differentiable(alpha)
+        return rgb, alpha, sums
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_alpha, g_sums):
+        atlas_dyn, atlas_sta, rgb, ts = ctx.saved_tensors
+        if g_rgb is None:
+            g_rgb = torch.zeros_like(rgb)
+        if not g_rgb.is_contiguous():
+            g_rgb = g_rgb.contiguous()
+        w = None
+        if ctx.smooth and g_sums is not None:
+            w = g_sums.to(torch.float32).contiguous()
+        grad_dyn = torch.zeros_like(atlas_dyn)     # preserves the channels_last texel layout
+        grad_sta = torch.zeros_like(atlas_sta)
+        composite_bwd(ctx.view, ctx.pack, atlas_dyn, atlas_sta, ts, ctx.T, ctx.pad, g_rgb, rgb, w, grad_dyn, grad_sta)
+        return grad_dyn, grad_sta, None, None, None, None, None, None

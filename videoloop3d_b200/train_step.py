@@ -1,0 +1,268 @@
+"""The stage-2 optimisation step (reference: train_3dvid.py:214-255 `run_iter`).
+
+Two front ends over the same kernels:
+
+* `make_run_iter(args, nerf, device)` — reference-shaped closure `run_iter(stepi, optimizer_, datainfo_)`
+  that goes through `nerf(...)`, autograd and `optimizer_.step()` exactly like the reference loop, so
+  the surrounding `train()` code can stay as it is.
+* `FusedLoopStep` — the same step without autograd bookkeeping: persistent buffers, no host
+  synchronisation, one stream; optionally T-sharded over `torch.distributed` ranks
+  (SURVEY.md §8(e)): every rank renders / back-propagates / optimises its own contiguous block of
+  frames, rendered frames are all-gathered (NCCL) for the temporal patches, static-tile gradients are
+  all-reduced.  This is what bench.py times.
+"""
+from __future__ import annotations
+
+from argparse import Namespace
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import Vl3dError
+from .loop_loss import Patch3DGPNNDirectLoss, Patch3DGPNNLowMemLoss
+from .mpv import MPMeshVid, pose2extrin_torch
+
+
+def default_args(**overrides):
+    """Namespace with the flags the hot path reads; defaults = config_parser.py defaults overlaid with
+    configs/mpv_base.txt (the config every shipped stage-2 scene uses)."""
+    a = dict(
+        mpv_frm_num=50, mpv_isloop=True, init_std=0.02, mpi_h_scale=1.1, mpi_w_scale=1.1, mpi_h_verts=27,
+        mpi_w_verts=48, mpi_d=32, atlas_grid_h=4, atlas_size_scale=1, atlas_cnl=4, normalize_verts=False, fp16=False,
+        rgb_mlp_type="direct", rgb_activate="sigmoid", alpha_activate="sigmoid", bg_color="",
+        scale_invariant=True, add_intrin_noise=True, add_uv_noise=False,
+        sparsity_loss_weight=0.0, rgb_smooth_loss_weight=0.2, a_smooth_loss_weight=0.2, density_loss_weight=0.0,
+        d_smooth_loss_weight=0.0, l_smooth_loss_weight=0.0,
+        optimizer="adam", lrate=0.5, lrate_decay=100, lrate_adaptive=True, optimize_verts_gain=1.0,
+        optimize_geo_start=10000000,
+        swd_macro_block=65, swd_loss_gain_ref=3.5, loss_name_ref="gpnn_lm", swd_alpha_ref=0.0, swd_patch_size_ref=11,
+        swd_patcht_size_ref=3, swd_stride_ref=4, swd_stridet_ref=1, swd_dist_fn_ref="mse", swd_rou_ref="-2",
+        swd_scaling_ref=0.1, swd_factor_ref=1,
+        loss_name="gpnn_lm", swd_alpha=10000.0, swd_patch_size=3, swd_patcht_size=3, swd_stride=2, swd_stridet=1,
+        swd_dist_fn="mse", swd_rou="-2", swd_scaling=0.1, swd_factor=1,
+        patch_h_size=180, patch_w_size=320, patch_h_stride=90, patch_w_stride=160, i_img=20, i_print=10, gpu_num=1,
+    )
+    a.update(overrides)
+    return Namespace(**a)
+
+
+def loss_config(args, ref_view: bool):
+    """The two per-view loss configs built in train_3dvid.py:163-190."""
+    if ref_view:
+        return dict(loss_name=args.loss_name_ref, loss_gain=args.swd_loss_gain_ref, patch_size=args.swd_patch_size_ref,
+                    patcht_size=args.swd_patcht_size_ref, stride=args.swd_stride_ref, stridet=args.swd_stridet_ref,
+                    alpha=args.swd_alpha_ref, rou=args.swd_rou_ref, scaling=args.swd_scaling_ref,
+                    dist_fn=args.swd_dist_fn_ref, macro_block=args.swd_macro_block, factor=args.swd_factor_ref)
+    return dict(loss_name=args.loss_name, patch_size=args.swd_patch_size, patcht_size=args.swd_patcht_size,
+                stride=args.swd_stride, stridet=args.swd_stridet, alpha=args.swd_alpha, rou=args.swd_rou,
+                scaling=args.swd_scaling, dist_fn=args.swd_dist_fn, macro_block=args.swd_macro_block,
+                factor=args.swd_factor)
+
+
+def make_run_iter(args, nerf, device, writer=None, on_log=None):
+    """Reference-shaped `run_iter(stepi, optimizer_, datainfo_)` (train_3dvid.py:214-255).
+    `nerf` is the (DataParallel-like) wrapper or the bare module."""
+
+    def run_iter(stepi, optimizer_, datainfo_):
+        datainfo_ = [d.to(device) if torch.is_tensor(d) else d for d in datainfo_]
+        h_starts, w_starts, b_pose, b_intrin, b_rgbs, loss_cfg = datainfo_
+        b_extrin = pose2extrin_torch(b_pose)
+        patch_h, patch_w = b_rgbs.shape[-2:]
+        if args.add_intrin_noise:
+            dxy = torch.rand(2).type_as(b_intrin) - 0.5          # half pixel (train_3dvid.py:222-225)
+            b_intrin = b_intrin.clone()
+            b_intrin[:, :2, 2] += dxy
+        nerf.train()
+        rgb, extra = nerf(patch_h, patch_w, b_extrin, b_intrin, res=b_rgbs, losscfg=loss_cfg)
+        swd_loss = extra.pop("swd").mean()
+        args_var = vars(args)
+        extra_losses = {k: v.mean() * args_var[f"{k}_loss_weight"] for k, v in extra.items()
+                        if args_var[f"{k}_loss_weight"] > 0}
+        loss = swd_loss
+        for v in extra_losses.values():
+            loss = loss + v
+        optimizer_.zero_grad()
+        loss.backward()
+        optimizer_.step()
+        if on_log is not None:
+            on_log(stepi, loss, swd_loss, extra_losses)
+        return loss.detach()
+
+    return run_iter
+
+
+class FusedLoopStep:
+    """render + looping loss + backward + Adam for one (view, patch) item, fused and sync-free.
+
+    step(h, w, tar_extrin (1,4,4), tar_intrin (1,3,3), res (1,F,3,h,w) on device, losscfg (un-batched dict), lr)
+    returns a dict of device scalars {'loss','swd','rgb_smooth','a_smooth'} (no host sync).
+
+    With `group` (a torch.distributed process group, world size G) the T frames are sharded in
+    contiguous blocks: this rank owns frames [t0, t1) of `atlas_dyn` (parameters, gradients and Adam
+    state of other frames are never touched here).
+    """
+
+    def __init__(self, model: MPMeshVid, group=None, betas=(0.9, 0.999), eps=6e-8):
+        if not model.atlas_dyn.is_cuda:
+            raise Vl3dError("FusedLoopStep needs the model on a CUDA device")
+        self.model = model
+        self.group = group
+        self.betas, self.eps = betas, eps
+        self.t = 0                       # Adam step counter (fresh optimiser per pyramid level: call reset())
+        self._buf = {}
+        self._state = {}
+        self.world, self.rank = 1, 0
+        if group is not None:
+            import torch.distributed as dist
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        T = model.atlas_dyn.shape[0]
+        self.T = T
+        bounds = [(T * r) // self.world for r in range(self.world + 1)]
+        self.bounds = bounds
+        self.t0, self.t1 = bounds[self.rank], bounds[self.rank + 1]
+        if self.t1 <= self.t0:
+            raise Vl3dError(f"rank {self.rank} owns no frames (T={T}, world={self.world})")
+
+    def reset(self):
+        """Fresh optimiser state (the reference builds a new Adam per pyramid level, train_3dvid.py:265)."""
+        self.t = 0
+        self._state = {}
+
+    def _get(self, key, shape, dtype, zero=False):
+        b = self._buf.get(key)
+        if b is None or tuple(b.shape) != tuple(shape) or b.dtype != dtype:
+            b = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.model.atlas_dyn.device)
+            self._buf[key] = b
+        return b
+
+    def _adam(self, name, p, g, lr):
+        st = self._state.get(name)
+        if st is None:
+            st = (torch.zeros_like(p), torch.zeros_like(p))
+            self._state[name] = st
+        ops.adam_step(p, g, st[0], st[1], self.t, lr, self.betas[0], self.betas[1], self.eps)
+
+    @torch.no_grad()
+    def step(self, h, w, tar_extrin, tar_intrin, res, losscfg, lr, optimise=True):
+        m = self.model
+        args = m.args
+        dev = m.atlas_dyn.device
+        atlas_dyn, atlas = m._texels()
+        cfg = dict(losscfg)
+        loss_name = cfg.pop("loss_name")
+        gain = float(cfg.pop("loss_gain", 1.0))
+        lossobj = m.losses[loss_name]
+        if not isinstance(lossobj, (Patch3DGPNNLowMemLoss, Patch3DGPNNDirectLoss)):
+            raise NotImplementedError(f"FusedLoopStep supports the gpnn / gpnn_lm losses, not {loss_name!r}")
+        T, t0, t1 = self.T, self.t0, self.t1
+        Tl = t1 - t0
+        pad = m.swd_patcht_size - 1 if m.isloop else 0
+        res0 = res[0] if res.dim() == 5 else res
+        if not res0.is_contiguous():
+            res0 = res0.contiguous()
+        ext = tar_extrin.reshape(4, 4).double().cpu().numpy() @ np.linalg.inv(m.ref_extrin.double().cpu().numpy())
+        view = m.make_view(h, w, ext, tar_intrin)
+        pack = m._pack
+        smooth = args.rgb_smooth_loss_weight > 0 or args.a_smooth_loss_weight > 0
+
+        rgb_pad = self._get("rgb_pad", (T + pad, 3, h, w), torch.float32)
+        sums = self._get("sums", (4,), torch.float64)
+        sums.zero_()
+        dyn_local = atlas_dyn.data[t0:t1]
+        if self.world == 1:
+            ops.composite_fwd(view, pack, dyn_local, atlas.data, None, T, pad, rgb_out=rgb_pad,
+                              smooth_sums=sums if smooth else None)
+        else:
+            import torch.distributed as dist
+            # render the owned frames straight into their slot of the gathered video, then all-gather
+            ops.composite_fwd(view, pack, dyn_local, atlas.data, None, Tl, 0, rgb_out=rgb_pad[t0:t1],
+                              smooth_sums=sums if smooth else None)
+            if len(set(b - a for a, b in zip(self.bounds[:-1], self.bounds[1:]))) == 1:
+                dist.all_gather_into_tensor(rgb_pad[:T], rgb_pad[t0:t1], group=self.group)
+            else:
+                parts = [rgb_pad[a:b] for a, b in zip(self.bounds[:-1], self.bounds[1:])]
+                dist.all_gather(parts, rgb_pad[t0:t1].clone(), group=self.group)
+            if pad:
+                rgb_pad[T:T + pad].copy_(rgb_pad[:pad])                      # loop pad (MPV.py:490-492)
+            if smooth:
+                dist.all_reduce(sums, group=self.group)
+
+        xscale = None
+        if args.scale_invariant:
+            xscale = ops.scale_invariant(rgb_pad, T, res0, out=self._get("xscale", (1,), torch.float32),
+                                         partials=self._get("scale_part", (ops._lib.load().vl3d_scale_partials(),),
+                                                            torch.float64))
+        desc = ops.make_loss_desc(rgb_pad.shape, (rgb_pad.stride(0), rgb_pad.stride(1), rgb_pad.stride(2)), res0.shape,
+                                  (res0.stride(0), res0.stride(1), res0.stride(2)), cfg["patch_size"],
+                                  cfg["patcht_size"], cfg["stride"], cfg["stridet"], cfg.get("alpha", 1e10),
+                                  fit=lossobj.fit)
+        nn = self._get("nn", (desc.ho, desc.wo, desc.n1), torch.int32)
+        if self.world == 1:
+            ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn)
+        else:
+            import torch.distributed as dist
+            # patch positions are independent (utils_vid.py:211-215): each rank searches a band of patch
+            # rows, then the int32 index map is summed across ranks (disjoint rows, zeros elsewhere)
+            r0, r1 = (desc.ho * self.rank) // self.world, (desc.ho * (self.rank + 1)) // self.world
+            nn.zero_()
+            ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn, rows=(r0, r1))
+            dist.all_reduce(nn, group=self.group)
+        grad_rgb = self._get("grad_rgb", (T + pad, 3, h, w), torch.float32)
+        n_part = ops._lib.load().vl3d_vote_partials(T + pad, h, w)
+        loss_out, _, _, _ = ops.vote_loss(desc, rgb_pad, xscale, res0, nn, cfg.get("rou", 0), cfg.get("scaling", 0.2),
+                                          gain, (T + pad, h, w), grad_out=grad_rgb,
+                                          partials=self._get("vote_part", (n_part,), torch.float64),
+                                          loss_out=self._get("loss_out", (1,), torch.float32))
+        # d total / d smooth_sums (host constants): MPV.py:517-531 with K cancelled, train_3dvid.py:230-240
+        w_smooth = None
+        nx = max(T * h * (w - 1), 1) * m.mpi_d
+        ny = max(T * (h - 1) * w, 1) * m.mpi_d
+        wr, wa = args.rgb_smooth_loss_weight, args.a_smooth_loss_weight
+        if smooth:
+            key = ("w_smooth", T, h, w, gain, wr, wa)
+            w_smooth = self._buf.get(key)
+            if w_smooth is None:
+                w_smooth = torch.tensor([wr * gain / (3 * nx), wr * gain / (3 * ny), wa * gain / nx, wa * gain / ny],
+                                        dtype=torch.float32, device=dev)
+                self._buf[key] = w_smooth
+
+        out = {"swd": loss_out[0] * gain}
+        total = out["swd"]
+        if wr > 0:
+            out["rgb_smooth"] = ((sums[0] / (3 * nx) + sums[1] / (3 * ny)) * gain).float()
+            total = total + out["rgb_smooth"] * wr
+        if wa > 0:
+            out["a_smooth"] = ((sums[2] / nx + sums[3] / ny) * gain).float()
+            total = total + out["a_smooth"] * wa
+        out["loss"] = total
+        if not optimise:
+            return out
+
+        # backward into persistent gradient buffers
+        g_dyn = self._get("g_dyn", tuple(dyn_local.shape), torch.float32)
+        if tuple(g_dyn.stride()) != tuple(dyn_local.stride()):
+            g_dyn = torch.empty_like(dyn_local)
+            self._buf["g_dyn"] = g_dyn
+        g_sta = self._buf.get("g_sta")
+        if g_sta is None or g_sta.shape != atlas.shape or tuple(g_sta.stride()) != tuple(atlas.stride()):
+            g_sta = torch.empty_like(atlas.data)
+            self._buf["g_sta"] = g_sta
+        g_dyn.zero_()
+        g_sta.zero_()
+        if self.world == 1:
+            ops.composite_bwd(view, pack, dyn_local, atlas.data, None, T, pad, grad_rgb, rgb_pad, w_smooth, g_dyn, g_sta)
+        else:
+            import torch.distributed as dist
+            # fold the loop-pad gradient onto frames 0..pad-1, then each rank back-propagates its own frames
+            if pad:
+                grad_rgb[:pad] += grad_rgb[T:T + pad]
+            ops.composite_bwd(view, pack, dyn_local, atlas.data, None, Tl, 0, grad_rgb[t0:t1], rgb_pad[t0:t1],
+                              w_smooth, g_dyn, g_sta)
+            if pack.n_static > 0:
+                dist.all_reduce(g_sta, group=self.group)                     # the one gradient all-reduce
+        self.t += 1
+        self._adam("atlas_dyn", dyn_local, g_dyn, lr)
+        if pack.n_static > 0:
+            self._adam("atlas", atlas.data, g_sta, lr)
+        return out
