@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py — VideoLoop3D stage-2 hot path on B200: render + looping loss + backward + Adam.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Prints ONE JSON line (rank 0).  Metric (BASELINE.json): "MPV render+loop-loss optim steps/sec
+@ D=32,T=48,720p".  Workload `step720p` = BASELINE configs[2] (the configuration the metric is quoted on;
+it contains configs[1], the render fwd+bwd, as a sub-part that is also reported):
+dense synthetic MPV, D=32 planes, T=48 frames, 720x1280, 36x64 vertex mesh, 1 texel : 1 pixel, reference-view
+loss config of configs/mpv_base.txt (p=11, pt=3, s=4, alpha=0, rou=-2, gain 3.5), rgb/a smoothness 0.2,
+scale-invariant gain, F=258 target frames (n2=256), Adam(eps=6e-8) over every texel.
+With --gpus N the T frames are sharded over N ranks (strong scaling: the step is the same).
+
+`--impl reference`: the reference's own algorithm on the host CPU (oracle port of its PyTorch path; the
+reference itself needs pytorch3d/unfoldNd which cannot be installed here), bounded sample, same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "MPV render+loop-loss optim steps/sec @ D=32,T=48,720p"
+WORKLOADS = {
+    # name: H, W, D, T, F, hv, wv
+    "step720p": dict(H=720, W=1280, D=32, T=48, F=258, hv=36, wv=64),
+    "step360p": dict(H=360, W=640, D=32, T=48, F=258, hv=36, wv=64),
+    "patch180": dict(H=180, W=320, D=32, T=48, F=258, hv=36, wv=64),      # the reference's own step shape
+    "tiny": dict(H=45, W=80, D=8, T=6, F=12, hv=6, wv=9),
+}
+CPU_SAMPLE = dict(H=90, W=160, D=32, T=48, F=258, hv=36, wv=64)             # 1/64 of the 720p frame
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def view_for(wl, jitter=(0.21, -0.13)):
+    """Target camera of SURVEY §8(d): 0.05 rad about y + translation (0.08,-0.03,0.02)*near, jittered
+    principal point."""
+    H, W = wl["H"], wl["W"]
+    c, s = np.cos(0.05), np.sin(0.05)
+    ext = np.eye(4, dtype=np.float32)
+    ext[:3, :3] = [[c, 0, s], [0, 1, 0], [-s, 0, c]]
+    ext[:3, 3] = [0.08, -0.03, 0.02]
+    f = 0.8 * W
+    intr = np.array([[f, 0, W / 2 + jitter[0]], [0, f, H / 2 + jitter[1]], [0, 0, 1]], dtype=np.float32)
+    return torch.from_numpy(ext)[None], torch.from_numpy(intr)[None]
+
+
+def make_args(wl, **kw):
+    from videoloop3d_b200 import default_args
+    return default_args(mpi_d=wl["D"], mpi_h_verts=wl["hv"], mpi_w_verts=wl["wv"], atlas_grid_h=4 if wl["D"] % 4 == 0 else 1,
+                        mpi_h_scale=1.0, mpi_w_scale=1.0, mpv_frm_num=1, **kw)
+
+
+def build_model(wl, device, frames, seed=2):
+    """Dense model as MPMeshVid.__init__ lays it out; the (frames,4,Hd,Wd) dynamic atlas is generated on the
+    device (N(0,1) rgb logits, N(-1,1) alpha logits) straight into the RGBA-interleaved layout."""
+    from videoloop3d_b200 import MPMeshVid
+    H, W = wl["H"], wl["W"]
+    args = make_args(wl)
+    f = 0.8 * W
+    ref_intrin = np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32)
+    torch.manual_seed(seed)
+    m = MPMeshVid(args, H, W, np.eye(4, dtype=np.float32), ref_intrin, 1.0, 10.0)
+    hd, wd = m.atlas_dyn.shape[-2:]
+    m.atlas.data = m.atlas.data[:, :, :1, :1].clone()             # dummy static atlas (MPV.py:266)
+    m.atlas_dyn.data = m.atlas_dyn.data[:, :, :1, :1].clone()
+    m = m.to(device)
+    g = torch.Generator(device=device).manual_seed(seed)
+    tex = torch.empty((frames, hd, wd, 4), dtype=torch.float32, device=device)
+    for t in range(frames):
+        tex[t].normal_(generator=g)
+    tex[..., 3] -= 1.0
+    m.atlas_dyn.data = tex.permute(0, 3, 1, 2)                     # logical (T,4,Hd,Wd), channels_last memory
+    m.frm_num = frames
+    m.invalidate_geometry()
+    return m
+
+
+def make_target(wl, device=None, seed=3, pinned=False):
+    """res ~ U(0,1) low-pass filtered in time (box 9), (1,F,3,H,W)."""
+    F_, H, W = wl["F"], wl["H"], wl["W"]
+    if device is not None and device.type == "cuda":
+        g = torch.Generator(device=device).manual_seed(seed)
+        raw = torch.rand((F_ + 8, 3, H, W), generator=g, device=device)
+        cs = torch.cumsum(raw, 0)
+        res = torch.empty((F_, 3, H, W), device=device)
+        res[0] = cs[8] / 9
+        res[1:] = (cs[9:] - cs[:-9]) / 9
+        return res[None]
+    g = torch.Generator().manual_seed(seed)
+    raw = torch.rand((F_ + 8, 3, H, W), generator=g)
+    cs = torch.cumsum(raw, 0)
+    res = torch.cat([cs[8:9], cs[9:] - cs[:-9]]) / 9
+    res = res[None].contiguous()
+    return res.pin_memory() if pinned else res
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 8 and r[4 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def algorithmic_bytes(wl, frames):
+    """each live texel touched once per pass, geometry recomputed in-kernel.
+    Dense 1:1 case N_tex = D*H*W per frame: fwd 16 B/texel + 12 B/pixel out; bwd re-reads the atlas and
+    writes the gradient (32 B/texel) + reads dL/drgb (12 B/pixel)."""
+    px = wl["H"] * wl["W"]
+    ntex = wl["D"] * px
+    fwd = frames * (16 * ntex + 12 * px)
+    bwd = frames * (32 * ntex + 12 * px)
+    return fwd, bwd
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_step(sample, threads, steps, warmup=1):
+    """The reference's algorithm (oracle port of its PyTorch CPU path, fp32) on a bounded sample:
+    forward (render + gpnn_lm + smoothness) + backward + Adam.  Returns seconds per sample step."""
+    from oracle import mpv_oracle as MO
+    torch.set_num_threads(threads)
+    st = MO.dense_state(sample["H"], sample["W"], sample["D"], sample["hv"], sample["wv"], 4 if sample["D"] % 4 == 0 else 1,
+                        sample["T"], 1.0, 10.0, 1.0, 1.0, seed=2)
+    st.atlas = st.atlas[:, :, :1, :1].clone()
+    ext, intr = view_for(sample)
+    res = make_target(sample)
+    cfg = dict(loss_name="gpnn_lm", loss_gain=3.5, patch_size=11, patcht_size=3, stride=4, stridet=1, alpha=0.0,
+               rou="-2", scaling=0.1, dist_fn="mse", macro_block=65, factor=1)
+    geo = MO.geometry(st, sample["H"], sample["W"], ext, intr)
+    ad = st.atlas_dyn.float().requires_grad_(True)
+    a = st.atlas.float().requires_grad_(True)
+    mom, var = torch.zeros_like(ad), torch.zeros_like(ad)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        MO_geo = MO.geometry(st, sample["H"], sample["W"], ext, intr)          # the reference rasterises every step
+        extra, _ = MO.forward_train(st, sample["H"], sample["W"], ext, intr, res, cfg, dtype=torch.float32, atlas=a,
+                                    atlas_dyn=ad, nn_mode="ref32")
+        loss = MO.total_loss(extra)
+        ad.grad = None
+        loss.backward()
+        with torch.no_grad():
+            p, mom, var = MO.adam_step(ad.detach(), ad.grad, mom, var, i + 1, 0.01)
+            ad.data.copy_(p)
+        times.append(time.perf_counter() - t0)
+        del MO_geo
+    return float(np.mean(times[warmup:]))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    wl = WORKLOADS[args.workload]
+    sample = dict(CPU_SAMPLE) if args.workload == "step720p" else dict(wl)
+    ratio = (wl["H"] * wl["W"]) / (sample["H"] * sample["W"])
+    sec = cpu_reference_step(sample, threads, max(1, args.steps), warmup=min(1, args.warmup))
+    value = 1.0 / (sec * ratio)
+    desc = (f"{sample['H']}x{sample['W']} patch (1/{ratio:.0f} of the frame), D={sample['D']}, T={sample['T']}, "
+            f"F={sample['F']}; {sec:.2f} s per sample step, scaled x{ratio:.0f} to the full frame")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sec * ratio, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "device": "host CPU"},
+            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from videoloop3d_b200 import FusedLoopStep, _lib
+    from videoloop3d_b200.train_step import loss_config
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the vl3d hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    wl = WORKLOADS[args.workload]
+    T = wl["T"]
+    t0, t1 = (T * rank) // world, (T * (rank + 1)) // world
+    model = build_model(wl, dev, t1 - t0, seed=2 + rank)
+    margs = model.args
+    cfg = loss_config(margs, ref_view=True)
+    ext, intr = view_for(wl)
+    H, W = wl["H"], wl["W"]
+    res_dev = make_target(wl, dev)
+    lr = margs.lrate * 0.01
+    step = FusedLoopStep(model, group=group, global_frames=T, timers=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- resident-input arm (value) ----------------
+    for _ in range(args.warmup):
+        step.step(H, W, ext, intr, res_dev, cfg, lr)
+    barrier()
+    n_warm_events = len(step.timers.get("composite_fwd", []))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.LAUNCHES
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step.step(H, W, ext, intr, res_dev, cfg, lr)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.LAUNCHES - launches0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms) / args.steps
+    kernel_ms = step.timer_ms(skip=n_warm_events)
+    final_loss = float(out["loss"])
+
+    # ---------------- end-to-end arm: host buffers, H2D + D2H inside the timed region ----------------
+    # The public call (FusedLoopStep.step, the run_iter equivalent) is fed from pinned host memory the way
+    # train_3dvid.run_iter feeds it (`datainfo_.to(device)`, train_3dvid.py:215); the next item's copy is
+    # issued on a side stream while the current step computes (double buffer), the loss is read back.
+    res_host = [make_target(wl, None, seed=3, pinned=True)]
+    res_host.append(res_host[0])                                     # two views of one pinned item (same bytes copied)
+    bufs = [torch.empty_like(res_dev), res_dev]
+    copy_stream = torch.cuda.Stream()
+    ext_h, intr_h = ext.pin_memory(), intr.pin_memory()
+    h2d = res_host[0].numel() * 4 + ext_h.numel() * 4 + intr_h.numel() * 4
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def e2e_loop(n):
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        with torch.cuda.stream(copy_stream):
+            bufs[0].copy_(res_host[0], non_blocking=True)
+            ready[0].record()
+        for i in range(n):
+            cur, nxt = i & 1, (i + 1) & 1
+            if i + 1 < n:
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(done[nxt])             # buffer `nxt` was consumed by step i-1
+                    bufs[nxt].copy_(res_host[nxt], non_blocking=True)
+                    ready[nxt].record()
+            torch.cuda.current_stream().wait_event(ready[cur])
+            e_d, i_d = ext_h.to(dev, non_blocking=True), intr_h.to(dev, non_blocking=True)
+            o = step.step(H, W, e_d, i_d, bufs[cur], cfg, lr)
+            done[cur].record()
+            loss_host.copy_(o["loss"].reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_loop(min(2, args.warmup))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    e0.record()
+    e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1000
+    ems = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ems) / args.steps
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        fwd_b, bwd_b = algorithmic_bytes(wl, t1 - t0)
+        dom = "composite_bwd" if kernel_ms.get("composite_bwd", 0) >= kernel_ms.get("composite_fwd", 0) else "composite_fwd"
+        dom_bytes = bwd_b if dom == "composite_bwd" else fwd_b
+        ach = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9
+        fwd_ach = fwd_b / (kernel_ms["composite_fwd"] * 1e-3) / 1e9
+        bwd_ach = bwd_b / (kernel_ms["composite_bwd"] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": 1000.0 / ms_per_step, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "H": H, "W": W, "planes": wl["D"], "frames": T,
+                       "target_frames": wl["F"], "mesh": [wl["hv"], wl["wv"]], "atlas": "dense 1 texel:1 pixel",
+                       "loss": "gpnn_lm p=11 pt=3 s=4 alpha=0 rou=-2 gain=3.5 + rgb/a smooth 0.2 + scale-invariant",
+                       "optimizer": "Adam eps=6e-8 over all texels", "parallelism": f"T-shard x{world}",
+                       "l2": "inputs (>= 22 GB of texels per step) far exceed the 126 MB L2; no explicit flush"},
+            "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms / args.steps,
+                    "api": "FusedLoopStep.step fed from pinned host memory (double-buffered H2D), loss read back"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes),
+                         "ms_per_launch": kernel_ms[dom]},
+            "kernels_ms": {k: round(v, 4) for k, v in kernel_ms.items()},
+            "composite": {"fwd_GBps": fwd_ach, "fwd_frac": fwd_ach / peak, "bwd_GBps": bwd_ach, "bwd_frac": bwd_ach / peak,
+                          "render_fwd_bwd_steps_per_s": 1000.0 / (kernel_ms["composite_fwd"] + kernel_ms["composite_bwd"]
+                                                                  + kernel_ms.get("grad_zero", 0.0))},
+            "final_loss": final_loss,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sample = dict(CPU_SAMPLE) if args.workload == "step720p" else dict(wl)
+            ratio = (H * W) / (sample["H"] * sample["W"])
+            sec = cpu_reference_step(sample, threads, 1, warmup=0)
+            line["cpu_baseline"] = {"value": 1.0 / (sec * ratio), "unit": "steps/s", "cores": threads, "kind": "port",
+                                    "sample": f"oracle port of the reference's PyTorch CPU path on one {sample['H']}x{sample['W']} "
+                                              f"patch (1/{ratio:.0f} of the frame), D={sample['D']}, T={sample['T']}, F={sample['F']}: "
+                                              f"{sec:.2f} s, scaled x{ratio:.0f}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="step720p", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -103,7 +103,7 @@ class FusedLoopStep:
     state of other frames are never touched here).
     """
 
-    def __init__(self, model: MPMeshVid, group=None, betas=(0.9, 0.999), eps=6e-8):
+    def __init__(self, model: MPMeshVid, group=None, betas=(0.9, 0.999), eps=6e-8, global_frames=None, timers=False):
         if not model.atlas_dyn.is_cuda:
             raise Vl3dError("FusedLoopStep needs the model on a CUDA device")
         self.model = model
@@ -116,13 +116,31 @@ class FusedLoopStep:
         if group is not None:
             import torch.distributed as dist
             self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        T = model.atlas_dyn.shape[0]
+        # `global_frames`: the model on this rank holds ONLY its own block of frames (memory-sharded);
+        # otherwise every rank holds all T frames and touches only its block.
+        self.local_model = global_frames is not None
+        T = int(global_frames) if self.local_model else model.atlas_dyn.shape[0]
         self.T = T
         bounds = [(T * r) // self.world for r in range(self.world + 1)]
         self.bounds = bounds
         self.t0, self.t1 = bounds[self.rank], bounds[self.rank + 1]
         if self.t1 <= self.t0:
             raise Vl3dError(f"rank {self.rank} owns no frames (T={T}, world={self.world})")
+        if self.local_model and model.atlas_dyn.shape[0] != self.t1 - self.t0:
+            raise Vl3dError(f"memory-sharded model must hold {self.t1 - self.t0} frames, has {model.atlas_dyn.shape[0]}")
+        self.timers = {} if timers else None
+
+    def _timed(self, name):
+        return _Timed(self.timers, name)
+
+    def timer_ms(self, skip=0):
+        """{kernel name: mean ms} from the CUDA events recorded so far (call after a synchronize)."""
+        out = {}
+        for k, evs in (self.timers or {}).items():
+            evs = evs[skip:]
+            if evs:
+                out[k] = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        return out
 
     def reset(self):
         """Fresh optimiser state (the reference builds a new Adam per pyramid level, train_3dvid.py:265)."""
@@ -169,15 +187,17 @@ class FusedLoopStep:
         rgb_pad = self._get("rgb_pad", (T + pad, 3, h, w), torch.float32)
         sums = self._get("sums", (4,), torch.float64)
         sums.zero_()
-        dyn_local = atlas_dyn.data[t0:t1]
+        dyn_local = atlas_dyn.data if self.local_model else atlas_dyn.data[t0:t1]
         if self.world == 1:
-            ops.composite_fwd(view, pack, dyn_local, atlas.data, None, T, pad, rgb_out=rgb_pad,
-                              smooth_sums=sums if smooth else None)
+            with self._timed("composite_fwd"):
+                ops.composite_fwd(view, pack, dyn_local, atlas.data, None, T, pad, rgb_out=rgb_pad,
+                                  smooth_sums=sums if smooth else None)
         else:
             import torch.distributed as dist
             # render the owned frames straight into their slot of the gathered video, then all-gather
-            ops.composite_fwd(view, pack, dyn_local, atlas.data, None, Tl, 0, rgb_out=rgb_pad[t0:t1],
-                              smooth_sums=sums if smooth else None)
+            with self._timed("composite_fwd"):
+                ops.composite_fwd(view, pack, dyn_local, atlas.data, None, Tl, 0, rgb_out=rgb_pad[t0:t1],
+                                  smooth_sums=sums if smooth else None)
             if len(set(b - a for a, b in zip(self.bounds[:-1], self.bounds[1:]))) == 1:
                 dist.all_gather_into_tensor(rgb_pad[:T], rgb_pad[t0:t1], group=self.group)
             else:
@@ -190,30 +210,34 @@ class FusedLoopStep:
 
         xscale = None
         if args.scale_invariant:
-            xscale = ops.scale_invariant(rgb_pad, T, res0, out=self._get("xscale", (1,), torch.float32),
-                                         partials=self._get("scale_part", (ops._lib.load().vl3d_scale_partials(),),
-                                                            torch.float64))
+            with self._timed("scale_invariant"):
+                xscale = ops.scale_invariant(rgb_pad, T, res0, out=self._get("xscale", (1,), torch.float32),
+                                             partials=self._get("scale_part", (ops._lib.load().vl3d_scale_partials(),),
+                                                                torch.float64))
         desc = ops.make_loss_desc(rgb_pad.shape, (rgb_pad.stride(0), rgb_pad.stride(1), rgb_pad.stride(2)), res0.shape,
                                   (res0.stride(0), res0.stride(1), res0.stride(2)), cfg["patch_size"],
                                   cfg["patcht_size"], cfg["stride"], cfg["stridet"], cfg.get("alpha", 1e10),
                                   fit=lossobj.fit)
         nn = self._get("nn", (desc.ho, desc.wo, desc.n1), torch.int32)
         if self.world == 1:
-            ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn)
+            with self._timed("patchnn_search"):
+                ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn)
         else:
             import torch.distributed as dist
             # patch positions are independent (utils_vid.py:211-215): each rank searches a band of patch
             # rows, then the int32 index map is summed across ranks (disjoint rows, zeros elsewhere)
             r0, r1 = (desc.ho * self.rank) // self.world, (desc.ho * (self.rank + 1)) // self.world
             nn.zero_()
-            ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn, rows=(r0, r1))
+            with self._timed("patchnn_search"):
+                ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn, rows=(r0, r1))
             dist.all_reduce(nn, group=self.group)
         grad_rgb = self._get("grad_rgb", (T + pad, 3, h, w), torch.float32)
         n_part = ops._lib.load().vl3d_vote_partials(T + pad, h, w)
-        loss_out, _, _, _ = ops.vote_loss(desc, rgb_pad, xscale, res0, nn, cfg.get("rou", 0), cfg.get("scaling", 0.2),
-                                          gain, (T + pad, h, w), grad_out=grad_rgb,
-                                          partials=self._get("vote_part", (n_part,), torch.float64),
-                                          loss_out=self._get("loss_out", (1,), torch.float32))
+        with self._timed("vote_loss"):
+            loss_out, _, _, _ = ops.vote_loss(desc, rgb_pad, xscale, res0, nn, cfg.get("rou", 0),
+                                              cfg.get("scaling", 0.2), gain, (T + pad, h, w), grad_out=grad_rgb,
+                                              partials=self._get("vote_part", (n_part,), torch.float64),
+                                              loss_out=self._get("loss_out", (1,), torch.float32))
         # d total / d smooth_sums (host constants): MPV.py:517-531 with K cancelled, train_3dvid.py:230-240
         w_smooth = None
         nx = max(T * h * (w - 1), 1) * m.mpi_d
@@ -248,21 +272,46 @@ class FusedLoopStep:
         if g_sta is None or g_sta.shape != atlas.shape or tuple(g_sta.stride()) != tuple(atlas.stride()):
             g_sta = torch.empty_like(atlas.data)
             self._buf["g_sta"] = g_sta
-        g_dyn.zero_()
-        g_sta.zero_()
+        with self._timed("grad_zero"):
+            g_dyn.zero_()
+            g_sta.zero_()
         if self.world == 1:
-            ops.composite_bwd(view, pack, dyn_local, atlas.data, None, T, pad, grad_rgb, rgb_pad, w_smooth, g_dyn, g_sta)
+            with self._timed("composite_bwd"):
+                ops.composite_bwd(view, pack, dyn_local, atlas.data, None, T, pad, grad_rgb, rgb_pad, w_smooth, g_dyn,
+                                  g_sta)
         else:
             import torch.distributed as dist
             # fold the loop-pad gradient onto frames 0..pad-1, then each rank back-propagates its own frames
             if pad:
                 grad_rgb[:pad] += grad_rgb[T:T + pad]
-            ops.composite_bwd(view, pack, dyn_local, atlas.data, None, Tl, 0, grad_rgb[t0:t1], rgb_pad[t0:t1],
-                              w_smooth, g_dyn, g_sta)
+            with self._timed("composite_bwd"):
+                ops.composite_bwd(view, pack, dyn_local, atlas.data, None, Tl, 0, grad_rgb[t0:t1], rgb_pad[t0:t1],
+                                  w_smooth, g_dyn, g_sta)
             if pack.n_static > 0:
                 dist.all_reduce(g_sta, group=self.group)                     # the one gradient all-reduce
         self.t += 1
-        self._adam("atlas_dyn", dyn_local, g_dyn, lr)
-        if pack.n_static > 0:
-            self._adam("atlas", atlas.data, g_sta, lr)
+        with self._timed("adam"):
+            self._adam("atlas_dyn", dyn_local, g_dyn, lr)
+            if pack.n_static > 0:
+                self._adam("atlas", atlas.data, g_sta, lr)
         return out
+
+
+class _Timed:
+    """CUDA-event bracket on the current stream (the stream the kernels are launched on)."""
+
+    def __init__(self, store, name):
+        self.store, self.name = store, name
+
+    def __enter__(self):
+        if self.store is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.store is not None:
+            self.b.record()
+            self.store.setdefault(self.name, []).append((self.a, self.b))
+        return False
