@@ -115,11 +115,13 @@ int vl3d_composite_bwd(const vl3d_view* view, const vl3d_quad* quads, const floa
 int vl3d_scale_partials(void);
 int vl3d_scale_invariant(const float* rgb, int32_t T, const float* res, int32_t F, int32_t H, int32_t W,
                          double* partials, float* out, void* stream);
+/* out[i] = x[i] * xscale[0] for n contiguous floats (rgb_pad * scale, MPV.py:504). */
+int vl3d_scale_video(const float* x, const float* xscale, float* out, int64_t n, void* stream);
 
 /* ---- looping loss (utils_vid.py) ---------------------------------------------------------------
  * vl3d_patchnn_search: extract_3Dpatches + efficient_compute_distances + get_col_mins_efficient +
  *   get_NN_indices_low_memory (utils_vid.py:60-142) fused; distances are direct sums of squared
- *   differences in fp32.  x values are multiplied by *xscale (device scalar, NULL = 1).
+ *   differences in fp32.  x must already carry the scale-invariant gain (vl3d_scale_video).
  *   nn_out: (ho, wo, n1) int32, first-minimum tie rule.  Only patch rows [row_begin, row_end) are
  *   searched and written (patch positions are independent: this is how ranks split the search).
  * vl3d_vote_loss: gather + FoldNd votes / counts + robust_lossfun + its derivative
@@ -128,7 +130,7 @@ int vl3d_scale_invariant(const float* rgb, int32_t T, const float* res, int32_t 
  *   grad_out: (Tx_full, 3, Hfull, Wfull) = gcoef * xscale * rho'(x*xscale - y2x) / N inside the
  *   fitted crop, 0 outside (optional).  loss_out[0] = mean rho (1 float). partials: workspace of
  *   >= vl3d_vote_partials(Tx_full, Hfull, Wfull) doubles. */
-int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, const float* xscale, const float* y,
+int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, const float* y,
                         int32_t row_begin, int32_t row_end, int32_t* nn_out, void* stream);
 int vl3d_vote_partials(int32_t Tx_full, int32_t Hfull, int32_t Wfull);
 int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const float* xscale, const float* y,

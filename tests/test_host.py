@@ -113,7 +113,7 @@ def test_argument_validation_happens_before_any_launch():
                   ctypes.c_void_p(16), None, None, None, None, None)
     d = ops.make_loss_desc((50, 3, 180, 320), (1, 1, 1), (258, 3, 180, 320), (1, 1, 1), 11, 3, 4, 1, 0.0)
     with pytest.raises(_lib.Vl3dError, match="NULL"):
-        _lib.call("vl3d_patchnn_search", ctypes.byref(d), None, None, None, 0, 1, None, None)
+        _lib.call("vl3d_patchnn_search", ctypes.byref(d), None, None, 0, 1, None, None)
     with pytest.raises(_lib.Vl3dError, match="step"):
         _lib.call("vl3d_adam_step", ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16),
                   8, 0, 0.1, 0.9, 0.999, 6e-8, None)

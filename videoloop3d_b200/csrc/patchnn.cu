@@ -26,7 +26,6 @@ constexpr int NN_MAX_N1 = 256;
 struct SearchParams {
     vl3d_loss_desc d;
     const float* x;
-    const float* xscale;
     const float* y;
     int* nn;
     int groups;     // float4 groups per slab = ceil(3p/4)
@@ -51,7 +50,6 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_search_kernel(const __grid
     const int pxi = blockIdx.x, pyi = P.row0 + blockIdx.y;                   // patch position on the stride-s grid
     const int x0 = pxi * L.s, y0 = pyi * L.s;
     const int p = L.p, pt = L.pt, st = L.st;
-    const float xsc = P.xscale ? __ldg(P.xscale) : 1.f;
     const float inv_d = 1.f / (float)(3 * pt * p * p);              // dist /= d (utils_vid.py:83-84)
     const int tb = tid & 15, ta = tid >> 4;                         // thread tile: x frames ta+16*i, y frames tb+16*j
 
@@ -88,10 +86,9 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_search_kernel(const __grid
                     const bool ok = gf < (which ? ty_used : tx_used);
                     const float* src = which ? P.y + (size_t)gf * L.y_sf + (size_t)c * L.y_sc + (size_t)(y0 + row) * L.y_sr + x0
                                              : P.x + (size_t)gf * L.x_sf + (size_t)c * L.x_sc + (size_t)(y0 + row) * L.x_sr + x0;
-                    const float mul = which ? 1.f : xsc;
                     for (int dx = 0; dx < p; ++dx) {
                         const int e = c * p + dx;
-                        const float val = ok ? __ldg(src + dx) * mul : 0.f;
+                        const float val = ok ? __ldg(src + dx) : 0.f;
                         dst[((e >> 2) * NN_CF + fr) * 4 + (e & 3)] = val;
                     }
                 }
@@ -201,27 +198,34 @@ static size_t search_smem_bytes(const vl3d_loss_desc* L) {
 struct StripParams {
     vl3d_loss_desc d;
     const float* x;
-    const float* xscale;
     const float* y;
     int* nn;
     int groups;     // float4 groups per slab
     int row0, row1; // patch-row range of this launch
     int SL;         // patches per strip
-    int nta;        // x-frame groups: blockDim.x = 16 * nta, x frames per block XF = 4 * nta
+    int nta, ntb;   // thread tile grid: blockDim.x = nta * ntb; x frames XF = 4*nta, chunk frames CF = 4*ntb
 };
+
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 4 : 0;                                // src-size 0 => zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int M>
 __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_constant__ StripParams P) {
     extern __shared__ __align__(16) float smem[];
     const vl3d_loss_desc& L = P.d;
-    const int G4 = P.groups, NTA = P.nta, XF = 4 * NTA;
-    const int nthreads = 16 * NTA;
+    const int G4 = P.groups, NTA = P.nta, NTB = P.ntb, XF = 4 * NTA, CF = 4 * NTB;
+    const int nthreads = NTA * NTB;
     float4* xs4 = reinterpret_cast<float4*>(smem);                  // [2][G4][XF]
-    float4* ys4 = xs4 + 2 * G4 * XF;                                // [2][G4][64]
-    float* Gs = reinterpret_cast<float*>(ys4 + 2 * G4 * NN_CF);     // [XF][65]
-    float* Ds = Gs + XF * (NN_CF + 1);                              // [n1][64]
-    float* colmin = Ds + (size_t)L.n1 * NN_CF;                      // [64]
-    float* best_val = colmin + NN_CF;                               // [SL][n1]
+    float4* ys4 = xs4 + 2 * G4 * XF;                                // [2][G4][CF]
+    float* Gs = reinterpret_cast<float*>(ys4 + 2 * G4 * CF);        // [XF][CF+1]
+    float* Ds = Gs + XF * (CF + 1);                                 // [n1][CF]
+    float* colmin = Ds + (size_t)L.n1 * CF;                         // [CF]
+    float* best_val = colmin + CF;                                  // [SL][n1]
     int* best_idx = reinterpret_cast<int*>(best_val + (size_t)P.SL * L.n1);
 
     const int tid = threadIdx.x;
@@ -231,48 +235,55 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
     const int x0 = pxi * L.s;
     const int p = L.p, pt = L.pt, st = L.st, s = L.s;
     const int rem = p - M * s;                                      // rows of the (M+1)-th group used by a patch
-    const float xsc = P.xscale ? __ldg(P.xscale) : 1.f;
     const float inv_d = 1.f / (float)(3 * pt * p * p);
-    const int tb = tid & 15, ta = tid >> 4;
+    const int ta = tid / NTB, tb = tid - ta * NTB;
     const int tx_used = (L.n1 - 1) * st + pt, ty_used = (L.n2 - 1) * st + pt;
     const int nrows = (k1 - 1 - k0) * s + p;                        // pixel rows swept by this strip
     const int ybase = k0 * s;
+    const int cand_per_chunk = (CF - pt) / st + 1;
 
     for (int i = tid; i < (k1 - k0) * L.n1; i += nthreads) { best_val[i] = INFINITY; best_idx[i] = 0; }
 
+    // asynchronous global -> shared staging of one pixel row of the window (3 channels, all frames):
+    // LDGSTS, no register round trip; frames beyond the video are zero-filled
     auto stage = [&](int c0, int row, int buf) {
-        const int nx = 3 * XF, ny = 3 * NN_CF;
+        const int nx = 3 * XF, ny = 3 * CF;
         for (int id = tid; id < nx + ny; id += nthreads) {
             const bool isy = id >= nx;
             const int q = isy ? id - nx : id;
-            const int nf = isy ? NN_CF : XF;
+            const int nf = isy ? CF : XF;
             const int c = q / nf, fr = q - c * nf;
-            float* dst = reinterpret_cast<float*>(isy ? ys4 + (size_t)buf * G4 * NN_CF : xs4 + (size_t)buf * G4 * XF);
+            float* dst = reinterpret_cast<float*>(isy ? ys4 + (size_t)buf * G4 * CF : xs4 + (size_t)buf * G4 * XF);
             const int gf = isy ? c0 + fr : fr;
             const bool ok = gf < (isy ? ty_used : tx_used);
-            const float* src = isy ? P.y + (size_t)gf * L.y_sf + (size_t)c * L.y_sc + (size_t)(ybase + row) * L.y_sr + x0
-                                   : P.x + (size_t)gf * L.x_sf + (size_t)c * L.x_sc + (size_t)(ybase + row) * L.x_sr + x0;
-            const float mul = isy ? 1.f : xsc;
-            for (int dx = 0; dx < p; ++dx) {
-                const int e = c * p + dx;
-                dst[((e >> 2) * nf + fr) * 4 + (e & 3)] = ok ? __ldg(src + dx) * mul : 0.f;
-            }
+            const int gfc = ok ? gf : 0;
+            const float* src = isy ? P.y + (size_t)gfc * L.y_sf + (size_t)c * L.y_sc + (size_t)(ybase + row) * L.y_sr + x0
+                                   : P.x + (size_t)gfc * L.x_sf + (size_t)c * L.x_sc + (size_t)(ybase + row) * L.x_sr + x0;
+            float* d0 = dst + fr * 4;
+            int e = c * p;
+            for (int dx = 0; dx < p; ++dx, ++e) cp_async_f32(d0 + (e >> 2) * (nf * 4) + (e & 3), src + dx, ok);
         }
+        cp_async_commit();
+    };
+    // padding lanes of the last float4 group never change: zero them once in both buffers
+    {
         const int npad = 4 * G4 - 3 * p;
-        for (int id = tid; id < npad * (XF + NN_CF); id += nthreads) {
-            const int e = 3 * p + id / (XF + NN_CF);
-            const int q = id % (XF + NN_CF);
+        for (int id = tid; id < 2 * npad * (XF + CF); id += nthreads) {
+            const int buf = id / (npad * (XF + CF));
+            const int r2 = id - buf * npad * (XF + CF);
+            const int e = 3 * p + r2 / (XF + CF);
+            const int q = r2 % (XF + CF);
             const bool isy = q >= XF;
             const int fr = isy ? q - XF : q;
-            const int nf = isy ? NN_CF : XF;
-            float* dst = reinterpret_cast<float*>(isy ? ys4 + (size_t)buf * G4 * NN_CF : xs4 + (size_t)buf * G4 * XF);
+            const int nf = isy ? CF : XF;
+            float* dst = reinterpret_cast<float*>(isy ? ys4 + (size_t)buf * G4 * CF : xs4 + (size_t)buf * G4 * XF);
             dst[((e >> 2) * nf + fr) * 4 + (e & 3)] = 0.f;
         }
-    };
+    }
 
     for (int j0 = 0; j0 < L.n2;) {
         const int c0 = j0 * st;
-        int j1 = (c0 + NN_CF - pt) / st + 1;
+        int j1 = j0 + cand_per_chunk;
         if (j1 > L.n2) j1 = L.n2;
         const int cj = j1 - j0;
 
@@ -287,22 +298,23 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
                 for (int m = 0; m < (M > 0 ? M : 1); ++m) hist[m][i][j] = 0.f;
             }
 
-        __syncthreads();
+        __syncthreads();                                            // previous chunk's readers are done
         stage(c0, 0, 0);
-        __syncthreads();
         for (int row = 0; row < nrows; ++row) {
             const int buf = row & 1;
-            if (row + 1 < nrows) stage(c0, row + 1, buf ^ 1);
+            cp_async_wait_all();
+            __syncthreads();                                        // row `row` landed; buffer buf^1 is free
+            if (row + 1 < nrows) stage(c0, row + 1, buf ^ 1);       // overlaps the arithmetic below
             const int grp = row / s, rin = row - grp * s;           // group of s rows, row inside the group
             if (M > 0 || rin < p) {                                 // (p < s: rows between patches are unused)
-                const float4* xb = xs4 + (size_t)buf * G4 * XF;
-                const float4* yb = ys4 + (size_t)buf * G4 * NN_CF;
-                for (int g = 0; g < G4; ++g) {
+                const float4* xp = xs4 + (size_t)buf * G4 * XF + ta;
+                const float4* yp = ys4 + (size_t)buf * G4 * CF + tb;
+                for (int g = 0; g < G4; ++g, xp += XF, yp += CF) {
                     float4 xa[NN_R], ya[NN_R];
 #pragma unroll
-                    for (int i = 0; i < NN_R; ++i) xa[i] = xb[g * XF + ta + NTA * i];
+                    for (int i = 0; i < NN_R; ++i) xa[i] = xp[NTA * i];
 #pragma unroll
-                    for (int j = 0; j < NN_R; ++j) ya[j] = yb[g * NN_CF + tb + 16 * j];
+                    for (int j = 0; j < NN_R; ++j) ya[j] = yp[NTB * j];
 #pragma unroll
                     for (int i = 0; i < NN_R; ++i)
 #pragma unroll
@@ -323,31 +335,26 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
                 for (int i = 0; i < NN_R; ++i)
 #pragma unroll
                     for (int j = 0; j < NN_R; ++j) {
-                        float gsum = (rem > 0) ? cur[i][j] : 0.f;
-                        if (rem > 0) {
+                        float gsum = cur[i][j];
 #pragma unroll
-                            for (int m = 0; m < M; ++m) gsum += hist[m][i][j];
-                        } else {                                   // p == M*s: cur is the last of the M groups
-                            gsum = cur[i][j];
-#pragma unroll
-                            for (int m = 0; m + 1 < M; ++m) gsum += hist[m][i][j];
-                        }
-                        Gs[(ta + NTA * i) * (NN_CF + 1) + tb + 16 * j] = gsum;
+                        for (int m = 0; m < M; ++m)
+                            if (rem > 0 || m + 1 < M) gsum += hist[m][i][j];   // p == M*s: cur is the M-th group itself
+                        Gs[(ta + NTA * i) * (CF + 1) + tb + NTB * j] = gsum;
                     }
                 __syncthreads();
                 for (int id = tid; id < L.n1 * cj; id += nthreads) {
                     const int il = id / cj, jl = id - il * cj;
-                    const int gx = il * st, gy = (j0 + jl) * st - c0;
+                    const int gx = il * st, gy = jl * st;
                     float sum = 0.f;
-                    for (int dt = 0; dt < pt; ++dt) sum += Gs[(gx + dt) * (NN_CF + 1) + gy + dt];
-                    Ds[(size_t)il * NN_CF + jl] = sum * inv_d;
+                    for (int dt = 0; dt < pt; ++dt) sum += Gs[(gx + dt) * (CF + 1) + gy + dt];
+                    Ds[(size_t)il * CF + jl] = sum * inv_d;
                 }
                 __syncthreads();
                 if (L.use_alpha) {
                     for (int jl = tid; jl < cj; jl += nthreads) {
                         float mn = INFINITY;
                         for (int i = 0; i < L.n1; ++i) {
-                            const float vv = Ds[(size_t)i * NN_CF + jl];
+                            const float vv = Ds[(size_t)i * CF + jl];
                             mn = (vv < mn || vv != vv) ? vv : mn;
                         }
                         colmin[jl] = L.alpha + mn;
@@ -358,7 +365,7 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
                     float bv = best_val[kr * L.n1 + i];
                     int bi = best_idx[kr * L.n1 + i];
                     for (int jl = 0; jl < cj; ++jl) {
-                        float vv = Ds[(size_t)i * NN_CF + jl];
+                        float vv = Ds[(size_t)i * CF + jl];
                         if (L.use_alpha) vv = vv / colmin[jl];
                         const bool better = (vv < bv) || (vv != vv && bv == bv);
                         if (better) { bv = vv; bi = j0 + jl; }
@@ -377,7 +384,6 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
                         cur[i][j] = 0.f;
                     }
             }
-            __syncthreads();
         }
         j0 = j1;
     }
@@ -388,10 +394,9 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
     }
 }
 
-static size_t strip_smem_bytes(const vl3d_loss_desc* L, int nta, int SL) {
-    const int G4 = (3 * L->p + 3) / 4, XF = 4 * nta;
-    size_t fl = (size_t)4 * 2 * G4 * (XF + NN_CF) + (size_t)XF * (NN_CF + 1) + (size_t)L->n1 * NN_CF + NN_CF +
-                2 * (size_t)SL * L->n1;
+static size_t strip_smem_bytes(const vl3d_loss_desc* L, int nta, int ntb, int SL) {
+    const int G4 = (3 * L->p + 3) / 4, XF = 4 * nta, CF = 4 * ntb;
+    size_t fl = (size_t)4 * 2 * G4 * (XF + CF) + (size_t)XF * (CF + 1) + (size_t)L->n1 * CF + CF + 2 * (size_t)SL * L->n1;
     return fl * sizeof(float);
 }
 
@@ -543,6 +548,13 @@ __global__ void __launch_bounds__(1024) scale_finalize_kernel(const double* part
     }
 }
 
+// rgb_pad * scale (MPV.py:504): the search consumes a pre-scaled copy so it can stage with cp.async
+__global__ void __launch_bounds__(256) scale_video_kernel(const float* __restrict__ x, const float* __restrict__ xscale,
+                                                          float* __restrict__ out, size_t n) {
+    const float sc = __ldg(xscale);
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = x[i] * sc;
+}
+
 static int validate_desc(const vl3d_loss_desc* L) {
     VL3D_REQUIRE(L != nullptr, VL3D_ENULL, "loss desc is NULL");
     VL3D_REQUIRE(L->p >= 1 && L->pt >= 1 && L->s >= 1 && L->st >= 1, VL3D_EINVAL, "bad patch config");
@@ -560,8 +572,8 @@ static int validate_desc(const vl3d_loss_desc* L) {
 
 using namespace vl3d;
 
-extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, const float* xscale, const float* y,
-                                   int32_t row_begin, int32_t row_end, int32_t* nn_out, void* stream) {
+extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, const float* y, int32_t row_begin,
+                                   int32_t row_end, int32_t* nn_out, void* stream) {
     if (int e = validate_desc(desc)) return e;
     VL3D_REQUIRE(row_begin >= 0 && row_end <= desc->ho && row_begin <= row_end, VL3D_EINVAL, "bad row range [%d,%d)",
                  row_begin, row_end);
@@ -573,16 +585,31 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
     if (tx_used <= NN_CF && M <= 3) {
         // strip kernel: rows shared between vertically overlapping patches
         StripParams P{};
-        P.d = *desc; P.x = x; P.xscale = xscale; P.y = y; P.nn = nn_out; P.groups = (3 * desc->p + 3) / 4;
+        P.d = *desc; P.x = x; P.y = y; P.nn = nn_out; P.groups = (3 * desc->p + 3) / 4;
         P.row0 = row_begin; P.row1 = row_end;
         P.nta = (tx_used + 3) / 4;
-        if (P.nta < 2) P.nta = 2;                                   // at least one full warp
+        if (P.nta < 2) P.nta = 2;
+        // candidate chunk width: 4*ntb frames per sweep; pick the ntb that wastes the fewest frame-sweeps
+        {
+            const int ty_used = (desc->n2 - 1) * desc->st + desc->pt;
+            int best_ntb = 0; long long best_cost = 0;
+            const int ntb_max = NN_THREADS / P.nta;
+            for (int ntb = (desc->pt + 3) / 4 + 1; ntb <= ntb_max; ++ntb) {
+                const int cands = (4 * ntb - desc->pt) / desc->st + 1;
+                const int chunks = (desc->n2 + cands - 1) / cands;
+                const long long cost = (long long)chunks * 4 * ntb * 64 + 2000LL * chunks;   // + per-chunk overhead
+                if (P.nta * ntb < 64 && 4 * ntb < ty_used) continue;   // keep at least two warps busy
+                if (best_ntb == 0 || cost < best_cost) { best_ntb = ntb; best_cost = cost; }
+            }
+            if (best_ntb == 0) best_ntb = ntb_max;
+            P.ntb = best_ntb;
+        }
         const int rows = row_end - row_begin;
         int SL = 16;                                                // longer strips share more rows, shorter ones fill the GPU
         while (SL > 2 && (long long)desc->wo * ((rows + SL - 1) / SL) < 148 * 6) SL >>= 1;
         if (SL > rows) SL = rows;
         P.SL = SL;
-        const size_t smem = strip_smem_bytes(desc, P.nta, SL);
+        const size_t smem = strip_smem_bytes(desc, P.nta, P.ntb, SL);
         VL3D_REQUIRE(smem <= 200 * 1024, VL3D_ERANGE, "patch_size %d / n1 %d need %zu B of shared memory", desc->p,
                      desc->n1, smem);
         void (*kern)(StripParams) = M == 0 ? patchnn_strip_kernel<0> : M == 1 ? patchnn_strip_kernel<1>
@@ -590,7 +617,7 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
         cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (ce != cudaSuccess) return set_err((int)ce, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
         dim3 grid(desc->wo, (rows + SL - 1) / SL);
-        kern<<<grid, 16 * P.nta, smem, st>>>(P);
+        kern<<<grid, P.nta * P.ntb, smem, st>>>(P);
         return check_launch("patchnn_search(strip)");
     }
     const size_t smem = search_smem_bytes(desc);
@@ -598,7 +625,7 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
     cudaError_t ce = cudaFuncSetAttribute(patchnn_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (ce != cudaSuccess) return set_err((int)ce, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
     SearchParams P{};
-    P.d = *desc; P.x = x; P.xscale = xscale; P.y = y; P.nn = nn_out; P.groups = (3 * desc->p + 3) / 4;
+    P.d = *desc; P.x = x; P.y = y; P.nn = nn_out; P.groups = (3 * desc->p + 3) / 4;
     P.row0 = row_begin;
     dim3 grid(desc->wo, row_end - row_begin);
     patchnn_search_kernel<<<grid, NN_THREADS, smem, st>>>(P);
@@ -638,6 +665,16 @@ extern "C" int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const 
 }
 
 extern "C" int vl3d_scale_partials(void) { return SCALE_BLOCKS; }
+
+extern "C" int vl3d_scale_video(const float* x, const float* xscale, float* out, int64_t n, void* stream) {
+    VL3D_REQUIRE(x && xscale && out, VL3D_ENULL, "scale_video: NULL pointer");
+    VL3D_REQUIRE(n >= 0, VL3D_EINVAL, "scale_video: n < 0");
+    if (n == 0) return 0;
+    size_t blocks = ((size_t)n + 1023) / 1024;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    scale_video_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, xscale, out, (size_t)n);
+    return check_launch("scale_video");
+}
 
 extern "C" int vl3d_scale_invariant(const float* rgb, int32_t T, const float* res, int32_t F, int32_t H, int32_t W,
                                     double* partials, float* out, void* stream) {

@@ -154,11 +154,28 @@ def make_loss_desc(x_tchw_shape, x_strides, y_fchw_shape, y_strides, patch_size,
     return d
 
 
-def patchnn_search(desc, x, xscale, y, nn_out=None, rows=None):
+def scale_video(x, xscale, out=None):
+    """x * xscale into a contiguous buffer (MPV.py:504)."""
+    if not x.is_contiguous():
+        x = x.contiguous()
+    if out is None or out.shape != x.shape:
+        out = torch.empty_like(x)
+    _lib.call("vl3d_scale_video", _lib.ptr(x), _lib.ptr(xscale), _lib.ptr(out), int(x.numel()), _lib.stream_ptr())
+    return out
+
+
+def patchnn_search(desc, x, xscale, y, nn_out=None, rows=None, scaled_ws=None):
+    """NN indices (ho,wo,n1) int32.  With a scale-invariant gain the search runs on a pre-scaled copy of x
+    (`scaled_ws`: optional persistent workspace of x's shape)."""
     if nn_out is None:
         nn_out = torch.empty((desc.ho, desc.wo, desc.n1), dtype=torch.int32, device=x.device)
     r0, r1 = (0, desc.ho) if rows is None else rows
-    _lib.call("vl3d_patchnn_search", C.byref(desc), _lib.ptr(x), _lib.ptr(xscale), _lib.ptr(y), int(r0), int(r1),
+    if xscale is not None:
+        x = scale_video(x, xscale, out=scaled_ws)
+        d2 = _lib.LossDesc.from_buffer_copy(desc)
+        d2.x_sf, d2.x_sc, d2.x_sr = x.stride(0), x.stride(1), x.stride(2)
+        desc = d2
+    _lib.call("vl3d_patchnn_search", C.byref(desc), _lib.ptr(x), _lib.ptr(y), int(r0), int(r1),
               _lib.ptr(nn_out), _lib.stream_ptr())
     return nn_out
 

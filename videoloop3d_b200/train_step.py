@@ -221,7 +221,8 @@ class FusedLoopStep:
         nn = self._get("nn", (desc.ho, desc.wo, desc.n1), torch.int32)
         if self.world == 1:
             with self._timed("patchnn_search"):
-                ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn)
+                ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn,
+                                   scaled_ws=self._get("x_scaled", tuple(rgb_pad.shape), torch.float32))
         else:
             import torch.distributed as dist
             # patch positions are independent (utils_vid.py:211-215): each rank searches a band of patch
@@ -229,7 +230,8 @@ class FusedLoopStep:
             r0, r1 = (desc.ho * self.rank) // self.world, (desc.ho * (self.rank + 1)) // self.world
             nn.zero_()
             with self._timed("patchnn_search"):
-                ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn, rows=(r0, r1))
+                ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn, rows=(r0, r1),
+                                   scaled_ws=self._get("x_scaled", tuple(rgb_pad.shape), torch.float32))
             dist.all_reduce(nn, group=self.group)
         grad_rgb = self._get("grad_rgb", (T + pad, 3, h, w), torch.float32)
         n_part = ops._lib.load().vl3d_vote_partials(T + pad, h, w)
