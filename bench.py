@@ -234,6 +234,8 @@ def run_ours(args):
     t0, t1 = (T * rank) // world, (T * (rank + 1)) // world
     model = build_model(wl, dev, t1 - t0, seed=2 + rank)
     margs = model.args
+    if args.no_smooth:
+        margs.rgb_smooth_loss_weight = margs.a_smooth_loss_weight = 0.0
     cfg = loss_config(margs, ref_view=True)
     ext, intr = view_for(wl)
     H, W = wl["H"], wl["W"]
@@ -371,6 +373,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="step720p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-smooth", action="store_true", help="tuning aid: drop the smoothness regularisers")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -101,12 +101,14 @@ int vl3d_composite_fwd(const vl3d_view* view, const vl3d_quad* quads, const floa
 /* Hand-written backward of the above (replaces autograd through MPV.py:413-451, utils_mpi.py:92-107
  * and MPV.py:517-531).  grad_rgb: (T + pad, 3, H, W) = dL/d rgb_out (pad frames folded in-kernel).
  * rgb: the forward's rgb_out.  w_smooth: 4 DEVICE floats dL/d(smooth_sums[i]), or NULL when the forward
- * ran without the regulariser pass (no host round trip of upstream scalars).
+ * ran without the regulariser pass (no host round trip of upstream scalars).  smooth_sums: optional 4
+ * doubles (ACCUMULATED) — the backward can emit the regulariser sums itself (it exchanges the same
+ * neighbour values anyway), which lets a fused step run the forward as a pure render.
  * grad_dyn (Tall,Hd,Wd,4) and grad_sta (Hs,Ws,4) are ACCUMULATED into (caller zeroes them). */
 int vl3d_composite_bwd(const vl3d_view* view, const vl3d_quad* quads, const float* atlas_dyn,
                        const float* atlas_sta, const int32_t* ts, int32_t T, int32_t pad,
                        const float* grad_rgb, const float* rgb, const float* w_smooth,
-                       float* grad_dyn, float* grad_sta, void* stream);
+                       double* smooth_sums, float* grad_dyn, float* grad_sta, void* stream);
 
 /* ---- scale-invariant gain (MPV.py:499-504):
  *      out[0] = (exp(mean_{c,h,w} log((mean_F res + .01)/(mean_T rgb + .01))) + 3) / 4

@@ -36,7 +36,7 @@ _SIGNATURES = {
     "vl3d_version": (C.c_int, []),
     "vl3d_last_error_string": (C.c_char_p, []),
     "vl3d_composite_fwd": (C.c_int, [C.POINTER(View), _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
-    "vl3d_composite_bwd": (C.c_int, [C.POINTER(View), _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "vl3d_composite_bwd": (C.c_int, [C.POINTER(View), _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "vl3d_scale_partials": (C.c_int, []),
     "vl3d_scale_invariant": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "vl3d_patchnn_search": (C.c_int, [C.POINTER(LossDesc), _P, _P, C.c_int32, C.c_int32, _P, _P]),

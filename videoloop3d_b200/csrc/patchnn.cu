@@ -223,8 +223,8 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
     float4* xs4 = reinterpret_cast<float4*>(smem);                  // [2][G4][XF]
     float4* ys4 = xs4 + 2 * G4 * XF;                                // [2][G4][CF]
     float* Gs = reinterpret_cast<float*>(ys4 + 2 * G4 * CF);        // [XF][CF+1]
-    float* Ds = Gs + XF * (CF + 1);                                 // [n1][CF]
-    float* colmin = Ds + (size_t)L.n1 * CF;                         // [CF]
+    float* Ds = Gs + XF * (CF + 1);                                 // [n1][CF+1]
+    float* colmin = Ds + (size_t)L.n1 * (CF + 1);                   // [CF]
     float* best_val = colmin + CF;                                  // [SL][n1]
     int* best_idx = reinterpret_cast<int*>(best_val + (size_t)P.SL * L.n1);
 
@@ -347,14 +347,14 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
                     const int gx = il * st, gy = jl * st;
                     float sum = 0.f;
                     for (int dt = 0; dt < pt; ++dt) sum += Gs[(gx + dt) * (CF + 1) + gy + dt];
-                    Ds[(size_t)il * CF + jl] = sum * inv_d;
+                    Ds[(size_t)il * (CF + 1) + jl] = sum * inv_d;
                 }
                 __syncthreads();
                 if (L.use_alpha) {
                     for (int jl = tid; jl < cj; jl += nthreads) {
                         float mn = INFINITY;
                         for (int i = 0; i < L.n1; ++i) {
-                            const float vv = Ds[(size_t)i * CF + jl];
+                            const float vv = Ds[(size_t)i * (CF + 1) + jl];
                             mn = (vv < mn || vv != vv) ? vv : mn;
                         }
                         colmin[jl] = L.alpha + mn;
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
                     float bv = best_val[kr * L.n1 + i];
                     int bi = best_idx[kr * L.n1 + i];
                     for (int jl = 0; jl < cj; ++jl) {
-                        float vv = Ds[(size_t)i * CF + jl];
+                        float vv = Ds[(size_t)i * (CF + 1) + jl];
                         if (L.use_alpha) vv = vv / colmin[jl];
                         const bool better = (vv < bv) || (vv != vv && bv == bv);
                         if (better) { bv = vv; bi = j0 + jl; }
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
 
 static size_t strip_smem_bytes(const vl3d_loss_desc* L, int nta, int ntb, int SL) {
     const int G4 = (3 * L->p + 3) / 4, XF = 4 * nta, CF = 4 * ntb;
-    size_t fl = (size_t)4 * 2 * G4 * (XF + CF) + (size_t)XF * (CF + 1) + (size_t)L->n1 * CF + CF + 2 * (size_t)SL * L->n1;
+    size_t fl = (size_t)4 * 2 * G4 * (XF + CF) + (size_t)XF * (CF + 1) + (size_t)L->n1 * (CF + 1) + CF + 2 * (size_t)SL * L->n1;
     return fl * sizeof(float);
 }
 
@@ -582,7 +582,7 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
     cudaStream_t st = (cudaStream_t)stream;
     const int tx_used = (desc->n1 - 1) * desc->st + desc->pt;
     const int M = desc->p / desc->s;
-    if (tx_used <= NN_CF && M <= 3) {
+    if (tx_used <= NN_CF && M <= 3 && desc->p <= 32) {
         // strip kernel: rows shared between vertically overlapping patches
         StripParams P{};
         P.d = *desc; P.x = x; P.y = y; P.nn = nn_out; P.groups = (3 * desc->p + 3) / 4;

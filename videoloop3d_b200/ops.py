@@ -97,10 +97,11 @@ def composite_fwd(view, pack, atlas_dyn, atlas_sta, ts, T, pad, rgb_out=None, wa
     return rgb_out, alpha, mpi, hits
 
 
-def composite_bwd(view, pack, atlas_dyn, atlas_sta, ts, T, pad, grad_rgb, rgb, w_smooth, grad_dyn, grad_sta):
+def composite_bwd(view, pack, atlas_dyn, atlas_sta, ts, T, pad, grad_rgb, rgb, w_smooth, grad_dyn, grad_sta,
+                  smooth_sums=None):
     _lib.call("vl3d_composite_bwd", C.byref(view), _lib.ptr(pack.quads), _lib.ptr(atlas_dyn), _lib.ptr(atlas_sta),
               _lib.ptr(ts), int(T), int(pad), _lib.ptr(grad_rgb), _lib.ptr(rgb), _lib.ptr(w_smooth),
-              _lib.ptr(grad_dyn), _lib.ptr(grad_sta), _lib.stream_ptr())
+              _lib.ptr(smooth_sums), _lib.ptr(grad_dyn), _lib.ptr(grad_sta), _lib.stream_ptr())
 
 
 def scale_invariant(rgb, T, res, out=None, partials=None):

@@ -187,17 +187,20 @@ class FusedLoopStep:
         rgb_pad = self._get("rgb_pad", (T + pad, 3, h, w), torch.float32)
         sums = self._get("sums", (4,), torch.float64)
         sums.zero_()
+        # with a backward pass coming, the regulariser sums are produced there (it exchanges the same
+        # neighbour values anyway) and the forward stays a pure render
+        fwd_sums = sums if (smooth and not optimise) else None
         dyn_local = atlas_dyn.data if self.local_model else atlas_dyn.data[t0:t1]
         if self.world == 1:
             with self._timed("composite_fwd"):
                 ops.composite_fwd(view, pack, dyn_local, atlas.data, None, T, pad, rgb_out=rgb_pad,
-                                  smooth_sums=sums if smooth else None)
+                                  smooth_sums=fwd_sums)
         else:
             import torch.distributed as dist
             # render the owned frames straight into their slot of the gathered video, then all-gather
             with self._timed("composite_fwd"):
                 ops.composite_fwd(view, pack, dyn_local, atlas.data, None, Tl, 0, rgb_out=rgb_pad[t0:t1],
-                                  smooth_sums=sums if smooth else None)
+                                  smooth_sums=fwd_sums)
             if len(set(b - a for a, b in zip(self.bounds[:-1], self.bounds[1:]))) == 1:
                 dist.all_gather_into_tensor(rgb_pad[:T], rgb_pad[t0:t1], group=self.group)
             else:
@@ -205,7 +208,7 @@ class FusedLoopStep:
                 dist.all_gather(parts, rgb_pad[t0:t1].clone(), group=self.group)
             if pad:
                 rgb_pad[T:T + pad].copy_(rgb_pad[:pad])                      # loop pad (MPV.py:490-492)
-            if smooth:
+            if fwd_sums is not None:
                 dist.all_reduce(sums, group=self.group)
 
         xscale = None
@@ -253,17 +256,20 @@ class FusedLoopStep:
                                         dtype=torch.float32, device=dev)
                 self._buf[key] = w_smooth
 
-        out = {"swd": loss_out[0] * gain}
-        total = out["swd"]
-        if wr > 0:
-            out["rgb_smooth"] = ((sums[0] / (3 * nx) + sums[1] / (3 * ny)) * gain).float()
-            total = total + out["rgb_smooth"] * wr
-        if wa > 0:
-            out["a_smooth"] = ((sums[2] / nx + sums[3] / ny) * gain).float()
-            total = total + out["a_smooth"] * wa
-        out["loss"] = total
-        if not optimise:
+        def assemble():
+            out = {"swd": loss_out[0] * gain}
+            total = out["swd"]
+            if wr > 0:
+                out["rgb_smooth"] = ((sums[0] / (3 * nx) + sums[1] / (3 * ny)) * gain).float()
+                total = total + out["rgb_smooth"] * wr
+            if wa > 0:
+                out["a_smooth"] = ((sums[2] / nx + sums[3] / ny) * gain).float()
+                total = total + out["a_smooth"] * wa
+            out["loss"] = total
             return out
+
+        if not optimise:
+            return assemble()
 
         # backward into persistent gradient buffers
         g_dyn = self._get("g_dyn", tuple(dyn_local.shape), torch.float32)
@@ -280,7 +286,7 @@ class FusedLoopStep:
         if self.world == 1:
             with self._timed("composite_bwd"):
                 ops.composite_bwd(view, pack, dyn_local, atlas.data, None, T, pad, grad_rgb, rgb_pad, w_smooth, g_dyn,
-                                  g_sta)
+                                  g_sta, smooth_sums=sums if smooth else None)
         else:
             import torch.distributed as dist
             # fold the loop-pad gradient onto frames 0..pad-1, then each rank back-propagates its own frames
@@ -288,15 +294,17 @@ class FusedLoopStep:
                 grad_rgb[:pad] += grad_rgb[T:T + pad]
             with self._timed("composite_bwd"):
                 ops.composite_bwd(view, pack, dyn_local, atlas.data, None, Tl, 0, grad_rgb[t0:t1], rgb_pad[t0:t1],
-                                  w_smooth, g_dyn, g_sta)
+                                  w_smooth, g_dyn, g_sta, smooth_sums=sums if smooth else None)
             if pack.n_static > 0:
                 dist.all_reduce(g_sta, group=self.group)                     # the one gradient all-reduce
+            if smooth:
+                dist.all_reduce(sums, group=self.group)
         self.t += 1
         with self._timed("adam"):
             self._adam("atlas_dyn", dyn_local, g_dyn, lr)
             if pack.n_static > 0:
                 self._adam("atlas", atlas.data, g_sta, lr)
-        return out
+        return assemble()
 
 
 class _Timed:
