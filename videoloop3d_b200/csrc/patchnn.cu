@@ -214,7 +214,7 @@ __device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int M>
+template <int M, bool VEC>
 __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_constant__ StripParams P) {
     extern __shared__ __align__(16) float smem[];
     const vl3d_loss_desc& L = P.d;
@@ -245,7 +245,11 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
     for (int i = tid; i < (k1 - k0) * L.n1; i += nthreads) { best_val[i] = INFINITY; best_idx[i] = 0; }
 
     // asynchronous global -> shared staging of one pixel row of the window (3 channels, all frames):
-    // LDGSTS, no register round trip; frames beyond the video are zero-filled
+    // LDGSTS, no register round trip; frames beyond the video are zero-filled.
+    //  VEC: 16-byte copies.  Elements are laid out channel-padded (e = c*P4 + dx, P4 = 4*ceil(p/4)), so a
+    //       run of p pixels is P4/4 aligned chunks; the tail chunk copies 4*(p%4) bytes and zero-fills.
+    //       Needs 16-byte aligned runs (stride % 4 == 0, strides % 4 == 0; host-checked).
+    //  else: 4-byte copies, elements packed e = c*p + dx.
     auto stage = [&](int c0, int row, int buf) {
         const int nx = 3 * XF, ny = 3 * CF;
         for (int id = tid; id < nx + ny; id += nthreads) {
@@ -253,20 +257,30 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
             const int q = isy ? id - nx : id;
             const int nf = isy ? CF : XF;
             const int c = q / nf, fr = q - c * nf;
-            float* dst = reinterpret_cast<float*>(isy ? ys4 + (size_t)buf * G4 * CF : xs4 + (size_t)buf * G4 * XF);
             const int gf = isy ? c0 + fr : fr;
             const bool ok = gf < (isy ? ty_used : tx_used);
             const int gfc = ok ? gf : 0;
             const float* src = isy ? P.y + (size_t)gfc * L.y_sf + (size_t)c * L.y_sc + (size_t)(ybase + row) * L.y_sr + x0
                                    : P.x + (size_t)gfc * L.x_sf + (size_t)c * L.x_sc + (size_t)(ybase + row) * L.x_sr + x0;
-            float* d0 = dst + fr * 4;
-            int e = c * p;
-            for (int dx = 0; dx < p; ++dx, ++e) cp_async_f32(d0 + (e >> 2) * (nf * 4) + (e & 3), src + dx, ok);
+            if (VEC) {
+                const int nch = (p + 3) >> 2;
+                float4* d4 = (isy ? ys4 + (size_t)buf * G4 * CF : xs4 + (size_t)buf * G4 * XF) + (size_t)c * nch * nf + fr;
+                for (int j = 0; j < nch; ++j) {
+                    const int nval = ok ? min(4, p - 4 * j) * 4 : 0;
+                    const unsigned d = (unsigned)__cvta_generic_to_shared(d4 + (size_t)j * nf);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src + 4 * j), "r"(nval) : "memory");
+                }
+            } else {
+                float* dst = reinterpret_cast<float*>(isy ? ys4 + (size_t)buf * G4 * CF : xs4 + (size_t)buf * G4 * XF);
+                float* d0 = dst + fr * 4;
+                int e = c * p;
+                for (int dx = 0; dx < p; ++dx, ++e) cp_async_f32(d0 + (e >> 2) * (nf * 4) + (e & 3), src + dx, ok);
+            }
         }
         cp_async_commit();
     };
-    // padding lanes of the last float4 group never change: zero them once in both buffers
-    {
+    // packed layout: the padding lanes of the last float4 group never change; zero them once in both buffers
+    if (!VEC) {
         const int npad = 4 * G4 - 3 * p;
         for (int id = tid; id < 2 * npad * (XF + CF); id += nthreads) {
             const int buf = id / (npad * (XF + CF));
@@ -612,8 +626,15 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
         const size_t smem = strip_smem_bytes(desc, P.nta, P.ntb, SL);
         VL3D_REQUIRE(smem <= 200 * 1024, VL3D_ERANGE, "patch_size %d / n1 %d need %zu B of shared memory", desc->p,
                      desc->n1, smem);
-        void (*kern)(StripParams) = M == 0 ? patchnn_strip_kernel<0> : M == 1 ? patchnn_strip_kernel<1>
-                                  : M == 2 ? patchnn_strip_kernel<2> : patchnn_strip_kernel<3>;
+        const int P4 = (desc->p + 3) / 4 * 4;
+        const bool vec = desc->s % 4 == 0 && (3 * desc->p + 3) / 4 == 3 * P4 / 4 &&
+                         ((desc->x_sf | desc->x_sc | desc->x_sr | desc->y_sf | desc->y_sc | desc->y_sr) & 3) == 0 &&
+                         (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+        void (*kern)(StripParams) =
+            vec ? (M == 0 ? patchnn_strip_kernel<0, true> : M == 1 ? patchnn_strip_kernel<1, true>
+                 : M == 2 ? patchnn_strip_kernel<2, true> : patchnn_strip_kernel<3, true>)
+                : (M == 0 ? patchnn_strip_kernel<0, false> : M == 1 ? patchnn_strip_kernel<1, false>
+                 : M == 2 ? patchnn_strip_kernel<2, false> : patchnn_strip_kernel<3, false>);
         cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (ce != cudaSuccess) return set_err((int)ce, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
         dim3 grid(desc->wo, (rows + SL - 1) / SL);
