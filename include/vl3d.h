@@ -130,14 +130,16 @@ int vl3d_scale_video(const float* x, const float* xscale, float* out, int64_t n,
  *   (utils_vid.py:217-229, 344-348, 10-26).  rou_kind: 0 general float rou, 1 'mse', 2 'abs'.
  *   y2x_out (3,t,h,w)/weight_out (t,h,w) optional (last_y2x / last_weight caches).
  *   grad_out: (Tx_full, 3, Hfull, Wfull) = gcoef * xscale * rho'(x*xscale - y2x) / N inside the
- *   fitted crop, 0 outside (optional).  loss_out[0] = mean rho (1 float). partials: workspace of
+ *   fitted crop, 0 outside (optional).  Only frames [frame_begin, frame_end) of x are processed (ranks
+ *   split the frames); loss_out[0] = (sum of rho over those frames) / N_total, so partial results add up
+ *   to the mean. partials: workspace of
  *   >= vl3d_vote_partials(Tx_full, Hfull, Wfull) doubles. */
 int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, const float* y,
                         int32_t row_begin, int32_t row_end, int32_t* nn_out, void* stream);
 int vl3d_vote_partials(int32_t Tx_full, int32_t Hfull, int32_t Wfull);
 int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const float* xscale, const float* y,
                    const int32_t* nn, int32_t rou_kind, float rou, float scaling, float gcoef,
-                   int32_t Tx_full, int32_t Hfull, int32_t Wfull,
+                   int32_t Tx_full, int32_t Hfull, int32_t Wfull, int32_t frame_begin, int32_t frame_end,
                    float* y2x_out, float* weight_out, float* grad_out, double* partials, float* loss_out,
                    void* stream);
 

@@ -1,0 +1,80 @@
+"""N>1 host logic on CPU (gloo, world_size 2) + the multi-GPU equivalence check (needs >= 2 GPUs)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from videoloop3d_b200.train_step import owned_frame_ranges, partition
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_partitions_cover_everything_once():
+    for n, world in [(48, 1), (48, 2), (48, 8), (50, 4), (7, 3), (43, 8)]:
+        b = partition(n, world)
+        assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(world))
+        assert sum(b[i + 1] - b[i] for i in range(world)) == n
+    # every frame of the padded video is owned by exactly one rank
+    for T, pad, world in [(48, 2, 8), (48, 2, 1), (6, 2, 4), (7, 4, 3)]:
+        b = partition(T, world)
+        seen = []
+        for r in range(world):
+            for lo, hi in owned_frame_ranges(b, r, T, pad):
+                seen += list(range(lo, hi))
+        assert sorted(seen) == list(range(T + pad))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # the collective pattern of FusedLoopStep on CPU tensors: all-gather rendered frames into their slots,
+        # sum the disjoint NN row bands, all-reduce the 5 partial sums
+        T, pad, h, w, ho = 6, 2, 3, 4, 5
+        b = partition(T, world)
+        t0, t1 = b[rank], b[rank + 1]
+        video = torch.zeros(T + pad, 3, h, w)
+        truth = torch.arange(T * 3 * h * w, dtype=torch.float32).reshape(T, 3, h, w)
+        video[t0:t1] = truth[t0:t1]
+        dist.all_gather_into_tensor(video[:T], video[t0:t1].clone())
+        video[T:T + pad] = video[:pad]
+        rows = partition(ho, world)
+        nn = torch.zeros(ho, 2, 3, dtype=torch.int32)
+        nn[rows[rank]:rows[rank + 1]] = rank + 7
+        dist.all_reduce(nn)
+        sums = torch.tensor([1.0, 2.0, 3.0, 4.0, float(rank + 1)], dtype=torch.float64)
+        dist.all_reduce(sums)
+        ok = torch.equal(video[:T], truth) and torch.equal(video[T:], truth[:pad])
+        ok &= all(int(nn[r, 0, 0]) == 7 + (0 if r < rows[1] else 1) for r in range(ho))
+        ok &= sums.tolist() == [2.0, 4.0, 6.0, 8.0, 3.0]
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_collective_pattern_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, 29533, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = dict(q.get(timeout=10) for _ in range(2))
+    assert got == {0: True, 1: True}
+
+
+@pytest.mark.gpu
+def test_sharded_step_equals_single_gpu_step():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run scripts/check_sharded.py under gpurun --gpus 2)")
+    n = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+           "127.0.0.1", "--master-port", "29544", os.path.join(ROOT, "scripts", "check_sharded.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr

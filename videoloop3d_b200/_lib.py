@@ -43,7 +43,7 @@ _SIGNATURES = {
     "vl3d_scale_video": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "vl3d_vote_partials": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     "vl3d_vote_loss": (C.c_int, [C.POINTER(LossDesc), _P, _P, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_float,
-                                 C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
+                                 C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "vl3d_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)

@@ -423,6 +423,7 @@ struct VoteParams {
     const float* x; const float* xscale; const float* y; const int* nn;
     int rou_kind; float rou, scaling, gcoef;
     int Tx_full, Hfull, Wfull;
+    int f0;                     // first frame handled by this launch
     float* y2x; float* weight; float* grad; double* partials; float* loss;
 };
 
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) vote_loss_kernel(const __grid_co
     const vl3d_loss_desc& L = P.d;
     // frames vary fastest across the grid: the CTAs of one 32x8 pixel tile for all frames are co-resident, so
     // the target-video tile they gather from (all F frames, ~0.8 MB) is read from HBM once and then hit in L2
-    const int tf = blockIdx.x;
+    const int tf = P.f0 + blockIdx.x;
     const int px = blockIdx.y * 32 + (threadIdx.x & 31);
     const int py = blockIdx.z * 8 + (threadIdx.x >> 5);
     float lsum = 0.f;
@@ -664,18 +665,21 @@ extern "C" int vl3d_vote_partials(int32_t Tx_full, int32_t Hfull, int32_t Wfull)
 
 extern "C" int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const float* xscale, const float* y,
                               const int32_t* nn, int32_t rou_kind, float rou, float scaling, float gcoef,
-                              int32_t Tx_full, int32_t Hfull, int32_t Wfull, float* y2x_out, float* weight_out,
-                              float* grad_out, double* partials, float* loss_out, void* stream) {
+                              int32_t Tx_full, int32_t Hfull, int32_t Wfull, int32_t frame_begin, int32_t frame_end,
+                              float* y2x_out, float* weight_out, float* grad_out, double* partials, float* loss_out,
+                              void* stream) {
     if (int e = validate_desc(desc)) return e;
     VL3D_REQUIRE(x && y && nn && partials && loss_out, VL3D_ENULL, "required pointer is NULL");
     VL3D_REQUIRE(Tx_full >= desc->t && Hfull >= desc->h && Wfull >= desc->w, VL3D_EINVAL, "full dims smaller than the crop");
     VL3D_REQUIRE(rou_kind >= 0 && rou_kind <= 2, VL3D_EINVAL, "rou_kind %d", rou_kind);
-    dim3 grid = vote_grid(desc, Tx_full, Hfull, Wfull);
+    VL3D_REQUIRE(frame_begin >= 0 && frame_begin < frame_end && frame_end <= Tx_full, VL3D_EINVAL,
+                 "bad frame range [%d,%d)", frame_begin, frame_end);
+    dim3 grid = vote_grid(desc, frame_end - frame_begin, Hfull, Wfull);
     const int nblocks = grid.x * grid.y * grid.z;
     VoteParams P{};
     P.d = *desc; P.x = x; P.xscale = xscale; P.y = y; P.nn = nn;
     P.rou_kind = rou_kind; P.rou = rou; P.scaling = scaling; P.gcoef = gcoef;
-    P.Tx_full = Tx_full; P.Hfull = Hfull; P.Wfull = Wfull;
+    P.Tx_full = Tx_full; P.Hfull = Hfull; P.Wfull = Wfull; P.f0 = frame_begin;
     P.y2x = y2x_out; P.weight = weight_out; P.grad = grad_out; P.partials = partials; P.loss = loss_out;
     cudaStream_t st = (cudaStream_t)stream;
     vote_loss_kernel<<<grid, VOTE_THREADS, 0, st>>>(P);

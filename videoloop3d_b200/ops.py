@@ -191,7 +191,7 @@ def parse_rou(rou):
 
 
 def vote_loss(desc, x, xscale, y, nn, rou, scaling, gcoef, full_shape, want_cache=False, grad_out=None,
-              want_grad=True, partials=None, loss_out=None):
+              want_grad=True, partials=None, loss_out=None, frames=None):
     Tx, Hf, Wf = full_shape
     dev = x.device
     kind, rouf = parse_rou(rou)
@@ -206,7 +206,7 @@ def vote_loss(desc, x, xscale, y, nn, rou, scaling, gcoef, full_shape, want_cach
         loss_out = torch.empty(1, dtype=torch.float32, device=dev)
     _lib.call("vl3d_vote_loss", C.byref(desc), _lib.ptr(x), _lib.ptr(xscale), _lib.ptr(y), _lib.ptr(nn),
               int(kind), float(rouf), float(scaling), float(gcoef), int(Tx), int(Hf), int(Wf),
-              _lib.ptr(y2x), _lib.ptr(wgt), _lib.ptr(grad_out if want_grad else None), _lib.ptr(partials),
+              int(0 if frames is None else frames[0]), int(Tx if frames is None else frames[1]), _lib.ptr(y2x), _lib.ptr(wgt), _lib.ptr(grad_out if want_grad else None), _lib.ptr(partials),
               _lib.ptr(loss_out), _lib.stream_ptr())
     return loss_out, grad_out, y2x, wgt
 

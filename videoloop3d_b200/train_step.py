@@ -92,15 +92,35 @@ def make_run_iter(args, nerf, device, writer=None, on_log=None):
     return run_iter
 
 
+def partition(n, world):
+    """Contiguous blocks [b[r], b[r+1]) of n units over `world` ranks."""
+    return [(n * r) // world for r in range(world + 1)]
+
+
+def owned_frame_ranges(bounds, rank, T, pad):
+    """Frame ranges of the padded video x = cat(rgb, rgb[:pad]) whose loss gradient a rank needs:
+    its own frames [t0,t1) and the looped copies T+t of the frames t < pad it owns (MPV.py:490-492)."""
+    t0, t1 = bounds[rank], bounds[rank + 1]
+    out = [(t0, t1)]
+    if t0 < pad:
+        out.append((T + t0, T + min(t1, pad)))
+    return out
+
+
 class FusedLoopStep:
     """render + looping loss + backward + Adam for one (view, patch) item, fused and sync-free.
 
     step(h, w, tar_extrin (1,4,4), tar_intrin (1,3,3), res (1,F,3,h,w) on device, losscfg (un-batched dict), lr)
     returns a dict of device scalars {'loss','swd','rgb_smooth','a_smooth'} (no host sync).
 
-    With `group` (a torch.distributed process group, world size G) the T frames are sharded in
-    contiguous blocks: this rank owns frames [t0, t1) of `atlas_dyn` (parameters, gradients and Adam
-    state of other frames are never touched here).
+    With `group` (a torch.distributed process group, world size G) the work is sharded:
+      * frames: rank r owns the contiguous block [t0,t1) of `atlas_dyn` — it renders, back-propagates and
+        optimises only those frames (parameters / gradients / Adam state of other frames never move);
+        `global_frames=T` means the model on this rank holds ONLY its own block (memory-sharded);
+      * one all-gather of the rendered frames (temporal patches, loop pad and the scale-invariant mean need
+        the whole video), patch rows of the NN search split across ranks + one all-reduce of the int32 index
+        map, the loss/regulariser partial sums all-reduced as 5 doubles;
+      * static-tile gradients all-reduced (SUM) — the single gradient collective.
     """
 
     def __init__(self, model: MPMeshVid, group=None, betas=(0.9, 0.999), eps=6e-8, global_frames=None, timers=False):
@@ -116,14 +136,11 @@ class FusedLoopStep:
         if group is not None:
             import torch.distributed as dist
             self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        # `global_frames`: the model on this rank holds ONLY its own block of frames (memory-sharded);
-        # otherwise every rank holds all T frames and touches only its block.
         self.local_model = global_frames is not None
         T = int(global_frames) if self.local_model else model.atlas_dyn.shape[0]
         self.T = T
-        bounds = [(T * r) // self.world for r in range(self.world + 1)]
-        self.bounds = bounds
-        self.t0, self.t1 = bounds[self.rank], bounds[self.rank + 1]
+        self.bounds = partition(T, self.world)
+        self.t0, self.t1 = self.bounds[self.rank], self.bounds[self.rank + 1]
         if self.t1 <= self.t0:
             raise Vl3dError(f"rank {self.rank} owns no frames (T={T}, world={self.world})")
         if self.local_model and model.atlas_dyn.shape[0] != self.t1 - self.t0:
@@ -147,10 +164,17 @@ class FusedLoopStep:
         self.t = 0
         self._state = {}
 
-    def _get(self, key, shape, dtype, zero=False):
+    def _get(self, key, shape, dtype):
         b = self._buf.get(key)
         if b is None or tuple(b.shape) != tuple(shape) or b.dtype != dtype:
-            b = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.model.atlas_dyn.device)
+            b = torch.empty(shape, dtype=dtype, device=self.model.atlas_dyn.device)
+            self._buf[key] = b
+        return b
+
+    def _like(self, key, ref):
+        b = self._buf.get(key)
+        if b is None or b.shape != ref.shape or tuple(b.stride()) != tuple(ref.stride()):
+            b = torch.empty_like(ref)
             self._buf[key] = b
         return b
 
@@ -166,6 +190,9 @@ class FusedLoopStep:
         m = self.model
         args = m.args
         dev = m.atlas_dyn.device
+        dist = None
+        if self.world > 1:
+            import torch.distributed as dist
         atlas_dyn, atlas = m._texels()
         cfg = dict(losscfg)
         loss_name = cfg.pop("loss_name")
@@ -176,41 +203,42 @@ class FusedLoopStep:
         T, t0, t1 = self.T, self.t0, self.t1
         Tl = t1 - t0
         pad = m.swd_patcht_size - 1 if m.isloop else 0
+        if pad > T:
+            raise ValueError("loop pad longer than the video")
         res0 = res[0] if res.dim() == 5 else res
         if not res0.is_contiguous():
             res0 = res0.contiguous()
         ext = tar_extrin.reshape(4, 4).double().cpu().numpy() @ np.linalg.inv(m.ref_extrin.double().cpu().numpy())
         view = m.make_view(h, w, ext, tar_intrin)
         pack = m._pack
-        smooth = args.rgb_smooth_loss_weight > 0 or args.a_smooth_loss_weight > 0
-
-        rgb_pad = self._get("rgb_pad", (T + pad, 3, h, w), torch.float32)
-        sums = self._get("sums", (4,), torch.float64)
-        sums.zero_()
-        # with a backward pass coming, the regulariser sums are produced there (it exchanges the same
-        # neighbour values anyway) and the forward stays a pure render
-        fwd_sums = sums if (smooth and not optimise) else None
+        wr, wa = args.rgb_smooth_loss_weight, args.a_smooth_loss_weight
+        smooth = wr > 0 or wa > 0
         dyn_local = atlas_dyn.data if self.local_model else atlas_dyn.data[t0:t1]
-        if self.world == 1:
-            with self._timed("composite_fwd"):
-                ops.composite_fwd(view, pack, dyn_local, atlas.data, None, T, pad, rgb_out=rgb_pad,
-                                  smooth_sums=fwd_sums)
-        else:
-            import torch.distributed as dist
-            # render the owned frames straight into their slot of the gathered video, then all-gather
-            with self._timed("composite_fwd"):
+
+        # ---- render.  With a backward pass coming the regulariser sums are produced there (it exchanges the
+        # same neighbour values anyway) and the forward stays a pure render.
+        rgb_pad = self._get("rgb_pad", (T + pad, 3, h, w), torch.float32)
+        sums = self._get("sums", (5,), torch.float64)             # 4 regulariser sums + the loss partial
+        sums.zero_()
+        fwd_sums = sums[:4] if (smooth and not optimise) else None
+        with self._timed("composite_fwd"):
+            if self.world == 1:
+                ops.composite_fwd(view, pack, dyn_local, atlas.data, None, T, pad, rgb_out=rgb_pad, smooth_sums=fwd_sums)
+            else:
                 ops.composite_fwd(view, pack, dyn_local, atlas.data, None, Tl, 0, rgb_out=rgb_pad[t0:t1],
                                   smooth_sums=fwd_sums)
-            if len(set(b - a for a, b in zip(self.bounds[:-1], self.bounds[1:]))) == 1:
-                dist.all_gather_into_tensor(rgb_pad[:T], rgb_pad[t0:t1], group=self.group)
-            else:
-                parts = [rgb_pad[a:b] for a, b in zip(self.bounds[:-1], self.bounds[1:])]
-                dist.all_gather(parts, rgb_pad[t0:t1].clone(), group=self.group)
-            if pad:
-                rgb_pad[T:T + pad].copy_(rgb_pad[:pad])                      # loop pad (MPV.py:490-492)
-            if fwd_sums is not None:
-                dist.all_reduce(sums, group=self.group)
+        if self.world > 1:
+            with self._timed("allgather_rgb"):
+                sizes = {b - a for a, b in zip(self.bounds[:-1], self.bounds[1:])}
+                if len(sizes) == 1:
+                    dist.all_gather_into_tensor(rgb_pad[:T], rgb_pad[t0:t1], group=self.group)
+                else:
+                    parts = [rgb_pad[a:b] for a, b in zip(self.bounds[:-1], self.bounds[1:])]
+                    dist.all_gather(parts, rgb_pad[t0:t1].clone(), group=self.group)
+                if pad:
+                    rgb_pad[T:T + pad].copy_(rgb_pad[:pad])          # loop pad (MPV.py:490-492)
 
+        # ---- looping loss
         xscale = None
         if args.scale_invariant:
             with self._timed("scale_invariant"):
@@ -222,32 +250,35 @@ class FusedLoopStep:
                                   cfg["patcht_size"], cfg["stride"], cfg["stridet"], cfg.get("alpha", 1e10),
                                   fit=lossobj.fit)
         nn = self._get("nn", (desc.ho, desc.wo, desc.n1), torch.int32)
+        x_scaled = self._get("x_scaled", tuple(rgb_pad.shape), torch.float32)
         if self.world == 1:
             with self._timed("patchnn_search"):
-                ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn,
-                                   scaled_ws=self._get("x_scaled", tuple(rgb_pad.shape), torch.float32))
+                ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn, scaled_ws=x_scaled)
         else:
-            import torch.distributed as dist
-            # patch positions are independent (utils_vid.py:211-215): each rank searches a band of patch
-            # rows, then the int32 index map is summed across ranks (disjoint rows, zeros elsewhere)
-            r0, r1 = (desc.ho * self.rank) // self.world, (desc.ho * (self.rank + 1)) // self.world
+            # patch positions are independent (utils_vid.py:211-215): each rank searches a band of patch rows,
+            # then the int32 index map is summed across ranks (disjoint rows, zeros elsewhere)
+            rows = partition(desc.ho, self.world)
             nn.zero_()
             with self._timed("patchnn_search"):
-                ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn, rows=(r0, r1),
-                                   scaled_ws=self._get("x_scaled", tuple(rgb_pad.shape), torch.float32))
-            dist.all_reduce(nn, group=self.group)
+                ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn, rows=(rows[self.rank], rows[self.rank + 1]),
+                                   scaled_ws=x_scaled)
+            with self._timed("allreduce_nn"):
+                dist.all_reduce(nn, group=self.group)
         grad_rgb = self._get("grad_rgb", (T + pad, 3, h, w), torch.float32)
         n_part = ops._lib.load().vl3d_vote_partials(T + pad, h, w)
+        vote_part = self._get("vote_part", (n_part,), torch.float64)
         with self._timed("vote_loss"):
-            loss_out, _, _, _ = ops.vote_loss(desc, rgb_pad, xscale, res0, nn, cfg.get("rou", 0),
-                                              cfg.get("scaling", 0.2), gain, (T + pad, h, w), grad_out=grad_rgb,
-                                              partials=self._get("vote_part", (n_part,), torch.float64),
-                                              loss_out=self._get("loss_out", (1,), torch.float32))
+            ranges = [(0, T + pad)] if self.world == 1 else owned_frame_ranges(self.bounds, self.rank, T, pad)
+            for i, fr in enumerate(ranges):
+                lo = self._get(f"loss_out{i}", (1,), torch.float32)
+                ops.vote_loss(desc, rgb_pad, xscale, res0, nn, cfg.get("rou", 0), cfg.get("scaling", 0.2), gain,
+                              (T + pad, h, w), grad_out=grad_rgb, partials=vote_part, loss_out=lo, frames=fr)
+                sums[4] += lo[0]
+
         # d total / d smooth_sums (host constants): MPV.py:517-531 with K cancelled, train_3dvid.py:230-240
-        w_smooth = None
         nx = max(T * h * (w - 1), 1) * m.mpi_d
         ny = max(T * (h - 1) * w, 1) * m.mpi_d
-        wr, wa = args.rgb_smooth_loss_weight, args.a_smooth_loss_weight
+        w_smooth = None
         if smooth:
             key = ("w_smooth", T, h, w, gain, wr, wa)
             w_smooth = self._buf.get(key)
@@ -257,7 +288,9 @@ class FusedLoopStep:
                 self._buf[key] = w_smooth
 
         def assemble():
-            out = {"swd": loss_out[0] * gain}
+            if self.world > 1:
+                dist.all_reduce(sums, group=self.group)              # 5 doubles: regulariser sums + loss partials
+            out = {"swd": (sums[4] * gain).float()}
             total = out["swd"]
             if wr > 0:
                 out["rgb_smooth"] = ((sums[0] / (3 * nx) + sums[1] / (3 * ny)) * gain).float()
@@ -271,34 +304,26 @@ class FusedLoopStep:
         if not optimise:
             return assemble()
 
-        # backward into persistent gradient buffers
-        g_dyn = self._get("g_dyn", tuple(dyn_local.shape), torch.float32)
-        if tuple(g_dyn.stride()) != tuple(dyn_local.stride()):
-            g_dyn = torch.empty_like(dyn_local)
-            self._buf["g_dyn"] = g_dyn
-        g_sta = self._buf.get("g_sta")
-        if g_sta is None or g_sta.shape != atlas.shape or tuple(g_sta.stride()) != tuple(atlas.stride()):
-            g_sta = torch.empty_like(atlas.data)
-            self._buf["g_sta"] = g_sta
+        # ---- backward into persistent gradient buffers, then Adam on the owned frames
+        g_dyn = self._like("g_dyn", dyn_local)
+        g_sta = self._like("g_sta", atlas.data)
         with self._timed("grad_zero"):
             g_dyn.zero_()
             g_sta.zero_()
-        if self.world == 1:
-            with self._timed("composite_bwd"):
+        bwd_sums = sums[:4] if smooth else None
+        with self._timed("composite_bwd"):
+            if self.world == 1:
                 ops.composite_bwd(view, pack, dyn_local, atlas.data, None, T, pad, grad_rgb, rgb_pad, w_smooth, g_dyn,
-                                  g_sta, smooth_sums=sums if smooth else None)
-        else:
-            import torch.distributed as dist
-            # fold the loop-pad gradient onto frames 0..pad-1, then each rank back-propagates its own frames
-            if pad:
-                grad_rgb[:pad] += grad_rgb[T:T + pad]
-            with self._timed("composite_bwd"):
+                                  g_sta, smooth_sums=bwd_sums)
+            else:
+                if t0 < pad:                                         # adjoint of the loop pad for the frames we own
+                    n = min(t1, pad) - t0
+                    grad_rgb[t0:t0 + n] += grad_rgb[T + t0:T + t0 + n]
                 ops.composite_bwd(view, pack, dyn_local, atlas.data, None, Tl, 0, grad_rgb[t0:t1], rgb_pad[t0:t1],
-                                  w_smooth, g_dyn, g_sta, smooth_sums=sums if smooth else None)
-            if pack.n_static > 0:
-                dist.all_reduce(g_sta, group=self.group)                     # the one gradient all-reduce
-            if smooth:
-                dist.all_reduce(sums, group=self.group)
+                                  w_smooth, g_dyn, g_sta, smooth_sums=bwd_sums)
+        if self.world > 1 and pack.n_static > 0:
+            with self._timed("allreduce_static_grad"):
+                dist.all_reduce(g_sta, group=self.group)             # the one gradient all-reduce
         self.t += 1
         with self._timed("adam"):
             self._adam("atlas_dyn", dyn_local, g_dyn, lr)
