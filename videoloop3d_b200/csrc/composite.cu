@@ -42,7 +42,7 @@ struct CompositeParams {
     float4* grad_dyn;
     float4* grad_sta;
     const float* w_smooth;
-    int dbg_nored;   // tuning aid: skip the texel REDs (VL3D_BWD_NORED=1); results are then wrong
+    int dbg_nored;   // tuning aids (results are then wrong): bit0 skip REDs, bit1 skip sign maths, bit2 skip sums, bit3 skip exchange
 };
 
 // quad-grid coordinates of pixel (u, v) on plane with homography h; false if behind / outside.
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(BX* BY) composite_bwd_kernel(const __grid_cons
         float4 gs[TF];   // dL/d(activated value) from the smoothness terms
 #pragma unroll
         for (int f = 0; f < TF; ++f) gs[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (SMOOTH) {
+        if (SMOOTH && !(p.dbg_nored & 8)) {
             const int buf = k & 1;
 #pragma unroll
             for (int f = 0; f < TF; ++f) s_ex[buf][f][ty][tx] = val[f];
@@ -579,11 +579,13 @@ __global__ void __launch_bounds__(BX* BY) composite_bwd_kernel(const __grid_cons
                 const float dxr = c.x - r.x, dyr = c.y - r.y, dzr = c.z - r.z, dwr = c.w - r.w;
                 const float dxd = c.x - dn.x, dyd = c.y - dn.y, dzd = c.z - dn.z, dwd = c.w - dn.w;
                 // d|a-b|/da = sign(a-b);  the pair (left, this) contributes -sign(left - this) = sign(this - left)
+                if (!(p.dbg_nored & 2)) {
                 gs[f].x = wsign(wr_c, dxr) + wsign(wl_c, c.x - l.x) + wsign(wd_c, dxd) + wsign(wu_c, c.x - up.x);
                 gs[f].y = wsign(wr_c, dyr) + wsign(wl_c, c.y - l.y) + wsign(wd_c, dyd) + wsign(wu_c, c.y - up.y);
                 gs[f].z = wsign(wr_c, dzr) + wsign(wl_c, c.z - l.z) + wsign(wd_c, dzd) + wsign(wu_c, c.z - up.z);
                 gs[f].w = wsign(wr_a, dwr) + wsign(wl_a, c.w - l.w) + wsign(wd_a, dwd) + wsign(wu_a, c.w - up.w);
-                if (p.smooth != nullptr) {                         // the regulariser values themselves (MPV.py:517-531)
+                } else { gs[f].x = dxr + l.x + up.x; gs[f].y = dyd; gs[f].z = dzr; gs[f].w = dwd + dwr; }
+                if (p.smooth != nullptr && !(p.dbg_nored & 4)) {                         // the regulariser values themselves (MPV.py:517-531)
                     sxr = fmaf(mx, fabsf(dxr) + fabsf(dyr) + fabsf(dzr), sxr);
                     sxa = fmaf(mx, fabsf(dwr), sxa);
                     syr = fmaf(my, fabsf(dxd) + fabsf(dyd) + fabsf(dzd), syr);
@@ -633,7 +635,7 @@ __global__ void __launch_bounds__(BX* BY) composite_bwd_kernel(const __grid_cons
             i1.z = __shfl_up_sync(0xffffffffu, r1.z, 1); i1.w = __shfl_up_sync(0xffffffffu, r1.w, 1);
             if (recv0) { l0.x += i0.x; l0.y += i0.y; l0.z += i0.z; l0.w += i0.w; }
             if (recv1) { l1.x += i1.x; l1.y += i1.y; l1.z += i1.z; l1.w += i1.w; }
-            if (dynf && !p.dbg_nored) {
+            if (dynf && !(p.dbg_nored & 1)) {
                 float4* gb = p.grad_dyn + foff[f];
                 red_add_v4(gb + tp.o00, l0);
                 red_add_v4(gb + tp.o01, l1);

@@ -123,7 +123,8 @@ class FusedLoopStep:
       * static-tile gradients all-reduced (SUM) — the single gradient collective.
     """
 
-    def __init__(self, model: MPMeshVid, group=None, betas=(0.9, 0.999), eps=6e-8, global_frames=None, timers=False):
+    def __init__(self, model: MPMeshVid, group=None, betas=(0.9, 0.999), eps=6e-8, global_frames=None, timers=False,
+                 overlap_chunks=1):
         if not model.atlas_dyn.is_cuda:
             raise Vl3dError("FusedLoopStep needs the model on a CUDA device")
         self.model = model
@@ -146,6 +147,11 @@ class FusedLoopStep:
         if self.local_model and model.atlas_dyn.shape[0] != self.t1 - self.t0:
             raise Vl3dError(f"memory-sharded model must hold {self.t1 - self.t0} frames, has {model.atlas_dyn.shape[0]}")
         self.timers = {} if timers else None
+        # optional: pipeline backward / Adam over `overlap_chunks` frame chunks on two streams.  Measured on
+        # B200 at 720p: no gain (both contend for the L2/HBM path; the backward slows down by what Adam
+        # gains), so the default is 1 (off).
+        self.overlap_chunks = max(1, int(overlap_chunks))
+        self._side = torch.cuda.Stream(device=model.atlas_dyn.device)
 
     def _timed(self, name):
         return _Timed(self.timers, name)
@@ -307,27 +313,47 @@ class FusedLoopStep:
         # ---- backward into persistent gradient buffers, then Adam on the owned frames
         g_dyn = self._like("g_dyn", dyn_local)
         g_sta = self._like("g_sta", atlas.data)
-        with self._timed("grad_zero"):
-            g_dyn.zero_()
+        main = torch.cuda.current_stream()
+        with self._timed("grad_zero"):      # (overlapping this memset with the NN search on a side stream was
+            g_dyn.zero_()                   #  measured to give nothing: the search slows down by the same amount)
             g_sta.zero_()
         bwd_sums = sums[:4] if smooth else None
-        with self._timed("composite_bwd"):
-            if self.world == 1:
-                ops.composite_bwd(view, pack, dyn_local, atlas.data, None, T, pad, grad_rgb, rgb_pad, w_smooth, g_dyn,
-                                  g_sta, smooth_sums=bwd_sums)
-            else:
-                if t0 < pad:                                         # adjoint of the loop pad for the frames we own
-                    n = min(t1, pad) - t0
-                    grad_rgb[t0:t0 + n] += grad_rgb[T + t0:T + t0 + n]
-                ops.composite_bwd(view, pack, dyn_local, atlas.data, None, Tl, 0, grad_rgb[t0:t1], rgb_pad[t0:t1],
-                                  w_smooth, g_dyn, g_sta, smooth_sums=bwd_sums)
-        if self.world > 1 and pack.n_static > 0:
-            with self._timed("allreduce_static_grad"):
-                dist.all_reduce(g_sta, group=self.group)             # the one gradient all-reduce
+        # adjoint of the loop pad for the frames we own, so the backward can run per frame chunk with pad = 0
+        if pad and t0 < pad:
+            n = min(t1, pad) - t0
+            grad_rgb[t0:t0 + n] += grad_rgb[T + t0:T + t0 + n]
         self.t += 1
-        with self._timed("adam"):
-            self._adam("atlas_dyn", dyn_local, g_dyn, lr)
-            if pack.n_static > 0:
+        nch = min(self.overlap_chunks, Tl)
+        cb = partition(Tl, nch)
+        st = self._state.get("atlas_dyn")
+        if st is None:
+            st = (torch.zeros_like(dyn_local), torch.zeros_like(dyn_local))
+            self._state["atlas_dyn"] = st
+        for c in range(nch):
+            a, b = cb[c], cb[c + 1]
+            with self._timed("composite_bwd"):
+                ops.composite_bwd(view, pack, dyn_local[a:b], atlas.data, None, b - a, 0, grad_rgb[t0 + a:t0 + b],
+                                  rgb_pad[t0 + a:t0 + b], w_smooth, g_dyn[a:b], g_sta, smooth_sums=bwd_sums)
+            if nch > 1:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(self._side):
+                    self._side.wait_event(ev)
+                    ops.adam_step(dyn_local[a:b], g_dyn[a:b], st[0][a:b], st[1][a:b], self.t, lr, self.betas[0],
+                                  self.betas[1], self.eps)
+            else:
+                with self._timed("adam"):
+                    ops.adam_step(dyn_local[a:b], g_dyn[a:b], st[0][a:b], st[1][a:b], self.t, lr, self.betas[0],
+                                  self.betas[1], self.eps)
+        if nch > 1:
+            done = torch.cuda.Event()
+            done.record(self._side)
+            main.wait_event(done)
+        if pack.n_static > 0:
+            if self.world > 1:
+                with self._timed("allreduce_static_grad"):
+                    dist.all_reduce(g_sta, group=self.group)         # the one gradient all-reduce
+            with self._timed("adam_static"):
                 self._adam("atlas", atlas.data, g_sta, lr)
         return assemble()
 
