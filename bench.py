@@ -145,6 +145,11 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
+# `ncu --set full` capture of this same command (profiles/r01_final_ncu_full_step720p.md); None if not captured.
+NCU_TRAFFIC_BYTES = {("step720p", 1, "composite_bwd"): 42.256709e9 + 20.444168e9}
+
+
 def algorithmic_bytes(wl, frames):
     """each live texel touched once per pass, geometry recomputed in-kernel.
     Dense 1:1 case N_tex = D*H*W per frame: fwd 16 B/texel + 12 B/pixel out; bwd re-reads the atlas and
@@ -343,7 +348,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes),
+                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, world, dom)), "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes),
                          "ms_per_launch": kernel_ms[dom]},
             "kernels_ms": {k: round(v, 4) for k, v in kernel_ms.items()},
             "composite": {"fwd_GBps": fwd_ach, "fwd_frac": fwd_ach / peak, "bwd_GBps": bwd_ach, "bwd_frac": bwd_ach / peak,
