@@ -282,19 +282,34 @@ def run_ours(args):
     # The public call (FusedLoopStep.step, the run_iter equivalent) is fed from pinned host memory the way
     # train_3dvid.run_iter feeds it (`datainfo_.to(device)`, train_3dvid.py:215); the next item's copy is
     # issued on a side stream while the current step computes (double buffer), the loss is read back.
-    res_host = [make_target(wl, None, seed=3, pinned=True)]
-    res_host.append(res_host[0])                                     # two views of one pinned item (same bytes copied)
+    # With N ranks every rank needs the whole target video: each rank copies only ITS block of target frames
+    # from its pinned host buffer (1/N of the bytes over its own PCIe link) and the blocks are all-gathered
+    # over NVLink on the copy stream (a second NCCL communicator, so it cannot interleave with the step's own
+    # collectives).  h2d_bytes_per_step is the total over all ranks.
+    fb = [(wl["F"] * r) // world for r in range(world + 1)]
+    f0, f1 = fb[rank], fb[rank + 1]
+    res_full_host = make_target(wl, None, seed=3, pinned=False)
+    res_host = res_full_host[:, f0:f1].contiguous().pin_memory()        # this rank's share of the item
+    del res_full_host
+    loader_group = dist.new_group(backend="nccl") if world > 1 else None
     bufs = [torch.empty_like(res_dev), res_dev]
     copy_stream = torch.cuda.Stream()
     ext_h, intr_h = ext.pin_memory(), intr.pin_memory()
-    h2d = res_host[0].numel() * 4 + 1216          # target video + the 1.2 KB view descriptor (kernel parameter)
+    h2d = wl["F"] * 3 * H * W * 4 + 1216 * world      # target video (all ranks together) + the view descriptors
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def load(buf):
+        """H2D of this rank's frames (+ NVLink all-gather of the other ranks' frames) on the copy stream."""
+        buf[:, f0:f1].copy_(res_host, non_blocking=True)
+        if world > 1:
+            parts = [buf[0, a:b] for a, b in zip(fb[:-1], fb[1:])]
+            dist.all_gather(parts, buf[0, f0:f1], group=loader_group)
 
     def e2e_loop(n):
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         done = [torch.cuda.Event(), torch.cuda.Event()]
         with torch.cuda.stream(copy_stream):
-            bufs[0].copy_(res_host[0], non_blocking=True)
+            load(bufs[0])
             ready[0].record()
         for i in range(n):
             cur, nxt = i & 1, (i + 1) & 1
@@ -302,7 +317,7 @@ def run_ours(args):
                 with torch.cuda.stream(copy_stream):
                     if i >= 1:
                         copy_stream.wait_event(done[nxt])             # buffer `nxt` was consumed by step i-1
-                    bufs[nxt].copy_(res_host[nxt], non_blocking=True)
+                    load(bufs[nxt])
                     ready[nxt].record()
             torch.cuda.current_stream().wait_event(ready[cur])
             # pose / intrinsics stay on the host: the view descriptor (plane homographies) is built there
@@ -344,7 +359,8 @@ def run_ours(args):
                        "l2": "inputs (>= 22 GB of texels per step) far exceed the 126 MB L2; no explicit flush"},
             "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms / args.steps,
-                    "api": "FusedLoopStep.step fed from pinned host memory (double-buffered H2D), loss read back"},
+                    "api": "FusedLoopStep.step fed from pinned host memory (double-buffered H2D; with N ranks each "
+                           "copies 1/N of the target frames and they are all-gathered over NVLink), loss read back"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
