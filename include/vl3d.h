@@ -143,6 +143,14 @@ int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const float* xsca
                    float* y2x_out, float* weight_out, float* grad_out, double* partials, float* loss_out,
                    void* stream);
 
+/* ---- "next" rows ------------------------------------------------------------
+ * vl3d_patch_l1 (N3, evaluations/NNMSE.py:45-53): err_out[ho,wo,n1] = mean |y_patch[nn] - x_patch| over the
+ *   3*pt*p*p elements of each (patch position, query) pair, given the NN map from vl3d_patchnn_search.
+ * vl3d_to8b (N1, utils.py:17 `to8b`): rgb (T,3,H,W) float -> out (T,H,W,3) uint8 = trunc(255*clip(x,0,1)). */
+int vl3d_patch_l1(const vl3d_loss_desc* desc, const float* x, const float* y, const int32_t* nn, float* err_out,
+                  void* stream);
+int vl3d_to8b(const float* rgb, uint8_t* out, int32_t T, int32_t H, int32_t W, void* stream);
+
 /* ---- optimiser (MPV.py:200-218: torch.optim.Adam(betas=(0.9,0.999), eps=6e-8), one tensor) ------
  * p, g, m, v: n floats each; step >= 1.  lr etc. are host scalars. */
 int vl3d_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr,

@@ -205,11 +205,30 @@ def golden_pointwise(name):
     print(name)
 
 
+def golden_nnerr(name):
+    """evaluations/NNMSE.compute_nnerr of the unmodified reference."""
+    sys.path.insert(0, os.path.join(ref_env.REFERENCE_DIR, "evaluations"))
+    import NNMSE  # reference
+    g = torch.Generator().manual_seed(21)
+    tar = torch.rand(1, 3, 14, 40, 52, generator=g)
+    tar = (tar + tar.roll(1, 2) + tar.roll(1, 4)) / 3
+    src = (tar[:, :, 3:12] * 0.7 + 0.3 * torch.rand(1, 3, 9, 40, 52, generator=g)).contiguous()
+    out = dict(src=src, tar=tar)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i, (p, s, pt, st) in enumerate([(5, 2, 7, 1), (11, 4, 5, 1), (17, 6, 3, 1)]):   # script_evaluate_ours.py:201-204
+            out[f"err{i}"] = NNMSE.compute_nnerr(src, tar, p, s, pt, st, macro_block=25)
+            out[f"cfg{i}"] = np.array([p, s, pt, st])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(out))
+    print(name, [float(out[f"err{i}"]) for i in range(3)])
+
+
 def main():
     assert ref_env.reference_available(), "needs /root/reference"
     ref_env.enable()
     os.makedirs(OUT, exist_ok=True)
     golden_pointwise("pointwise")
+    golden_nnerr("nnerr")
     golden_render("render_dense", "dense", seed=0)
     golden_render("render_sparse", "sparse", seed=1, D=6, hv=6, wv=9, T=2)
     golden_step("step_dense_refcfg", "dense", LOSS_CFG_REF, seed=2)

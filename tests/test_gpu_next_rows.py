@@ -1,0 +1,63 @@
+"""GPU: the SURVEY §8(f) "next" rows built on the hot-path kernels — N3 NN-error metric
+(evaluations/NNMSE.py) against the unmodified reference's values, N1 uint8 epilogue (utils.py:17), and
+the lod()/checkpoint plumbing of N2 (MPV.py:140-198, 290-304) as an API-level smoke test."""
+import numpy as np
+import pytest
+import torch
+
+from util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_compute_nnerr_matches_reference_golden():
+    from videoloop3d_b200 import compute_nnerr
+    g = load_golden("nnerr")
+    dev = torch.device("cuda:0")
+    src, tar = torch.as_tensor(g["src"]).to(dev), torch.as_tensor(g["tar"]).to(dev)
+    for i in range(3):
+        p, s, pt, st = (int(v) for v in g[f"cfg{i}"])
+        e = compute_nnerr(src, tar, p, s, pt, st, macro_block=25)
+        assert abs(e - float(g[f"err{i}"])) < 1e-5 * float(g[f"err{i}"]), (i, e)
+
+
+def test_to8b_matches_numpy():
+    from videoloop3d_b200 import to8b
+    x = torch.randn(3, 3, 37, 53, device="cuda:0") * 0.7 + 0.5
+    x[0, 0, 0, :4] = torch.tensor([0.0, 1.0, 1.0 - 1e-7, 254.999 / 255], device="cuda:0")
+    ref = (255 * np.clip(x.cpu().numpy(), 0, 1)).astype(np.uint8).transpose(0, 2, 3, 1)      # utils.py:17
+    assert np.array_equal(to8b(x).cpu().numpy(), ref)
+
+
+def test_lod_and_state_dict_roundtrip():
+    from oracle import mpv_oracle as MO
+    from test_gpu_parity import state_tensors
+    from videoloop3d_b200.testing import model_from_tensors
+    dev = torch.device("cuda:0")
+    H, W = 32, 48
+    st = MO.sparse_state(H, W, 4, 5, 7, 3, 1.0, 10.0, tile=8, occupancy=0.8, dyn_frac=0.5, h_scale=1.3, w_scale=1.3, seed=3)
+    m = model_from_tensors(state_tensors(st), H, W, dev)
+    m.atlas_grid_h, m.atlas_grid_w = st.atlas.shape[-2] // 8, st.atlas.shape[-1] // 8
+    m.atlas_full_h, m.atlas_full_w = st.atlas.shape[-2:]
+    m.atlas_grid_dyn_h, m.atlas_grid_dyn_w = st.atlas_dyn.shape[-2] // 8, st.atlas_dyn.shape[-1] // 8
+    m.atlas_full_dyn_h, m.atlas_full_dyn_w = st.atlas_dyn.shape[-2:]
+    ext = torch.eye(4, device=dev)[None]
+    intr = torch.tensor([[40., 0, 24.2], [0, 40., 15.7], [0, 0, 1]], device=dev)[None]
+    m.eval()
+    with torch.no_grad():
+        full, _ = m(H, W, ext, intr, ts=[0, 2])
+    m.lod(0.5)                                                            # 8x8 tiles -> 4x4 tiles, uvs re-aligned
+    assert m.atlas.shape[-1] == st.atlas.shape[-1] // 2 and m.atlas_dyn.shape[-2] == st.atlas_dyn.shape[-2] // 2
+    assert m.atlas_dyn.is_contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        half, _ = m(H, W, ext, intr, ts=[0, 2])
+    assert tuple(half.shape) == tuple(full.shape) and bool(torch.isfinite(half).all())
+    assert float((half - full).abs().mean()) < 0.25                       # same scene at half the texel density
+    sd = m.state_dict()
+    for k in ("atlas", "atlas_dyn", "uvs", "uvs_dyn", "_verts", "faces", "faces_dyn", "uvfaces", "uvfaces_dyn", "planedepth",
+              "ref_extrin", "ref_intrin", "self.is_sparse", "self.atlas_full_w", "self.atlas_grid_h", "self.has_dyn",
+              "self.atlas_full_dyn_h", "self.atlas_grid_dyn_w"):
+        assert k in sd, k                                                 # MPV.py:290-304
+    opt = m.get_optimizer(step=0)
+    assert len(opt.param_groups) == 2 and opt.param_groups[0]["eps"] == 6e-8
+    assert abs(m.get_lrate(1000)[0][1] - m.args.lrate * 0.1 ** (1000 / (m.args.lrate_decay * 1000))) < 1e-12

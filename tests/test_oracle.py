@@ -87,3 +87,16 @@ def test_macro_block_loop_is_a_memory_trick():
     l1, a1 = LL.gpnn_lowmem(x, y, use_macro_blocks=True, **cfg)
     assert abs(float(l0 - l1)) < 1e-12 and float((a0["y2x"] - a1["y2x"]).abs().max()) < 1e-12
     assert torch.equal(a0["weight"], a1["weight"])
+
+
+def test_nnerr_matches_reference():
+    """evaluations/NNMSE.compute_nnerr of the unmodified reference."""
+    import warnings
+    g = load_golden("nnerr")
+    src, tar = torch.as_tensor(g["src"]).double(), torch.as_tensor(g["tar"]).double()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(3):
+            p, s, pt, st = (int(v) for v in g[f"cfg{i}"])
+            e = LL.compute_nnerr(src, tar, p, s, pt, st, macro_block=25)
+            assert abs(e - float(g[f"err{i}"])) < 1e-6 * float(g[f"err{i}"])

@@ -11,6 +11,7 @@ from .loop_loss import (Patch3DAvg, Patch3DGPNNDirectLoss, Patch3DGPNNLowMemDown
                         Patch3DGPNNLowMemLoss, Patch3DMSE)
 from .mpv import MPMeshVid, get_new_intrin, make_depths, gen_mpi_vertices, pose2extrin_torch  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
+from .evaluations import compute_nnerr, to8b  # noqa: F401
 from .train_step import FusedLoopStep, make_run_iter, default_args  # noqa: F401
 
 __version__ = "0.1.0"

@@ -44,6 +44,8 @@ _SIGNATURES = {
     "vl3d_vote_partials": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     "vl3d_vote_loss": (C.c_int, [C.POINTER(LossDesc), _P, _P, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_float,
                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "vl3d_patch_l1": (C.c_int, [C.POINTER(LossDesc), _P, _P, _P, _P, _P]),
+    "vl3d_to8b": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "vl3d_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
@@ -51,7 +53,7 @@ EXPORTS = tuple(_SIGNATURES)
 _lib = None
 LAUNCHES = 0          # kernels launched through this binding (bench.py's gpu_launches)
 _LAUNCHES_PER_CALL = {"vl3d_composite_fwd": 1, "vl3d_composite_bwd": 1, "vl3d_scale_invariant": 2,
-                      "vl3d_patchnn_search": 1, "vl3d_scale_video": 1, "vl3d_vote_loss": 2, "vl3d_adam_step": 1}
+                      "vl3d_patchnn_search": 1, "vl3d_scale_video": 1, "vl3d_patch_l1": 1, "vl3d_to8b": 1, "vl3d_vote_loss": 2, "vl3d_adam_step": 1}
 
 
 class Vl3dError(RuntimeError):

@@ -570,6 +570,51 @@ __global__ void __launch_bounds__(256) scale_video_kernel(const float* __restric
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = x[i] * sc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// evaluation metric support (evaluations/NNMSE.py:45-53): mean |Y[NN] - X| per
+// (patch position, query): one warp per pair, lanes stride over the 3*pt*p*p patch elements.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) patch_l1_kernel(const vl3d_loss_desc L, const float* __restrict__ x,
+                                                       const float* __restrict__ y, const int* __restrict__ nn,
+                                                       float* __restrict__ err) {
+    const long long pair = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const long long npairs = (long long)L.ho * L.wo * L.n1;
+    if (pair >= npairs) return;
+    const int lane = threadIdx.x & 31;
+    const int i = (int)(pair % L.n1);
+    const long long b = pair / L.n1;
+    const int pxi = (int)(b % L.wo), pyi = (int)(b / L.wo);
+    const int j = __ldg(nn + pair);
+    const int pp = L.p * L.p, d = 3 * L.pt * pp;
+    const float* xb = x + (size_t)(i * L.st) * L.x_sf + (size_t)(pyi * L.s) * L.x_sr + pxi * L.s;
+    const float* yb = y + (size_t)(j * L.st) * L.y_sf + (size_t)(pyi * L.s) * L.y_sr + pxi * L.s;
+    float acc = 0.f;
+    for (int e = lane; e < d; e += 32) {
+        const int c = e / (L.pt * pp), r = e - c * (L.pt * pp);
+        const int dt = r / pp, r2 = r - dt * pp;
+        const int dy = r2 / L.p, dx = r2 - dy * L.p;
+        const float xv = __ldg(xb + (size_t)dt * L.x_sf + (size_t)c * L.x_sc + (size_t)dy * L.x_sr + dx);
+        const float yv = __ldg(yb + (size_t)dt * L.y_sf + (size_t)c * L.y_sc + (size_t)dy * L.y_sr + dx);
+        acc += fabsf(yv - xv);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) err[pair] = acc / (float)d;
+}
+
+// to8b (utils.py:17): (255 * clip(x, 0, 1)).astype(uint8), planar (T,3,H,W) float -> (T,H,W,3) uint8
+__global__ void __launch_bounds__(256) to8b_kernel(const float* __restrict__ rgb, unsigned char* __restrict__ out, size_t hw,
+                                                   size_t total) {
+    for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
+        const size_t t = idx / hw, pix = idx - t * hw;
+        const float* src = rgb + t * 3 * hw + pix;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = fminf(fmaxf(src[c * hw], 0.f), 1.f) * 255.f;
+            out[idx * 3 + c] = (unsigned char)v;                 // truncation, as numpy's astype
+        }
+    }
+}
+
 static int validate_desc(const vl3d_loss_desc* L) {
     VL3D_REQUIRE(L != nullptr, VL3D_ENULL, "loss desc is NULL");
     VL3D_REQUIRE(L->p >= 1 && L->pt >= 1 && L->s >= 1 && L->st >= 1, VL3D_EINVAL, "bad patch config");
@@ -687,6 +732,25 @@ extern "C" int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const 
     const double denom = (double)desc->t * desc->h * desc->w * 3.0;
     finalize_mean_kernel<<<1, 1024, 0, st>>>(partials, nblocks, denom, loss_out);
     return check_launch("vote_finalize");
+}
+
+extern "C" int vl3d_patch_l1(const vl3d_loss_desc* desc, const float* x, const float* y, const int32_t* nn, float* err_out,
+                             void* stream) {
+    if (int e = validate_desc(desc)) return e;
+    VL3D_REQUIRE(x && y && nn && err_out, VL3D_ENULL, "patch_l1: NULL pointer");
+    const long long npairs = (long long)desc->ho * desc->wo * desc->n1;
+    patch_l1_kernel<<<(unsigned)((npairs + 7) / 8), 256, 0, (cudaStream_t)stream>>>(*desc, x, y, nn, err_out);
+    return check_launch("patch_l1");
+}
+
+extern "C" int vl3d_to8b(const float* rgb, uint8_t* out, int32_t T, int32_t H, int32_t W, void* stream) {
+    VL3D_REQUIRE(rgb && out, VL3D_ENULL, "to8b: NULL pointer");
+    VL3D_REQUIRE(T >= 1 && H >= 1 && W >= 1, VL3D_EINVAL, "to8b: bad sizes");
+    const size_t hw = (size_t)H * W, total = hw * T;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    to8b_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rgb, out, hw, total);
+    return check_launch("to8b");
 }
 
 extern "C" int vl3d_scale_partials(void) { return SCALE_BLOCKS; }
