@@ -30,6 +30,7 @@ struct CompositeParams {
     const float4* atlas_sta;
     const int* ts;
     int T, pad;
+    int tb;          // first frame of this launch (lean kernels: a call is split into a TF-multiple + a tail)
     // forward
     float* rgb_out;
     float* alpha_out;
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(BX* BY) composite_fwd_kernel(const __grid_cons
 // (pixel, plane) and no slot bookkeeping is needed because nothing compares neighbouring pixels.
 // ------------------------------------------------------------------------------------------------
 template <int TF>
-__global__ void __launch_bounds__(BX* BY) composite_render_kernel(const __grid_constant__ CompositeParams p) {
+__global__ void __launch_bounds__(BX* BY) composite_render_v1_kernel(const __grid_constant__ CompositeParams p) {
     const int px = blockIdx.x * BX + threadIdx.x, py = blockIdx.y * BY + threadIdx.y;
     const int H = p.view.H, W = p.view.W;
     if (px >= W || py >= H) return;
@@ -480,7 +481,7 @@ __device__ __forceinline__ void red_tap(float4* base, int off, const float4& g, 
 }
 
 template <int TF, bool SMOOTH>
-__global__ void __launch_bounds__(BX* BY) composite_bwd_kernel(const __grid_constant__ CompositeParams p) {
+__global__ void __launch_bounds__(BX* BY) composite_bwd_v1_kernel(const __grid_constant__ CompositeParams p) {
     constexpr int SX = SMOOTH ? BX - 1 : BX, SY = SMOOTH ? BY - 1 : BY;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int px = blockIdx.x * SX + tx, py = blockIdx.y * SY + ty;
@@ -681,26 +682,61 @@ __global__ void __launch_bounds__(BX* BY) composite_bwd_kernel(const __grid_cons
     }
 }
 
-// frames per thread of the pure-render forward (geometry is shared by the frames of a chunk).
-// VL3D_FWD_TF overrides (tuning aid).
+}  // namespace vl3d
+
+#include "composite_lean.cuh"
+
+namespace vl3d {
+
+// frames per thread (geometry is shared by the frames of a chunk).  VL3D_FWD_TF / VL3D_BWD_TF override
+// (tuning aids); VL3D_COMPOSITE_V1=1 selects the first-generation kernels (kept for A/B measurements).
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+// (read on every call: getenv costs nanoseconds and in-process sweeps can flip the knobs)
+static bool use_v1() { return env_int("VL3D_COMPOSITE_V1", 0) != 0; }
+
 static int fwd_tf(int T) {
-    static int env = -1;
-    if (env < 0) { const char* e = getenv("VL3D_FWD_TF"); env = e ? atoi(e) : 0; }
+    const int env = env_int("VL3D_FWD_TF", 0);
     if (env == 1 || env == 2 || env == 3 || env == 4 || env == 6 || env == 8) return env;
     return T >= 3 ? 3 : T;
 }
 
-static bool render_pipe() {
-    static int env = -1;
-    if (env < 0) { const char* e = getenv("VL3D_PIPE"); env = e ? atoi(e) : 0; }
-    return env != 0;
-}
+static bool render_pipe() { return env_int("VL3D_PIPE", 0) != 0; }
 
 static int bwd_tf(int T) {
-    static int env = -1;
-    if (env < 0) { const char* e = getenv("VL3D_BWD_TF"); env = e ? atoi(e) : 0; }
+    const int env = env_int("VL3D_BWD_TF", 0);
     if (env >= 1 && env <= 4) return env;
     return T >= 2 ? 2 : 1;
+}
+
+// lean kernels: frames [0, T) = nz chunks of TF frames + a tail of T % TF single frames
+template <int TF, int MINB>
+static void launch_render(CompositeParams p, int T, dim3 grid2, dim3 block, cudaStream_t st) {
+    const int nz = T / TF;
+    if (nz > 0) {
+        p.tb = 0;
+        composite_render_kernel<TF, MINB><<<dim3(grid2.x, grid2.y, nz), block, 0, st>>>(p);
+    }
+    if (TF > 1 && T % TF) {
+        p.tb = nz * TF;
+        composite_render_kernel<1, 4><<<dim3(grid2.x, grid2.y, T % TF), block, 0, st>>>(p);
+    }
+}
+
+template <int TF, bool SMOOTH>
+static void launch_bwd(CompositeParams p, int T, dim3 grid2, dim3 block, cudaStream_t st) {
+    const int nz = T / TF;
+    if (nz > 0) {
+        p.tb = 0;
+        composite_bwd_kernel<TF, SMOOTH><<<dim3(grid2.x, grid2.y, nz), block, 0, st>>>(p);
+    }
+    if (TF > 1 && T % TF) {
+        p.tb = nz * TF;
+        composite_bwd_kernel<1, SMOOTH><<<dim3(grid2.x, grid2.y, T % TF), block, 0, st>>>(p);
+    }
 }
 
 static int validate_view(const vl3d_view* v, const vl3d_quad* quads, const float* dyn, const float* sta) {
@@ -736,7 +772,7 @@ extern "C" int vl3d_composite_fwd(const vl3d_view* view, const vl3d_quad* quads,
     const bool smooth = smooth_sums != nullptr, mpi = mpi_out != nullptr;
     const int sx = smooth ? BX - 1 : BX, sy = smooth ? BY - 1 : BY;
     int tf = (!smooth && !mpi) ? fwd_tf(T) : 4;
-    if (!smooth && !mpi && render_pipe() && tf > 4) tf = 4;
+    if (!smooth && !mpi && (render_pipe() || use_v1()) && tf > 4) tf = 4;
     dim3 grid((view->W + sx - 1) / sx, (view->H + sy - 1) / sy, (T + tf - 1) / tf), block(BX, BY);
     cudaStream_t st = (cudaStream_t)stream;
     if (smooth && mpi) composite_fwd_kernel<4, true, true><<<grid, block, 0, st>>>(p);
@@ -747,12 +783,21 @@ extern "C" int vl3d_composite_fwd(const vl3d_view* view, const vl3d_quad* quads,
               : tf == 3 ? launch_render_pipe<3>(p, grid, block, st) : launch_render_pipe<4>(p, grid, block, st);
         if (e) return e;
     }
-    else if (tf == 8) composite_render_kernel<8><<<grid, block, 0, st>>>(p);
-    else if (tf == 6) composite_render_kernel<6><<<grid, block, 0, st>>>(p);
-    else if (tf == 3) composite_render_kernel<3><<<grid, block, 0, st>>>(p);
-    else if (tf == 2) composite_render_kernel<2><<<grid, block, 0, st>>>(p);
-    else if (tf == 1) composite_render_kernel<1><<<grid, block, 0, st>>>(p);
-    else composite_render_kernel<4><<<grid, block, 0, st>>>(p);
+    else if (use_v1()) {
+        if (tf == 3) composite_render_v1_kernel<3><<<grid, block, 0, st>>>(p);
+        else if (tf == 2) composite_render_v1_kernel<2><<<grid, block, 0, st>>>(p);
+        else if (tf == 1) composite_render_v1_kernel<1><<<grid, block, 0, st>>>(p);
+        else composite_render_v1_kernel<4><<<grid, block, 0, st>>>(p);
+    } else {
+        // MINB = resident CTAs per SM the register budget is capped for (VL3D_FWD_MINB: tuning aid)
+        const int minb = env_int("VL3D_FWD_MINB", 0);
+        if (tf == 8) launch_render<8, 1>(p, T, grid, block, st);
+        else if (tf == 6) launch_render<6, 2>(p, T, grid, block, st);
+        else if (tf == 4) { if (minb == 4) launch_render<4, 4>(p, T, grid, block, st); else launch_render<4, 3>(p, T, grid, block, st); }
+        else if (tf == 3) { if (minb == 3) launch_render<3, 3>(p, T, grid, block, st); else if (minb == 5) launch_render<3, 5>(p, T, grid, block, st); else launch_render<3, 4>(p, T, grid, block, st); }
+        else if (tf == 2) { if (minb == 5) launch_render<2, 5>(p, T, grid, block, st); else if (minb == 6) launch_render<2, 6>(p, T, grid, block, st); else launch_render<2, 4>(p, T, grid, block, st); }
+        else launch_render<1, 4>(p, T, grid, block, st);
+    }
     return check_launch("composite_fwd");
 }
 
@@ -778,21 +823,30 @@ extern "C" int vl3d_composite_bwd(const vl3d_view* view, const vl3d_quad* quads,
     VL3D_REQUIRE(smooth || smooth_sums == nullptr, VL3D_EINVAL, "smooth_sums needs w_smooth");
     p.w_smooth = w_smooth;
     p.smooth = smooth_sums;
-    const int tf = bwd_tf(T);
-    { static int nored = -1; if (nored < 0) { const char* e = getenv("VL3D_BWD_NORED"); nored = e ? atoi(e) : 0; } p.dbg_nored = nored; }
+    int tf = bwd_tf(T);
+    if (use_v1() && tf > 2) tf = 2;
+    p.dbg_nored = env_int("VL3D_BWD_NORED", 0);
     const int sx = smooth ? BX - 1 : BX, sy = smooth ? BY - 1 : BY;
     dim3 grid((view->W + sx - 1) / sx, (view->H + sy - 1) / sy, (T + tf - 1) / tf), block(BX, BY);
     cudaStream_t st = (cudaStream_t)stream;
-    if (smooth) {
-        if (tf == 1) composite_bwd_kernel<1, true><<<grid, block, 0, st>>>(p);
-        else if (tf == 2) composite_bwd_kernel<2, true><<<grid, block, 0, st>>>(p);
-        else if (tf == 3) composite_bwd_kernel<3, true><<<grid, block, 0, st>>>(p);
-        else composite_bwd_kernel<4, true><<<grid, block, 0, st>>>(p);
+    if (use_v1()) {
+        if (smooth) {
+            if (tf == 1) composite_bwd_v1_kernel<1, true><<<grid, block, 0, st>>>(p);
+            else composite_bwd_v1_kernel<2, true><<<grid, block, 0, st>>>(p);
+        } else {
+            if (tf == 1) composite_bwd_v1_kernel<1, false><<<grid, block, 0, st>>>(p);
+            else composite_bwd_v1_kernel<2, false><<<grid, block, 0, st>>>(p);
+        }
+    } else if (smooth) {
+        if (tf == 1) launch_bwd<1, true>(p, T, grid, block, st);
+        else if (tf == 2) launch_bwd<2, true>(p, T, grid, block, st);
+        else if (tf == 3) launch_bwd<3, true>(p, T, grid, block, st);
+        else launch_bwd<4, true>(p, T, grid, block, st);
     } else {
-        if (tf == 1) composite_bwd_kernel<1, false><<<grid, block, 0, st>>>(p);
-        else if (tf == 2) composite_bwd_kernel<2, false><<<grid, block, 0, st>>>(p);
-        else if (tf == 3) composite_bwd_kernel<3, false><<<grid, block, 0, st>>>(p);
-        else composite_bwd_kernel<4, false><<<grid, block, 0, st>>>(p);
+        if (tf == 1) launch_bwd<1, false>(p, T, grid, block, st);
+        else if (tf == 2) launch_bwd<2, false>(p, T, grid, block, st);
+        else if (tf == 3) launch_bwd<3, false>(p, T, grid, block, st);
+        else launch_bwd<4, false>(p, T, grid, block, st);
     }
     return check_launch("composite_bwd");
 }

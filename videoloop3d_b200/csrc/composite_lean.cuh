@@ -1,0 +1,375 @@
+// Instruction-lean composite kernels (included by composite.cu after CompositeParams / the v1 kernels).
+//
+// The v1 kernels were issue-bound (ncu: 64 % issue active, 27 % DRAM; ~480 SASS instructions per
+// (pixel, plane, frame) sample in the backward).  These versions compute the same thing with about half
+// the instructions:
+//   * ex2.approx.ftz / rcp.approx.ftz (no denormal fix-up sequences around MUFU),
+//   * 32-bit texel offsets against a per-frame 64-bit base held in registers: one IMAD.WIDE per tap
+//     instead of a 4-instruction 64-bit add + shift chain,
+//   * out-of-image threads replicate the border pixel, so every missing neighbour compares equal and
+//     the eight per-direction pair masks collapse into two per-thread weights,
+//   * neighbour exchange entirely through shared memory (1 STS.128 + 4 LDS.128 per frame; no shuffles),
+//   * the shuffle hand-over of right-hand taps moves the 4-float sample gradient + two per-slot weights
+//     instead of two 4-float products per frame (FFMA on the receiving side),
+//   * static-tile work sits behind a warp-uniform branch,
+//   * no per-frame "t < T" predicates: the host splits a launch into a TF-multiple and a TF=1 tail.
+#pragma once
+
+namespace vl3d {
+
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// same value as sigmoidf_fast (ex2.approx of -x*log2(e), rcp.approx) except that sub-1e-38 intermediates flush to 0
+__device__ __forceinline__ float sigmoid_lean(float x) { return rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * x)); }
+
+template <typename P>
+__device__ __forceinline__ P opaque_ptr(P p) {   // keep a base pointer as one 64-bit register pair
+    asm volatile("" : "+l"(p));
+    return p;
+}
+
+struct Geo {
+    unsigned o00, o10, o01, o11;   // texel offsets inside one atlas frame
+    float w00, w10, w01, w11;      // bilinear weights (0 for taps outside the atlas, MPV.py:425-427)
+    int kind;                      // 0 none, 1 static, 2 dynamic
+};
+
+// quad-grid coordinates of pixel (u, v) on a plane; same arithmetic as plane_grid()
+__device__ __forceinline__ bool plane_grid_lean(const float* __restrict__ h, float u, float v, float qwf, float qhf,
+                                                float& gx, float& gy) {
+    const float w = fmaf(h[6], u, fmaf(h[7], v, h[8]));
+    float inv = rcp_ftz(w);
+    inv = inv * fmaf(-w, inv, 2.f);
+    gx = fmaf(h[0], u, fmaf(h[1], v, h[2])) * inv;
+    gy = fmaf(h[3], u, fmaf(h[4], v, h[5])) * inv;
+    return w > 0.f && gx > 0.f && gx < qwf && gy > 0.f && gy < qhf;
+}
+
+// quad under grid position (gx, gy) of plane d: returns its table entry (two 16-byte halves)
+__device__ __forceinline__ const float4* quad_at(const CompositeParams& p, int d, float gx, float gy, int& qx, int& qy) {
+    const int qw = p.view.qw, qh = p.view.qh;
+    qx = min((int)gx, qw - 1); qy = min((int)gy, qh - 1);
+    return reinterpret_cast<const float4*>(&p.quads[(d * qh + qy) * qw + qx]);
+}
+
+__device__ __forceinline__ Geo geo_from_quad(const CompositeParams& p, const float4* qp, const int4 qb, int qx, int qy,
+                                             float gx, float gy) {
+    Geo t;
+    const float4 qa = __ldg(qp);
+    const float a = gx - (float)qx, b = gy - (float)qy;
+    const float lx = fmaf(a, qa.z, qa.x), ly = fmaf(b, qa.w, qa.y);
+    const float flx = floorf(lx), fly = floorf(ly);
+    const float fx = lx - flx, fy = ly - fly;
+    const int ix = qb.x + (int)flx, iy = qb.y + (int)fly;            // >= 0: tiles lie inside the atlas (host-checked)
+    t.kind = qb.z;
+    const int aw = (t.kind == 2) ? p.view.dyn_w : p.view.sta_w;
+    const int ah = (t.kind == 2) ? p.view.dyn_h : p.view.sta_h;
+    // grid_sample zero padding can only trigger on the last row / column of the atlas
+    const int cx0 = min(ix, aw - 1), cx1 = min(ix + 1, aw - 1);
+    const int cy0 = min(iy, ah - 1), cy1 = min(iy + 1, ah - 1);
+    const float gx1 = (ix + 1 < aw) ? fx : 0.f, gx0 = (ix < aw) ? 1.f - fx : 0.f;
+    const float gy1 = (iy + 1 < ah) ? fy : 0.f, gy0 = (iy < ah) ? 1.f - fy : 0.f;
+    const int r0 = cy0 * aw, r1 = cy1 * aw;
+    t.o00 = (unsigned)(r0 + cx0); t.o10 = (unsigned)(r0 + cx1);
+    t.o01 = (unsigned)(r1 + cx0); t.o11 = (unsigned)(r1 + cx1);
+    t.w00 = gx0 * gy0; t.w10 = gx1 * gy0; t.w01 = gx0 * gy1; t.w11 = gx1 * gy1;
+    return t;
+}
+
+__device__ __forceinline__ Geo geo_from_grid(const CompositeParams& p, int d, float gx, float gy) {
+    int qx, qy;
+    const float4* qp = quad_at(p, d, gx, gy, qx, qy);
+    const int4 qb = __ldg(reinterpret_cast<const int4*>(qp + 1));
+    return geo_from_quad(p, qp, qb, qx, qy, gx, gy);
+}
+
+__device__ __forceinline__ float4 sample_lean(const float4* base, const Geo& t) {
+    const float4 a = __ldg(base + t.o00), b = __ldg(base + t.o10), c = __ldg(base + t.o01), d = __ldg(base + t.o11);
+    float4 r;
+    r.x = a.x * t.w00 + b.x * t.w10 + c.x * t.w01 + d.x * t.w11;
+    r.y = a.y * t.w00 + b.y * t.w10 + c.y * t.w01 + d.y * t.w11;
+    r.z = a.z * t.w00 + b.z * t.w10 + c.z * t.w01 + d.z * t.w11;
+    r.w = a.w * t.w00 + b.w * t.w10 + c.w * t.w01 + d.w * t.w11;
+    r.x = sigmoid_lean(r.x); r.y = sigmoid_lean(r.y); r.z = sigmoid_lean(r.z); r.w = sigmoid_lean(r.w);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pure render: planes in lockstep (CTA-uniform plane index => homography in uniform registers).
+// Frames [tb, tb + TF*gridDim.z) of the call; the host guarantees they exist.
+// ------------------------------------------------------------------------------------------------
+template <int TF, int MINB>
+__global__ void __launch_bounds__(BX* BY, MINB) composite_render_kernel(const __grid_constant__ CompositeParams p) {
+    const int px = blockIdx.x * BX + threadIdx.x, py = blockIdx.y * BY + threadIdx.y;
+    const int H = p.view.H, W = p.view.W;
+    if (px >= W || py >= H) return;
+    const int t0 = p.tb + blockIdx.z * TF;
+    const float u = (float)px + 0.5f - p.view.cx, v = (float)py + 0.5f - p.view.cy;
+    const size_t dyn_frame = (size_t)p.view.dyn_h * p.view.dyn_w;
+    const float4* fb[TF];
+#pragma unroll
+    for (int f = 0; f < TF; ++f) {
+        const int ft = p.ts ? __ldg(&p.ts[t0 + f]) : t0 + f;
+        fb[f] = opaque_ptr(p.atlas_dyn + (size_t)ft * dyn_frame);
+    }
+    const float4* sb = opaque_ptr(p.atlas_sta);
+    float Tr[TF], cr[TF], cg[TF], cb[TF], ca[TF];
+#pragma unroll
+    for (int f = 0; f < TF; ++f) { Tr[f] = 1.f; cr[f] = cg[f] = cb[f] = ca[f] = 0.f; }
+    const int D = p.view.D;
+    const float qwf = (float)p.view.qw, qhf = (float)p.view.qh;
+    int nhit = 0;
+    for (int d = 0; d < D; ++d) {
+        float gx, gy;
+        if (!plane_grid_lean(&p.view.hom[d * 9], u, v, qwf, qhf, gx, gy)) continue;
+        const Geo tp = geo_from_grid(p, d, gx, gy);
+        if (tp.kind == 0) continue;
+        ++nhit;
+        float4 val[TF];
+        if (tp.kind == 2) {
+#pragma unroll
+            for (int f = 0; f < TF; ++f) val[f] = sample_lean(fb[f], tp);
+        } else {
+            const float4 s = sample_lean(sb, tp);                 // static tile: same for all frames (MPV.py:445)
+#pragma unroll
+            for (int f = 0; f < TF; ++f) val[f] = s;
+        }
+#pragma unroll
+        for (int f = 0; f < TF; ++f) {
+            const float bw = val[f].w * Tr[f];                    // utils_mpi.py:100-104
+            cr[f] = fmaf(bw, val[f].x, cr[f]);
+            cg[f] = fmaf(bw, val[f].y, cg[f]);
+            cb[f] = fmaf(bw, val[f].z, cb[f]);
+            ca[f] += bw;
+            Tr[f] *= (1.f - val[f].w);
+        }
+    }
+    if (p.hits_out != nullptr && t0 == 0) p.hits_out[py * W + px] = nhit;
+    const size_t plane = (size_t)H * W;
+    const size_t pix = (size_t)py * W + px;
+#pragma unroll
+    for (int f = 0; f < TF; ++f) {
+        const int t = t0 + f;
+        float* o = p.rgb_out + (size_t)t * 3 * plane + pix;
+        o[0] = cr[f]; o[plane] = cg[f]; o[2 * plane] = cb[f];
+        if (t < p.pad) {                                          // loop pad: cat(rgb, rgb[:pt-1]) (MPV.py:490-492)
+            float* o2 = p.rgb_out + (size_t)(p.T + t) * 3 * plane + pix;
+            o2[0] = cr[f]; o2[plane] = cg[f]; o2[2 * plane] = cb[f];
+        }
+        if (p.alpha_out) p.alpha_out[(size_t)t * plane + pix] = ca[f];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward (see the derivation above composite_bwd_v1_kernel).  Threads outside the image replicate the
+// border pixel: a replica's value equals its in-image neighbour's bit for bit, so |a-b| and sign(a-b)
+// vanish for every pair that does not exist; replicas never write.  What is left of the pair
+// bookkeeping: horizontal pairs of the halo row and vertical pairs of the halo column belong to the
+// neighbouring CTA (weights wH / wV zeroed), and the regulariser sums are kept by owned pixels only.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sgn2(float c, float a, float b) {   // sign(c-a) + sign(c-b)
+    return ((c > a ? 1.f : 0.f) - (c < a ? 1.f : 0.f)) + ((c > b ? 1.f : 0.f) - (c < b ? 1.f : 0.f));
+}
+
+// scatter one sample gradient `gl` (w.r.t. the pre-sigmoid bilinear sample) to its four taps.  Lane i's
+// right-hand taps usually are lane i+1's left-hand taps: then the contribution travels by shuffle (gl_up
+// with the sender's weights wu10 / wu11, zero if nothing is received) and is folded into the receiver's RED.
+__device__ __forceinline__ void scatter_taps(float4* gb, const Geo& tp, const float4& gl, const float4& gl_up, float wu10,
+                                             float wu11, bool sent0, bool sent1) {
+    float4 l0, l1;
+    l0.x = fmaf(gl_up.x, wu10, gl.x * tp.w00); l0.y = fmaf(gl_up.y, wu10, gl.y * tp.w00);
+    l0.z = fmaf(gl_up.z, wu10, gl.z * tp.w00); l0.w = fmaf(gl_up.w, wu10, gl.w * tp.w00);
+    l1.x = fmaf(gl_up.x, wu11, gl.x * tp.w01); l1.y = fmaf(gl_up.y, wu11, gl.y * tp.w01);
+    l1.z = fmaf(gl_up.z, wu11, gl.z * tp.w01); l1.w = fmaf(gl_up.w, wu11, gl.w * tp.w01);
+    red_add_v4(gb + tp.o00, l0);
+    red_add_v4(gb + tp.o01, l1);
+    if (!sent0) red_add_v4(gb + tp.o10, make_float4(gl.x * tp.w10, gl.y * tp.w10, gl.z * tp.w10, gl.w * tp.w10));
+    if (!sent1) red_add_v4(gb + tp.o11, make_float4(gl.x * tp.w11, gl.y * tp.w11, gl.z * tp.w11, gl.w * tp.w11));
+}
+
+__device__ __forceinline__ float4 shfl_up4(const float4& v) {
+    float4 r;
+    r.x = __shfl_up_sync(0xffffffffu, v.x, 1); r.y = __shfl_up_sync(0xffffffffu, v.y, 1);
+    r.z = __shfl_up_sync(0xffffffffu, v.z, 1); r.w = __shfl_up_sync(0xffffffffu, v.w, 1);
+    return r;
+}
+
+template <int TF, bool SMOOTH>
+__global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(const __grid_constant__ CompositeParams p) {
+    constexpr int SX = SMOOTH ? BX - 1 : BX, SY = SMOOTH ? BY - 1 : BY;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int px0 = blockIdx.x * SX + tx, py0 = blockIdx.y * SY + ty;
+    const int H = p.view.H, W = p.view.W;
+    const bool active = px0 < W && py0 < H;
+    const bool owned = active && tx < SX && ty < SY;
+    const int px = min(px0, W - 1), py = min(py0, H - 1);          // replicas of the border pixel
+    const int t0 = p.tb + blockIdx.z * TF;
+    const float u = (float)px + 0.5f - p.view.cx, v = (float)py + 0.5f - p.view.cy;
+
+    __shared__ float4 s_ex[SMOOTH ? 2 : 1][SMOOTH ? TF : 1][SMOOTH ? BY : 1][SMOOTH ? BX : 1];
+
+    const size_t dyn_frame = (size_t)p.view.dyn_h * p.view.dyn_w;
+    const float4* ab[TF];
+    float4* gb[TF];
+    float g0[TF], g1[TF], g2[TF], tot[TF], Tr[TF], pre[TF];
+    const size_t plane = (size_t)H * W;
+    const size_t pix = (size_t)py * W + px;
+#pragma unroll
+    for (int f = 0; f < TF; ++f) {
+        const int t = t0 + f;
+        const int ft = p.ts ? __ldg(&p.ts[t]) : t;
+        ab[f] = opaque_ptr(p.atlas_dyn + (size_t)ft * dyn_frame);
+        gb[f] = opaque_ptr(p.grad_dyn + (size_t)ft * dyn_frame);
+        g0[f] = g1[f] = g2[f] = 0.f; tot[f] = 0.f; Tr[f] = 1.f; pre[f] = 0.f;
+        if (owned) {
+            const float* gp = p.grad_rgb + (size_t)t * 3 * plane + pix;
+            g0[f] = gp[0]; g1[f] = gp[plane]; g2[f] = gp[2 * plane];
+            if (t < p.pad) {                                      // adjoint of cat(rgb, rgb[:pad])
+                const float* gq = p.grad_rgb + (size_t)(p.T + t) * 3 * plane + pix;
+                g0[f] += gq[0]; g1[f] += gq[plane]; g2[f] += gq[2 * plane];
+            }
+            const float* rp = p.rgb + (size_t)t * 3 * plane + pix;
+            tot[f] = g0[f] * rp[0] + g1[f] * rp[plane] + g2[f] * rp[2 * plane];
+        }
+    }
+    const float4* sb = opaque_ptr(p.atlas_sta);
+    float4* gsb = opaque_ptr(p.grad_sta);
+
+    float wHc = 0.f, wVc = 0.f, wHa = 0.f, wVa = 0.f;
+    // shared-memory neighbours, clamped to the tile (a clamped read returns the thread's own value)
+    const int o_c = ty * BX + tx;
+    const int o_r = ty * BX + min(tx + 1, BX - 1), o_l = ty * BX + max(tx - 1, 0);
+    const int o_d = min(ty + 1, BY - 1) * BX + tx, o_u = max(ty - 1, 0) * BX + tx;
+    if (SMOOTH) {
+        if (ty < SY) { wHc = __ldg(p.w_smooth); wHa = __ldg(p.w_smooth + 2); }
+        if (tx < SX) { wVc = __ldg(p.w_smooth + 1); wVa = __ldg(p.w_smooth + 3); }
+    }
+    const bool want_sums = SMOOTH && p.smooth != nullptr;
+    float sxr = 0.f, syr = 0.f, sxa = 0.f, sya = 0.f;
+
+    const int D = p.view.D;
+    const float qwf = (float)p.view.qw, qhf = (float)p.view.qh;
+    int d = 0;                                                    // next plane to test
+    for (int k = 0;; ++k) {
+        // slot k of this pixel = its k-th hit plane along the ray (utils.py:64-69): advance to the next plane
+        // whose quad under the ray exists.  Nothing is known in advance; the loop ends when no thread of the
+        // tile (warp, without the regulariser) has a slot left.
+        Geo tp;
+        tp.kind = 0; tp.o00 = tp.o10 = tp.o01 = tp.o11 = 0u;
+        tp.w00 = tp.w10 = tp.w01 = tp.w11 = 0.f;
+        while (d < D) {
+            float gx, gy;
+            const bool hit = plane_grid_lean(&p.view.hom[d * 9], u, v, qwf, qhf, gx, gy);
+            const int dd = d++;
+            if (!hit) continue;
+            int qx, qy;
+            const float4* qp = quad_at(p, dd, gx, gy, qx, qy);
+            const int4 qb = __ldg(reinterpret_cast<const int4*>(qp + 1));
+            if (qb.z == 0) continue;
+            tp = geo_from_quad(p, qp, qb, qx, qy, gx, gy);
+            break;
+        }
+        const bool has = tp.kind != 0;
+        float4 val[TF];
+#pragma unroll
+        for (int f = 0; f < TF; ++f) val[f] = make_float4(0.f, 0.f, 0.f, 0.f);   // zero canvas (MPV.py:441)
+        if (tp.kind == 2) {
+#pragma unroll
+            for (int f = 0; f < TF; ++f) val[f] = sample_lean(ab[f], tp);
+        } else if (tp.kind == 1) {
+            const float4 s = sample_lean(sb, tp);
+#pragma unroll
+            for (int f = 0; f < TF; ++f) val[f] = s;
+        }
+        if (!SMOOTH) {
+            if (!__any_sync(0xffffffffu, has)) break;
+        }
+        float4 gs[TF];   // dL/d(activated value) from the smoothness terms
+#pragma unroll
+        for (int f = 0; f < TF; ++f) gs[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (SMOOTH) {
+            float4* ex = &s_ex[k & 1][0][0][0];
+#pragma unroll
+            for (int f = 0; f < TF; ++f) ex[f * (BX * BY) + o_c] = val[f];
+            if (!__syncthreads_or(has)) break;                    // (block-uniform)
+#pragma unroll
+            for (int f = 0; f < TF; ++f) {
+                const float4 c = val[f];
+                const float4 r = ex[f * (BX * BY) + o_r], l = ex[f * (BX * BY) + o_l];
+                const float4 dn = ex[f * (BX * BY) + o_d], up = ex[f * (BX * BY) + o_u];
+                // d|a-b|/da = sign(a-b); pairs that do not exist compare a value with itself
+                gs[f].x = fmaf(wHc, sgn2(c.x, r.x, l.x), wVc * sgn2(c.x, dn.x, up.x));
+                gs[f].y = fmaf(wHc, sgn2(c.y, r.y, l.y), wVc * sgn2(c.y, dn.y, up.y));
+                gs[f].z = fmaf(wHc, sgn2(c.z, r.z, l.z), wVc * sgn2(c.z, dn.z, up.z));
+                gs[f].w = fmaf(wHa, sgn2(c.w, r.w, l.w), wVa * sgn2(c.w, dn.w, up.w));
+                if (want_sums) {                                   // the regulariser values themselves (MPV.py:517-531)
+                    sxr += fabsf(c.x - r.x) + fabsf(c.y - r.y) + fabsf(c.z - r.z);
+                    sxa += fabsf(c.w - r.w);
+                    syr += fabsf(c.x - dn.x) + fabsf(c.y - dn.y) + fabsf(c.z - dn.z);
+                    sya += fabsf(c.w - dn.w);
+                }
+            }
+            // the other buffer is rewritten next iteration; its readers finished before this barrier
+        }
+        // ---- hand-over keys: (kind, texel offset) of the taps a lane writes / could absorb; lanes that do not
+        // write (replicas, empty slots) carry keys that match nothing
+        const bool wr = active && has;
+        const unsigned ktag = (unsigned)tp.kind << 30;
+        const unsigned rk0 = wr ? (tp.o00 | ktag) : 0xffffffffu, rk1 = wr ? (tp.o01 | ktag) : 0xffffffffu;
+        const unsigned sk0 = wr ? (tp.o10 | ktag) : 0xfffffffeu, sk1 = wr ? (tp.o11 | ktag) : 0xfffffffeu;
+        const unsigned up_sk0 = __shfl_up_sync(0xffffffffu, sk0, 1), up_sk1 = __shfl_up_sync(0xffffffffu, sk1, 1);
+        const unsigned dn_rk0 = __shfl_down_sync(0xffffffffu, rk0, 1), dn_rk1 = __shfl_down_sync(0xffffffffu, rk1, 1);
+        const bool recv0 = (tx > 0) & (up_sk0 == rk0), recv1 = (tx > 0) & (up_sk1 == rk1);
+        const bool sent0 = (tx < BX - 1) & (dn_rk0 == sk0), sent1 = (tx < BX - 1) & (dn_rk1 == sk1);
+        const float wu10s = __shfl_up_sync(0xffffffffu, tp.w10, 1), wu11s = __shfl_up_sync(0xffffffffu, tp.w11, 1);
+        const float wu10 = recv0 ? wu10s : 0.f, wu11 = recv1 ? wu11s : 0.f;
+        float4 gsta = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int f = 0; f < TF; ++f) {
+            // gradient w.r.t. the pre-sigmoid bilinear sample; an empty slot has c = 0, hence gl = 0
+            const float4 c = val[f];
+            const float a = c.w, om = 1.f - a;
+            const float bw = a * Tr[f];
+            const float gc = g0[f] * c.x + g1[f] * c.y + g2[f] * c.z;
+            pre[f] = fmaf(bw, gc, pre[f]);
+            const float S = tot[f] - pre[f];
+            float4 gl;
+            gl.x = fmaf(g0[f], bw, gs[f].x) * (c.x - c.x * c.x);
+            gl.y = fmaf(g1[f], bw, gs[f].y) * (c.y - c.y * c.y);
+            gl.z = fmaf(g2[f], bw, gs[f].z) * (c.z - c.z * c.z);
+            gl.w = a * (om * fmaf(Tr[f], gc, gs[f].w) - S);
+            Tr[f] *= om;
+            gsta.x += gl.x; gsta.y += gl.y; gsta.z += gl.z; gsta.w += gl.w;   // static tiles: sum over frames (MPV.py:445)
+            const float4 gl_up = shfl_up4(gl);
+            if (wr && tp.kind == 2 && !(p.dbg_nored & 1)) scatter_taps(gb[f], tp, gl, gl_up, wu10, wu11, sent0, sent1);
+        }
+        if (__any_sync(0xffffffffu, tp.kind == 1)) {
+            const float4 gl_up = shfl_up4(gsta);
+            if (wr && tp.kind == 1) scatter_taps(gsb, tp, gsta, gl_up, wu10, wu11, sent0, sent1);
+        }
+    }
+    if (want_sums) {
+        __shared__ float s_sum[4][(BX * BY) / 32];
+        const int warp = (ty * BX + tx) >> 5;
+        const float m = owned ? 1.f : 0.f;
+        const float a0 = warp_sum(sxr * m), a1 = warp_sum(syr * m), a2 = warp_sum(sxa * m), a3 = warp_sum(sya * m);
+        if (tx == 0) { s_sum[0][warp] = a0; s_sum[1][warp] = a1; s_sum[2][warp] = a2; s_sum[3][warp] = a3; }
+        __syncthreads();
+        if (ty == 0 && tx < 4) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < (BX * BY) / 32; ++i) acc += (double)s_sum[tx][i];
+            atomicAdd(&p.smooth[tx], acc);
+        }
+    }
+}
+
+}  // namespace vl3d
