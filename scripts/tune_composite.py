@@ -61,14 +61,9 @@ def main():
     variants = [
         ("v1", dict(VL3D_COMPOSITE_V1="1")),
         ("lean", dict()),
-        ("lean fwd3m3", dict(VL3D_FWD_MINB="3")),
-        ("lean fwd3m5", dict(VL3D_FWD_MINB="5")),
         ("lean fwd2", dict(VL3D_FWD_TF="2")),
-        ("lean fwd2m5", dict(VL3D_FWD_TF="2", VL3D_FWD_MINB="5")),
-        ("lean fwd2m6", dict(VL3D_FWD_TF="2", VL3D_FWD_MINB="6")),
-        ("lean fwd4m4", dict(VL3D_FWD_TF="4", VL3D_FWD_MINB="4")),
         ("lean fwd4", dict(VL3D_FWD_TF="4")),
-        ("lean fwd6", dict(VL3D_FWD_TF="6")),
+        ("lean fwd4m4", dict(VL3D_FWD_TF="4", VL3D_FWD_MINB="4")),
         ("lean bwd1", dict(VL3D_BWD_TF="1")),
         ("lean bwd3", dict(VL3D_BWD_TF="3")),
         ("lean bwd4", dict(VL3D_BWD_TF="4")),

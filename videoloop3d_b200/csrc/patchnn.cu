@@ -14,6 +14,8 @@
 // (min over all queries) and the running first-min argmin never need the whole matrix.
 // Distances are direct fp32 sums of squared differences (no |x|^2+|y|^2-2xy cancellation, no
 // tensor cores): index parity with an fp64 search is limited only by exact near-ties.
+#include <stdlib.h>
+
 #include "vl3d_common.cuh"
 
 namespace vl3d {
@@ -22,6 +24,7 @@ constexpr int NN_THREADS = 256;
 constexpr int NN_CF = 64;      // frames per chunk (both x block and y chunk)
 constexpr int NN_R = 4;        // register tile edge
 constexpr int NN_MAX_N1 = 256;
+constexpr int NB = 3;         // strip kernel: staging buffers (rows in flight = NB - 1)
 
 struct SearchParams {
     vl3d_loss_desc d;
@@ -211,18 +214,28 @@ __device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_
     const int bytes = valid ? 4 : 0;                                // src-size 0 => zero fill
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 template <int M, bool VEC>
-__global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_constant__ StripParams P) {
+__global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip_kernel(const __grid_constant__ StripParams P) {
     extern __shared__ __align__(16) float smem[];
     const vl3d_loss_desc& L = P.d;
     const int G4 = P.groups, NTA = P.nta, NTB = P.ntb, XF = 4 * NTA, CF = 4 * NTB;
+    // staging layout: [buffer][frame][G4S] float4, group index fastest.  A thread's operand address is then a
+    // per-thread base + an immediate per group (no address arithmetic in the FMA loop), and with G4S odd the
+    // lanes of a quarter-warp (consecutive frames, 16*G4S bytes apart) hit disjoint banks.
+    const int G4S = G4 | 1;
     const int nthreads = NTA * NTB;
-    float4* xs4 = reinterpret_cast<float4*>(smem);                  // [2][G4][XF]
-    float4* ys4 = xs4 + 2 * G4 * XF;                                // [2][G4][CF]
-    float* Gs = reinterpret_cast<float*>(ys4 + 2 * G4 * CF);        // [XF][CF+1]
+    float4* xs4 = reinterpret_cast<float4*>(smem);                  // [NBUF][XF][G4S]
+    float4* ys4 = xs4 + NB * G4S * XF;                         // [NBUF][CF][G4S]
+    float* Gs = reinterpret_cast<float*>(ys4 + NB * G4S * CF); // [XF][CF+1]
     float* Ds = Gs + XF * (CF + 1);                                 // [n1][CF+1]
     float* colmin = Ds + (size_t)L.n1 * (CF + 1);                   // [CF]
     float* best_val = colmin + CF;                                  // [SL][n1]
@@ -237,6 +250,13 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
     const int rem = p - M * s;                                      // rows of the (M+1)-th group used by a patch
     const float inv_d = 1.f / (float)(3 * pt * p * p);
     const int ta = tid / NTB, tb = tid - ta * NTB;
+    unsigned xsa[NN_R], ysa[NN_R];                              // shared-space byte addresses of the thread's operands
+#pragma unroll
+    for (int i = 0; i < NN_R; ++i) {
+        xsa[i] = (unsigned)__cvta_generic_to_shared(xs4 + (size_t)(ta + NTA * i) * G4S);
+        ysa[i] = (unsigned)__cvta_generic_to_shared(ys4 + (size_t)(tb + NTB * i) * G4S);
+    }
+    const unsigned xbuf_bytes = (unsigned)(G4S * XF) * 16u, ybuf_bytes = (unsigned)(G4S * CF) * 16u;
     const int tx_used = (L.n1 - 1) * st + pt, ty_used = (L.n2 - 1) * st + pt;
     const int nrows = (k1 - 1 - k0) * s + p;                        // pixel rows swept by this strip
     const int ybase = k0 * s;
@@ -264,17 +284,17 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
                                    : P.x + (size_t)gfc * L.x_sf + (size_t)c * L.x_sc + (size_t)(ybase + row) * L.x_sr + x0;
             if (VEC) {
                 const int nch = (p + 3) >> 2;
-                float4* d4 = (isy ? ys4 + (size_t)buf * G4 * CF : xs4 + (size_t)buf * G4 * XF) + (size_t)c * nch * nf + fr;
+                float4* d4 = (isy ? ys4 + (size_t)buf * G4S * CF : xs4 + (size_t)buf * G4S * XF) + (size_t)fr * G4S + c * nch;
                 for (int j = 0; j < nch; ++j) {
                     const int nval = ok ? min(4, p - 4 * j) * 4 : 0;
-                    const unsigned d = (unsigned)__cvta_generic_to_shared(d4 + (size_t)j * nf);
+                    const unsigned d = (unsigned)__cvta_generic_to_shared(d4 + j);
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src + 4 * j), "r"(nval) : "memory");
                 }
             } else {
-                float* dst = reinterpret_cast<float*>(isy ? ys4 + (size_t)buf * G4 * CF : xs4 + (size_t)buf * G4 * XF);
-                float* d0 = dst + fr * 4;
+                float* dst = reinterpret_cast<float*>(isy ? ys4 + (size_t)buf * G4S * CF : xs4 + (size_t)buf * G4S * XF);
+                float* d0 = dst + (size_t)fr * G4S * 4;
                 int e = c * p;
-                for (int dx = 0; dx < p; ++dx, ++e) cp_async_f32(d0 + (e >> 2) * (nf * 4) + (e & 3), src + dx, ok);
+                for (int dx = 0; dx < p; ++dx, ++e) cp_async_f32(d0 + e, src + dx, ok);
             }
         }
         cp_async_commit();
@@ -282,7 +302,7 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
     // packed layout: the padding lanes of the last float4 group never change; zero them once in both buffers
     if (!VEC) {
         const int npad = 4 * G4 - 3 * p;
-        for (int id = tid; id < 2 * npad * (XF + CF); id += nthreads) {
+        for (int id = tid; id < NB * npad * (XF + CF); id += nthreads) {
             const int buf = id / (npad * (XF + CF));
             const int r2 = id - buf * npad * (XF + CF);
             const int e = 3 * p + r2 / (XF + CF);
@@ -290,8 +310,8 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
             const bool isy = q >= XF;
             const int fr = isy ? q - XF : q;
             const int nf = isy ? CF : XF;
-            float* dst = reinterpret_cast<float*>(isy ? ys4 + (size_t)buf * G4 * CF : xs4 + (size_t)buf * G4 * XF);
-            dst[((e >> 2) * nf + fr) * 4 + (e & 3)] = 0.f;
+            float* dst = reinterpret_cast<float*>(isy ? ys4 + (size_t)buf * G4S * CF : xs4 + (size_t)buf * G4S * XF);
+            dst[(size_t)fr * G4S * 4 + e] = 0.f;
         }
     }
 
@@ -313,32 +333,54 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
             }
 
         __syncthreads();                                            // previous chunk's readers are done
+        // three staging buffers: rows r+1 and r+2 are in flight while row r is consumed (one row of arithmetic
+        // is about as long as a cp.async round trip, so a single row of lookahead left warps waiting here)
         stage(c0, 0, 0);
+        if (NB > 2 && nrows > 1) stage(c0, 1, 1);
+        int buf = 0;
         for (int row = 0; row < nrows; ++row) {
-            const int buf = row & 1;
-            cp_async_wait_all();
-            __syncthreads();                                        // row `row` landed; buffer buf^1 is free
-            if (row + 1 < nrows) stage(c0, row + 1, buf ^ 1);       // overlaps the arithmetic below
+            if (NB > 2 && row + 1 < nrows) cp_async_wait_1(); else cp_async_wait_all();
+            __syncthreads();                                        // row `row` landed; the buffer of row-1 is free
+            if (row + NB - 1 < nrows) stage(c0, row + NB - 1, buf >= 1 ? buf - 1 : NB - 1);   // == (buf + NB - 1) % NB
             const int grp = row / s, rin = row - grp * s;           // group of s rows, row inside the group
             if (M > 0 || rin < p) {                                 // (p < s: rows between patches are unused)
-                const float4* xp = xs4 + (size_t)buf * G4 * XF + ta;
-                const float4* yp = ys4 + (size_t)buf * G4 * CF + tb;
-                for (int g = 0; g < G4; ++g, xp += XF, yp += CF) {
-                    float4 xa[NN_R], ya[NN_R];
+                unsigned xa_[NN_R], ya_[NN_R];
 #pragma unroll
-                    for (int i = 0; i < NN_R; ++i) xa[i] = xp[NTA * i];
+                for (int i = 0; i < NN_R; ++i) {
+                    xa_[i] = xsa[i] + (unsigned)buf * xbuf_bytes;
+                    ya_[i] = ysa[i] + (unsigned)buf * ybuf_bytes;
+                }
+                auto fma_group = [&](int off) {
+                    {
+                        float4 xa[NN_R], ya[NN_R];
 #pragma unroll
-                    for (int j = 0; j < NN_R; ++j) ya[j] = yp[NTB * j];
+                        for (int i = 0; i < NN_R; ++i) xa[i] = lds128(xa_[i] + off);
 #pragma unroll
-                    for (int i = 0; i < NN_R; ++i)
+                        for (int j = 0; j < NN_R; ++j) ya[j] = lds128(ya_[j] + off);
 #pragma unroll
-                        for (int j = 0; j < NN_R; ++j) {
-                            float dlt;
-                            dlt = xa[i].x - ya[j].x; cur[i][j] = fmaf(dlt, dlt, cur[i][j]);
-                            dlt = xa[i].y - ya[j].y; cur[i][j] = fmaf(dlt, dlt, cur[i][j]);
-                            dlt = xa[i].z - ya[j].z; cur[i][j] = fmaf(dlt, dlt, cur[i][j]);
-                            dlt = xa[i].w - ya[j].w; cur[i][j] = fmaf(dlt, dlt, cur[i][j]);
-                        }
+                        for (int i = 0; i < NN_R; ++i)
+#pragma unroll
+                            for (int j = 0; j < NN_R; ++j) {
+                                float dlt;
+                                dlt = xa[i].x - ya[j].x; cur[i][j] = fmaf(dlt, dlt, cur[i][j]);
+                                dlt = xa[i].y - ya[j].y; cur[i][j] = fmaf(dlt, dlt, cur[i][j]);
+                                dlt = xa[i].z - ya[j].z; cur[i][j] = fmaf(dlt, dlt, cur[i][j]);
+                                dlt = xa[i].w - ya[j].w; cur[i][j] = fmaf(dlt, dlt, cur[i][j]);
+                            }
+                    }
+                };
+                if (VEC) {                                          // G4 = 3 * ceil(p/4): three groups per trip
+                    for (int g = 0; g < G4; g += 3) {
+                        fma_group(0); fma_group(16); fma_group(32);
+#pragma unroll
+                        for (int i = 0; i < NN_R; ++i) { xa_[i] += 48; ya_[i] += 48; }
+                    }
+                } else {
+                    for (int g = 0; g < G4; ++g) {
+                        fma_group(0);
+#pragma unroll
+                        for (int i = 0; i < NN_R; ++i) { xa_[i] += 16; ya_[i] += 16; }
+                    }
                 }
             }
             // does a patch end on this row?  patch kr (relative) ends at row kr*s + p - 1 = (kr+M)*s + rem - 1
@@ -364,27 +406,61 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
                     Ds[(size_t)il * (CF + 1) + jl] = sum * inv_d;
                 }
                 __syncthreads();
+                // The normaliser and the argmin are short reductions over n1 x cj numbers; done by one thread per
+                // column / query they are long dependent chains (LDS + IEEE division per step) during which
+                // most of the CTA idles, so each is split over PA / PB threads and the partial results are
+                // combined in order (same first-minimum / NaN rules as the sequential scan).
+                float* part_f = Gs;                                 // Gs is free once Ds is built
                 if (L.use_alpha) {
+                    const int PA = min(min(8, max(1, nthreads / cj)), XF), RA = (L.n1 + PA - 1) / PA;
+                    for (int id = tid; id < cj * PA; id += nthreads) {
+                        const int part = id / cj, jl = id - part * cj;
+                        const int i1 = min((part + 1) * RA, L.n1);
+                        float mn = INFINITY;
+                        for (int i = part * RA; i < i1; ++i) {
+                            const float vv = Ds[(size_t)i * (CF + 1) + jl];
+                            mn = (vv < mn || vv != vv) ? vv : mn;
+                        }
+                        part_f[part * (CF + 1) + jl] = mn;
+                    }
+                    __syncthreads();
                     for (int jl = tid; jl < cj; jl += nthreads) {
                         float mn = INFINITY;
-                        for (int i = 0; i < L.n1; ++i) {
-                            const float vv = Ds[(size_t)i * (CF + 1) + jl];
+                        for (int q = 0; q < PA; ++q) {
+                            const float vv = part_f[q * (CF + 1) + jl];
                             mn = (vv < mn || vv != vv) ? vv : mn;
                         }
                         colmin[jl] = L.alpha + mn;
                     }
                     __syncthreads();
                 }
-                for (int i = tid; i < L.n1; i += nthreads) {
-                    float bv = best_val[kr * L.n1 + i];
-                    int bi = best_idx[kr * L.n1 + i];
-                    for (int jl = 0; jl < cj; ++jl) {
-                        float vv = Ds[(size_t)i * (CF + 1) + jl];
-                        if (L.use_alpha) vv = vv / colmin[jl];
-                        const bool better = (vv < bv) || (vv != vv && bv == bv);
-                        if (better) { bv = vv; bi = j0 + jl; }
+                {
+                    const int PB = min(8, max(1, nthreads / L.n1)), SB = (cj + PB - 1) / PB;
+                    int* part_i = reinterpret_cast<int*>(part_f + PB * L.n1);
+                    for (int id = tid; id < L.n1 * PB; id += nthreads) {
+                        const int part = id / L.n1, i = id - part * L.n1;
+                        const int jb = min((part + 1) * SB, cj);
+                        float bv = INFINITY;
+                        int bi = -1;
+                        for (int jl = part * SB; jl < jb; ++jl) {
+                            float vv = Ds[(size_t)i * (CF + 1) + jl];
+                            if (L.use_alpha) vv = vv / colmin[jl];
+                            const bool better = (vv < bv) || (vv != vv && bv == bv);
+                            if (better) { bv = vv; bi = j0 + jl; }
+                        }
+                        part_f[id] = bv; part_i[id] = bi;
                     }
-                    best_val[kr * L.n1 + i] = bv; best_idx[kr * L.n1 + i] = bi;
+                    __syncthreads();
+                    for (int i = tid; i < L.n1; i += nthreads) {
+                        float bv = best_val[kr * L.n1 + i];
+                        int bi = best_idx[kr * L.n1 + i];
+                        for (int q = 0; q < PB; ++q) {
+                            const float vv = part_f[q * L.n1 + i];
+                            const bool better = (vv < bv) || (vv != vv && bv == bv);
+                            if (better) { bv = vv; bi = part_i[q * L.n1 + i]; }
+                        }
+                        best_val[kr * L.n1 + i] = bv; best_idx[kr * L.n1 + i] = bi;
+                    }
                 }
             }
             if (rin == s - 1) {                                     // group complete: shift the history
@@ -398,6 +474,7 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
                         cur[i][j] = 0.f;
                     }
             }
+            buf = buf + 1 < NB ? buf + 1 : 0;
         }
         j0 = j1;
     }
@@ -408,9 +485,9 @@ __global__ void __launch_bounds__(NN_THREADS) patchnn_strip_kernel(const __grid_
     }
 }
 
-static size_t strip_smem_bytes(const vl3d_loss_desc* L, int nta, int ntb, int SL) {
-    const int G4 = (3 * L->p + 3) / 4, XF = 4 * nta, CF = 4 * ntb;
-    size_t fl = (size_t)4 * 2 * G4 * (XF + CF) + (size_t)XF * (CF + 1) + (size_t)L->n1 * (CF + 1) + CF + 2 * (size_t)SL * L->n1;
+static size_t strip_smem_bytes(const vl3d_loss_desc* L, int nta, int ntb, int SL, int nbuf) {
+    const int G4 = ((3 * L->p + 3) / 4) | 1, XF = 4 * nta, CF = 4 * ntb;
+    size_t fl = (size_t)4 * nbuf * G4 * (XF + CF) + (size_t)XF * (CF + 1) + (size_t)L->n1 * (CF + 1) + CF + 2 * (size_t)SL * L->n1;
     return fl * sizeof(float);
 }
 
@@ -669,13 +746,13 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
         while (SL > 2 && (long long)desc->wo * ((rows + SL - 1) / SL) < 148 * 6) SL >>= 1;
         if (SL > rows) SL = rows;
         P.SL = SL;
-        const size_t smem = strip_smem_bytes(desc, P.nta, P.ntb, SL);
-        VL3D_REQUIRE(smem <= 200 * 1024, VL3D_ERANGE, "patch_size %d / n1 %d need %zu B of shared memory", desc->p,
-                     desc->n1, smem);
         const int P4 = (desc->p + 3) / 4 * 4;
         const bool vec = desc->s % 4 == 0 && (3 * desc->p + 3) / 4 == 3 * P4 / 4 &&
                          ((desc->x_sf | desc->x_sc | desc->x_sr | desc->y_sf | desc->y_sc | desc->y_sr) & 3) == 0 &&
                          (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+        const size_t smem = strip_smem_bytes(desc, P.nta, P.ntb, SL, NB);
+        VL3D_REQUIRE(smem <= 200 * 1024, VL3D_ERANGE, "patch_size %d / n1 %d need %zu B of shared memory", desc->p,
+                     desc->n1, smem);
         void (*kern)(StripParams) =
             vec ? (M == 0 ? patchnn_strip_kernel<0, true> : M == 1 ? patchnn_strip_kernel<1, true>
                  : M == 2 ? patchnn_strip_kernel<2, true> : patchnn_strip_kernel<3, true>)
