@@ -319,9 +319,9 @@ def run_ours(args):
                         copy_stream.wait_event(done[nxt])             # buffer `nxt` was consumed by step i-1
                     load(bufs[nxt])
                     ready[nxt].record()
-            torch.cuda.current_stream().wait_event(ready[cur])
-            # pose / intrinsics stay on the host: the view descriptor (plane homographies) is built there
-            o = step.step(H, W, ext_h, intr_h, bufs[cur], cfg, lr)
+            # pose / intrinsics stay on the host: the view descriptor (plane homographies) is built there;
+            # the step waits for the copy only where it first reads the target video (after the render)
+            o = step.step(H, W, ext_h, intr_h, bufs[cur], cfg, lr, res_ready=ready[cur])
             done[cur].record()
             loss_host.copy_(o["loss"].reshape(1), non_blocking=True)
         torch.cuda.synchronize()

@@ -192,7 +192,10 @@ class FusedLoopStep:
         ops.adam_step(p, g, st[0], st[1], self.t, lr, self.betas[0], self.betas[1], self.eps)
 
     @torch.no_grad()
-    def step(self, h, w, tar_extrin, tar_intrin, res, losscfg, lr, optimise=True):
+    def step(self, h, w, tar_extrin, tar_intrin, res, losscfg, lr, optimise=True, res_ready=None):
+        """`res_ready`: optional CUDA event after which `res` is valid (e.g. recorded behind an asynchronous
+        host-to-device copy on another stream); the render does not need the target video, so the wait is
+        placed right before the looping loss and the copy overlaps the render."""
         m = self.model
         args = m.args
         dev = m.atlas_dyn.device
@@ -245,6 +248,8 @@ class FusedLoopStep:
                     rgb_pad[T:T + pad].copy_(rgb_pad[:pad])          # loop pad (MPV.py:490-492)
 
         # ---- looping loss
+        if res_ready is not None:
+            torch.cuda.current_stream().wait_event(res_ready)
         xscale = None
         if args.scale_invariant:
             with self._timed("scale_invariant"):
