@@ -146,8 +146,9 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
-# `ncu --set full` capture of this same command (profiles/r01_final_ncu_full_step720p.md); None if not captured.
-NCU_TRAFFIC_BYTES = {("step720p", 1, "composite_bwd"): 42.256709e9 + 20.444168e9}
+# `ncu --set full` capture of this same command (profiles/r01b_ncu_full_step720p.md); None if not captured.
+NCU_TRAFFIC_BYTES = {("step720p", 1, "composite_bwd"): 42.263852e9 + 20.460910e9,
+                     ("step720p", 1, "composite_fwd"): 20.688009e9 + 0.552415e9}
 
 
 def algorithmic_bytes(wl, frames):
