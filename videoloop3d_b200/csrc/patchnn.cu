@@ -491,6 +491,12 @@ static size_t strip_smem_bytes(const vl3d_loss_desc* L, int nta, int ntb, int SL
     return fl * sizeof(float);
 }
 
+}  // namespace vl3d
+
+#include "patchnn_strip8.cuh"
+
+namespace vl3d {
+
 // ------------------------------------------------------------------------------------------------
 // vote / merge + robust loss + its derivative: one thread per pixel of the full x buffer.
 //   y2x[c,t',py,px] = mean over covering patches (i,j,k) of y[c, NN_ij[k]*st + t'-k*st, py, px]
@@ -721,6 +727,52 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
     const int M = desc->p / desc->s;
     if (tx_used <= NN_CF && M <= 3 && desc->p <= 32) {
         // strip kernel: rows shared between vertically overlapping patches
+        {   // 4 x 8 register tiles (patchnn_strip8.cuh) for the common shapes; VL3D_NN_TILE8=0: tuning aid
+            const char* t8 = getenv("VL3D_NN_TILE8");
+            const int P4 = (desc->p + 3) / 4 * 4;
+            const bool vec = desc->s % 4 == 0 && (3 * desc->p + 3) / 4 == 3 * P4 / 4 &&
+                             ((desc->x_sf | desc->x_sc | desc->x_sr | desc->y_sf | desc->y_sc | desc->y_sr) & 3) == 0 &&
+                             (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+            if (vec && (M == 1 || M == 2) && !(t8 && atoi(t8) == 0)) {
+                StripParams P{};
+                P.d = *desc; P.x = x; P.y = y; P.nn = nn_out; P.groups = 3 * (P4 / 4);
+                P.row0 = row_begin; P.row1 = row_end;
+                P.nta = (tx_used + S8_TI - 1) / S8_TI;
+                if (P.nta < 2) P.nta = 2;
+                int best_ntb = 0; long long best_cost = 0;
+                for (int ntb = (desc->pt + S8_TJ - 1) / S8_TJ + 1; ntb <= NN_THREADS / P.nta; ++ntb) {
+                    const int cands = (S8_TJ * ntb - desc->pt) / desc->st + 1;
+                    const int chunks = (desc->n2 + cands - 1) / cands;
+                    const long long cost = (long long)chunks * S8_TJ * ntb * 64 + 4000LL * chunks;
+                    if (P.nta * ntb < 64) continue;
+                    if (best_ntb == 0 || cost < best_cost) { best_ntb = ntb; best_cost = cost; }
+                }
+                const int rows = row_end - row_begin;
+                int SL = 16;
+                while (SL > 2 && (long long)desc->wo * ((rows + SL - 1) / SL) < 148 * 6) SL >>= 1;
+                if (SL > rows) SL = rows;
+                P.ntb = best_ntb; P.SL = SL;
+                const size_t smem = best_ntb ? strip8_smem_bytes(desc, P.nta, P.ntb, SL) : (size_t)1 << 30;
+                // measured on B200 (scripts/tune_search.py): the wide chunk pays when the whole candidate set is
+                // covered in at most two sweeps over the query rows (n2 = 256: 20.2 vs 22.0 ms at 720p); with more
+                // sweeps (n2 = 1024: 88 vs 79 ms) or few query frames (T = 24) the 4 x 4 kernel is faster.
+                const int cands8 = best_ntb ? (S8_TJ * best_ntb - desc->pt) / desc->st + 1 : 1;
+                const bool few_sweeps = (desc->n2 + cands8 - 1) / cands8 <= 2 && tx_used >= 40;
+                if (few_sweeps && smem <= 110 * 1024 && desc->n1 <= S8_TI * P.nta) {
+                    const int tail = desc->p - (P4 - 4);
+                    void (*kern)(StripParams) =
+                        M == 1 ? (tail == 1 ? patchnn_strip8_kernel<1, 1> : tail == 2 ? patchnn_strip8_kernel<1, 2>
+                                : tail == 3 ? patchnn_strip8_kernel<1, 3> : patchnn_strip8_kernel<1, 4>)
+                               : (tail == 1 ? patchnn_strip8_kernel<2, 1> : tail == 2 ? patchnn_strip8_kernel<2, 2>
+                                : tail == 3 ? patchnn_strip8_kernel<2, 3> : patchnn_strip8_kernel<2, 4>);
+                    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+                    if (ce != cudaSuccess) return set_err((int)ce, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
+                    dim3 grid(desc->wo, (rows + SL - 1) / SL);
+                    kern<<<grid, P.nta * P.ntb, smem, st>>>(P);
+                    return check_launch("patchnn_search(strip8)");
+                }
+            }
+        }
         StripParams P{};
         P.d = *desc; P.x = x; P.y = y; P.nn = nn_out; P.groups = (3 * desc->p + 3) / 4;
         P.row0 = row_begin; P.row1 = row_end;
