@@ -64,7 +64,13 @@ typedef struct vl3d_view {
     int32_t sta_h, sta_w;    /* static atlas size in texels */
     float   cx, cy;
     float   hom[VL3D_MAX_PLANES * 9];
+    int32_t flags;           /* VL3D_VIEW_* bits (hints; results never depend on them) */
 } vl3d_view;
+
+/* vl3d_view.flags: every plane's quads are dynamic and tile ONE axis-aligned rectangle of atlas_dyn contiguously
+ * (the dense layout of MPV.py:75-81), so the footprint of a screen tile on a plane is one atlas rectangle and the
+ * render may fetch it with a single TMA box per (tile, plane, frame) instead of four loads per pixel. */
+#define VL3D_VIEW_RECT_PLANES 1
 
 /* Looping-loss problem descriptor (fitted crop; utils_vid.py:305-320).
  * x = rendered (looped, scaled) video, frames tx in [0, t); y = target video, frames in [0, F).

@@ -61,9 +61,14 @@ def main():
     variants = [
         ("v1", dict(VL3D_COMPOSITE_V1="1")),
         ("lean", dict()),
-        ("lean fwd2", dict(VL3D_FWD_TF="2")),
-        ("lean fwd4", dict(VL3D_FWD_TF="4")),
-        ("lean fwd4m4", dict(VL3D_FWD_TF="4", VL3D_FWD_MINB="4")),
+        ("lean notma", dict(VL3D_TMA="0")),
+        ("tma s2", dict(VL3D_TMA_STAGES="2")),
+        ("tma s4", dict(VL3D_TMA_STAGES="4")),
+        ("tma tf2 s4", dict(VL3D_TMA_TF="2", VL3D_TMA_STAGES="4")),
+        ("tma tf4 s2", dict(VL3D_TMA_TF="4", VL3D_TMA_STAGES="2")),
+        ("tma tf4", dict(VL3D_TMA_TF="4")),
+        ("lean fwd2", dict(VL3D_FWD_TF="2", VL3D_TMA="0")),
+        ("lean fwd4", dict(VL3D_FWD_TF="4", VL3D_TMA="0")),
         ("lean bwd1", dict(VL3D_BWD_TF="1")),
         ("lean bwd3", dict(VL3D_BWD_TF="3")),
         ("lean bwd4", dict(VL3D_BWD_TF="4")),
@@ -72,7 +77,7 @@ def main():
     if a.only:
         keep = set(a.only.split(","))
         variants = [v for v in variants if v[0] in keep]
-    knobs = ("VL3D_COMPOSITE_V1", "VL3D_FWD_TF", "VL3D_FWD_MINB", "VL3D_BWD_TF", "VL3D_BWD_NORED")
+    knobs = ("VL3D_COMPOSITE_V1", "VL3D_FWD_TF", "VL3D_FWD_MINB", "VL3D_BWD_TF", "VL3D_BWD_NORED", "VL3D_TMA", "VL3D_TMA_TF", "VL3D_TMA_STAGES")
     ref = None
     print(f"{a.workload}: {H}x{W}, D={wl['D']}, T={T}; algorithmic GB fwd {fwd_b / 1e9:.2f} bwd {bwd_b / 1e9:.2f}")
     for name, env in variants:

@@ -100,7 +100,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.vl3d_version() == 100
-    assert ctypes.sizeof(_lib.View) == 4 * 9 + 4 * 2 + 4 * 32 * 9
+    assert ctypes.sizeof(_lib.View) == 4 * 9 + 4 * 2 + 4 * 32 * 9 + 4       # ... + flags
     assert ctypes.sizeof(_lib.LossDesc) == 4 * 12 + 8 * 6 + 8
 
 

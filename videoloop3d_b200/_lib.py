@@ -19,7 +19,10 @@ class Quad(C.Structure):
 class View(C.Structure):
     _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("D", C.c_int32), ("qh", C.c_int32), ("qw", C.c_int32),
                 ("dyn_h", C.c_int32), ("dyn_w", C.c_int32), ("sta_h", C.c_int32), ("sta_w", C.c_int32),
-                ("cx", C.c_float), ("cy", C.c_float), ("hom", C.c_float * (MAX_PLANES * 9))]
+                ("cx", C.c_float), ("cy", C.c_float), ("hom", C.c_float * (MAX_PLANES * 9)), ("flags", C.c_int32)]
+
+
+VIEW_RECT_PLANES = 1
 
 
 class LossDesc(C.Structure):

@@ -685,6 +685,7 @@ __global__ void __launch_bounds__(BX* BY) composite_bwd_v1_kernel(const __grid_c
 }  // namespace vl3d
 
 #include "composite_lean.cuh"
+#include "composite_tma.cuh"
 
 namespace vl3d {
 
@@ -700,7 +701,7 @@ static bool use_v1() { return env_int("VL3D_COMPOSITE_V1", 0) != 0; }
 
 static int fwd_tf(int T) {
     const int env = env_int("VL3D_FWD_TF", 0);
-    if (env == 1 || env == 2 || env == 3 || env == 4 || env == 6 || env == 8) return env;
+    if (env >= 1 && env <= 4) return env;
     return T >= 3 ? 3 : T;
 }
 
@@ -791,11 +792,28 @@ extern "C" int vl3d_composite_fwd(const vl3d_view* view, const vl3d_quad* quads,
     } else {
         // MINB = resident CTAs per SM the register budget is capped for (VL3D_FWD_MINB: tuning aid)
         const int minb = env_int("VL3D_FWD_MINB", 0);
-        if (tf == 8) launch_render<8, 1>(p, T, grid, block, st);
-        else if (tf == 6) launch_render<6, 2>(p, T, grid, block, st);
+        // dense layout: TMA-staged render (composite_tma.cuh); VL3D_TMA=0 selects the per-thread loads (tuning aid)
+        bool done = false;
+        if ((view->flags & VL3D_VIEW_RECT_PLANES) && ts == nullptr && atlas_dyn != nullptr && env_int("VL3D_TMA", 1) != 0) {
+            const int ttf = env_int("VL3D_TMA_TF", 3), tst = env_int("VL3D_TMA_STAGES", 3);   // tuning aids
+            int main_frames = 0;
+            if (ttf == 2) { if (tst == 4 ? launch_render_tma<2, 4>(p, atlas_dyn, T, st) : launch_render_tma<2, 3>(p, atlas_dyn, T, st)) main_frames = T / 2 * 2; }
+            else if (ttf == 4) { if (tst == 2 ? launch_render_tma<4, 2>(p, atlas_dyn, T, st) : launch_render_tma<4, 3>(p, atlas_dyn, T, st)) main_frames = T / 4 * 4; }
+            else if (tst == 2 ? launch_render_tma<3, 2>(p, atlas_dyn, T, st)
+                     : tst == 4 ? launch_render_tma<3, 4>(p, atlas_dyn, T, st) : launch_render_tma<3, 3>(p, atlas_dyn, T, st)) main_frames = T / 3 * 3;
+            if (main_frames > 0) {
+                done = true;
+                if (main_frames < T) {                              // tail frames: per-thread loads, one frame per CTA
+                    CompositeParams q = p;
+                    q.tb = main_frames;
+                    composite_render_kernel<1, 4><<<dim3(grid.x, grid.y, T - main_frames), block, 0, st>>>(q);
+                }
+            }
+        }
+        if (done) {}
         else if (tf == 4) { if (minb == 4) launch_render<4, 4>(p, T, grid, block, st); else launch_render<4, 3>(p, T, grid, block, st); }
-        else if (tf == 3) { if (minb == 3) launch_render<3, 3>(p, T, grid, block, st); else if (minb == 5) launch_render<3, 5>(p, T, grid, block, st); else launch_render<3, 4>(p, T, grid, block, st); }
-        else if (tf == 2) { if (minb == 5) launch_render<2, 5>(p, T, grid, block, st); else if (minb == 6) launch_render<2, 6>(p, T, grid, block, st); else launch_render<2, 4>(p, T, grid, block, st); }
+        else if (tf == 3) launch_render<3, 4>(p, T, grid, block, st);
+        else if (tf == 2) launch_render<2, 4>(p, T, grid, block, st);
         else launch_render<1, 4>(p, T, grid, block, st);
     }
     return check_launch("composite_fwd");

@@ -51,6 +51,7 @@ class MeshPack:
     qw: int
     n_static: int
     n_dynamic: int
+    rect_planes: bool = False    # dense layout: one atlas rectangle per plane (enables the TMA render)
 
 
 def make_mesh_pack(model_tensors, D, hv, wv, device):
@@ -60,7 +61,8 @@ def make_mesh_pack(model_tensors, D, hv, wv, device):
                                    t["faces_dyn"], t["uvs_dyn"], t["uvfaces_dyn"], t["atlas_dyn_hw"])
     q = torch.from_numpy(table.view(np.uint8).copy()).to(device)
     return MeshPack(quads=q, grids=grids, D=D, qh=hv - 1, qw=wv - 1,
-                    n_static=int((table["kind"] == 1).sum()), n_dynamic=int((table["kind"] == 2).sum()))
+                    n_static=int((table["kind"] == 1).sum()), n_dynamic=int((table["kind"] == 2).sum()),
+                    rect_planes=tiles.planes_are_rectangles(table, D, hv - 1, wv - 1))
 
 
 def make_view(pack: MeshPack, H, W, tar_extrin, tar_intrin, ref_extrin, dyn_hw, sta_hw):
@@ -73,6 +75,7 @@ def make_view(pack: MeshPack, H, W, tar_extrin, tar_intrin, ref_extrin, dyn_hw, 
     v.dyn_h, v.dyn_w = int(dyn_hw[0]), int(dyn_hw[1])
     v.sta_h, v.sta_w = int(sta_hw[0]), int(sta_hw[1])
     v.cx, v.cy = cx, cy
+    v.flags = _lib.VIEW_RECT_PLANES if pack.rect_planes else 0
     flat = homs.reshape(-1)
     C.memmove(v.hom, flat.ctypes.data, flat.nbytes)
     return v
