@@ -61,7 +61,8 @@ def main():
     variants = [
         ("v1", dict(VL3D_COMPOSITE_V1="1")),
         ("lean", dict()),
-        ("lean notma", dict(VL3D_TMA="0")),
+        ("lean notma", dict(VL3D_TMA="0", VL3D_TMA_BWD="0")),
+        ("bwd notma", dict(VL3D_TMA_BWD="0")),
         ("tma s2", dict(VL3D_TMA_STAGES="2")),
         ("tma s4", dict(VL3D_TMA_STAGES="4")),
         ("tma tf2 s4", dict(VL3D_TMA_TF="2", VL3D_TMA_STAGES="4")),
@@ -77,7 +78,7 @@ def main():
     if a.only:
         keep = set(a.only.split(","))
         variants = [v for v in variants if v[0] in keep]
-    knobs = ("VL3D_COMPOSITE_V1", "VL3D_FWD_TF", "VL3D_FWD_MINB", "VL3D_BWD_TF", "VL3D_BWD_NORED", "VL3D_TMA", "VL3D_TMA_TF", "VL3D_TMA_STAGES")
+    knobs = ("VL3D_COMPOSITE_V1", "VL3D_FWD_TF", "VL3D_FWD_MINB", "VL3D_BWD_TF", "VL3D_BWD_NORED", "VL3D_TMA", "VL3D_TMA_TF", "VL3D_TMA_STAGES", "VL3D_TMA_BWD")
     ref = None
     print(f"{a.workload}: {H}x{W}, D={wl['D']}, T={T}; algorithmic GB fwd {fwd_b / 1e9:.2f} bwd {bwd_b / 1e9:.2f}")
     for name, env in variants:

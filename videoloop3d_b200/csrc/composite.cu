@@ -684,6 +684,7 @@ __global__ void __launch_bounds__(BX* BY) composite_bwd_v1_kernel(const __grid_c
 
 }  // namespace vl3d
 
+#include "tma_common.cuh"
 #include "composite_lean.cuh"
 #include "composite_tma.cuh"
 
@@ -728,15 +729,34 @@ static void launch_render(CompositeParams p, int T, dim3 grid2, dim3 block, cuda
 }
 
 template <int TF, bool SMOOTH>
-static void launch_bwd(CompositeParams p, int T, dim3 grid2, dim3 block, cudaStream_t st) {
+static void launch_bwd(const CompositeParams& p0, int T, dim3 grid2, dim3 block, cudaStream_t st, const float* atlas_dyn,
+                       bool rect_planes) {
+    TmaRenderParams P;
+    P.p = p0;
     const int nz = T / TF;
     if (nz > 0) {
-        p.tb = 0;
-        composite_bwd_kernel<TF, SMOOTH><<<dim3(grid2.x, grid2.y, nz), block, 0, st>>>(p);
+        P.p.tb = 0;
+        bool split = false;
+        if constexpr (SMOOTH && TF == 2) {
+            // dense layout: tiles whose pixels all hit the same planes take the TMA-staged variant, the rest
+            // (image border) the per-thread loads; VL3D_TMA_BWD=0: tuning aid
+            if (rect_planes && P.p.ts == nullptr && env_int("VL3D_TMA_BWD", 1) != 0 && make_atlas_tmap(&P.tmap, P.p.view, atlas_dyn, T)) {
+                const size_t smem = (size_t)3 * TF * TMA_BOX_BYTES;
+                if (cudaFuncSetAttribute(composite_bwd_kernel<TF, SMOOTH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) ==
+                    cudaSuccess) {
+                    composite_bwd_kernel<TF, SMOOTH, 2><<<dim3(grid2.x, grid2.y, nz), block, smem, st>>>(P);
+                    composite_bwd_kernel<TF, SMOOTH, 1><<<dim3(grid2.x, grid2.y, nz), block, 0, st>>>(P);
+                    split = true;
+                } else {
+                    (void)cudaGetLastError();
+                }
+            }
+        }
+        if (!split) composite_bwd_kernel<TF, SMOOTH, 0><<<dim3(grid2.x, grid2.y, nz), block, 0, st>>>(P);
     }
     if (TF > 1 && T % TF) {
-        p.tb = nz * TF;
-        composite_bwd_kernel<1, SMOOTH><<<dim3(grid2.x, grid2.y, T % TF), block, 0, st>>>(p);
+        P.p.tb = nz * TF;
+        composite_bwd_kernel<1, SMOOTH, 0><<<dim3(grid2.x, grid2.y, T % TF), block, 0, st>>>(P);
     }
 }
 
@@ -856,15 +876,15 @@ extern "C" int vl3d_composite_bwd(const vl3d_view* view, const vl3d_quad* quads,
             else composite_bwd_v1_kernel<2, false><<<grid, block, 0, st>>>(p);
         }
     } else if (smooth) {
-        if (tf == 1) launch_bwd<1, true>(p, T, grid, block, st);
-        else if (tf == 2) launch_bwd<2, true>(p, T, grid, block, st);
-        else if (tf == 3) launch_bwd<3, true>(p, T, grid, block, st);
-        else launch_bwd<4, true>(p, T, grid, block, st);
+        if (tf == 1) launch_bwd<1, true>(p, T, grid, block, st, atlas_dyn, (view->flags & VL3D_VIEW_RECT_PLANES) != 0);
+        else if (tf == 2) launch_bwd<2, true>(p, T, grid, block, st, atlas_dyn, (view->flags & VL3D_VIEW_RECT_PLANES) != 0);
+        else if (tf == 3) launch_bwd<3, true>(p, T, grid, block, st, atlas_dyn, (view->flags & VL3D_VIEW_RECT_PLANES) != 0);
+        else launch_bwd<4, true>(p, T, grid, block, st, atlas_dyn, (view->flags & VL3D_VIEW_RECT_PLANES) != 0);
     } else {
-        if (tf == 1) launch_bwd<1, false>(p, T, grid, block, st);
-        else if (tf == 2) launch_bwd<2, false>(p, T, grid, block, st);
-        else if (tf == 3) launch_bwd<3, false>(p, T, grid, block, st);
-        else launch_bwd<4, false>(p, T, grid, block, st);
+        if (tf == 1) launch_bwd<1, false>(p, T, grid, block, st, atlas_dyn, (view->flags & VL3D_VIEW_RECT_PLANES) != 0);
+        else if (tf == 2) launch_bwd<2, false>(p, T, grid, block, st, atlas_dyn, (view->flags & VL3D_VIEW_RECT_PLANES) != 0);
+        else if (tf == 3) launch_bwd<3, false>(p, T, grid, block, st, atlas_dyn, (view->flags & VL3D_VIEW_RECT_PLANES) != 0);
+        else launch_bwd<4, false>(p, T, grid, block, st, atlas_dyn, (view->flags & VL3D_VIEW_RECT_PLANES) != 0);
     }
     return check_launch("composite_bwd");
 }

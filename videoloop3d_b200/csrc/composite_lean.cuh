@@ -102,6 +102,45 @@ __device__ __forceinline__ float4 sample_lean(const float4* base, const Geo& t) 
     return r;
 }
 
+// composite_lean's geo_from_quad plus the clamped integer tap coordinates (same arithmetic, same results)
+struct GeoXY {
+    Geo g;
+    int cx0, cx1, cy0, cy1;
+};
+
+__device__ __forceinline__ GeoXY geoxy_from_quad(const CompositeParams& p, const float4* qp, const int4 qb, int qx, int qy,
+                                                 float gx, float gy) {
+    GeoXY r;
+    const float4 qa = __ldg(qp);
+    const float a = gx - (float)qx, b = gy - (float)qy;
+    const float lx = fmaf(a, qa.z, qa.x), ly = fmaf(b, qa.w, qa.y);
+    const float flx = floorf(lx), fly = floorf(ly);
+    const float fx = lx - flx, fy = ly - fly;
+    const int ix = qb.x + (int)flx, iy = qb.y + (int)fly;
+    r.g.kind = qb.z;
+    const int aw = (r.g.kind == 2) ? p.view.dyn_w : p.view.sta_w;
+    const int ah = (r.g.kind == 2) ? p.view.dyn_h : p.view.sta_h;
+    r.cx0 = min(ix, aw - 1); r.cx1 = min(ix + 1, aw - 1);
+    r.cy0 = min(iy, ah - 1); r.cy1 = min(iy + 1, ah - 1);
+    const float gx1 = (ix + 1 < aw) ? fx : 0.f, gx0 = (ix < aw) ? 1.f - fx : 0.f;
+    const float gy1 = (iy + 1 < ah) ? fy : 0.f, gy0 = (iy < ah) ? 1.f - fy : 0.f;
+    const int r0 = r.cy0 * aw, r1 = r.cy1 * aw;
+    r.g.o00 = (unsigned)(r0 + r.cx0); r.g.o10 = (unsigned)(r0 + r.cx1);
+    r.g.o01 = (unsigned)(r1 + r.cx0); r.g.o11 = (unsigned)(r1 + r.cx1);
+    r.g.w00 = gx0 * gy0; r.g.w10 = gx1 * gy0; r.g.w01 = gx0 * gy1; r.g.w11 = gx1 * gy1;
+    return r;
+}
+
+__device__ __forceinline__ float4 filter_taps(const float4 a, const float4 b, const float4 c, const float4 d, const Geo& t) {
+    float4 r;
+    r.x = a.x * t.w00 + b.x * t.w10 + c.x * t.w01 + d.x * t.w11;
+    r.y = a.y * t.w00 + b.y * t.w10 + c.y * t.w01 + d.y * t.w11;
+    r.z = a.z * t.w00 + b.z * t.w10 + c.z * t.w01 + d.z * t.w11;
+    r.w = a.w * t.w00 + b.w * t.w10 + c.w * t.w01 + d.w * t.w11;
+    r.x = sigmoid_lean(r.x); r.y = sigmoid_lean(r.y); r.z = sigmoid_lean(r.z); r.w = sigmoid_lean(r.w);
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------
 // pure render: planes in lockstep (CTA-uniform plane index => homography in uniform registers).
 // Frames [tb, tb + TF*gridDim.z) of the call; the host guarantees they exist.
@@ -175,6 +214,42 @@ __global__ void __launch_bounds__(BX* BY, MINB) composite_render_kernel(const __
 // bookkeeping: horizontal pairs of the halo row and vertical pairs of the halo column belong to the
 // neighbouring CTA (weights wH / wV zeroed), and the regulariser sums are kept by owned pixels only.
 // ------------------------------------------------------------------------------------------------
+// How the pixel rectangle [x0,x1] x [y0,y1] (inclusive) of a screen tile meets plane d: 0 = no pixel hits the
+// plane, 1 = every pixel hits it, 2 = mixed / undecided.  The plane-grid coordinates are a projective image of
+// the pixel rectangle, i.e. a convex quadrilateral: all four corners inside the plane rectangle => every pixel
+// inside; bounding box outside on one side => nobody inside.  (Only meaningful when every quad of the plane
+// exists: VL3D_VIEW_RECT_PLANES.)  `box` receives the top-left texel of the tile's atlas footprint.
+__device__ __forceinline__ int tile_plane_class(const CompositeParams& p, int d, int x0, int x1, int y0, int y1, int4& box) {
+    const float qwf = (float)p.view.qw, qhf = (float)p.view.qh;
+    const float cu[2] = {(float)x0 + 0.5f - p.view.cx, (float)x1 + 0.5f - p.view.cx};
+    const float cv[2] = {(float)y0 + 0.5f - p.view.cy, (float)y1 + 0.5f - p.view.cy};
+    const float* h = &p.view.hom[d * 9];
+    float lxmin = 3e38f, lymin = 3e38f, gxmin = 3e38f, gxmax = -3e38f, gymin = 3e38f, gymax = -3e38f;
+    int nfront = 0, ninside = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float gx, gy;
+        const float u = cu[c & 1], v = cv[c >> 1];
+        // (a margin of 1e-3 quad keeps the verdict independent of the last-bit rounding of interior pixels)
+        const bool hit = plane_grid_lean(h, u, v, qwf, qhf, gx, gy);
+        ninside += (hit && gx > 1e-3f && gx < qwf - 1e-3f && gy > 1e-3f && gy < qhf - 1e-3f) ? 1 : 0;
+        nfront += (fmaf(h[6], u, fmaf(h[7], v, h[8])) > 0.f) ? 1 : 0;
+        gxmin = fminf(gxmin, gx); gxmax = fmaxf(gxmax, gx); gymin = fminf(gymin, gy); gymax = fmaxf(gymax, gy);
+        const float gxc = fminf(fmaxf(gx, 0.f), qwf), gyc = fminf(fmaxf(gy, 0.f), qhf);
+        const int qx = min((int)gxc, p.view.qw - 1), qy = min((int)gyc, p.view.qh - 1);
+        const float4* qp = reinterpret_cast<const float4*>(&p.quads[(d * p.view.qh + qy) * p.view.qw + qx]);
+        const float4 qa = __ldg(qp);
+        const int4 qb = __ldg(reinterpret_cast<const int4*>(qp + 1));
+        lxmin = fminf(lxmin, (float)qb.x + fmaf(gxc - (float)qx, qa.z, qa.x));
+        lymin = fminf(lymin, (float)qb.y + fmaf(gyc - (float)qy, qa.w, qa.y));
+    }
+    box = make_int4((int)floorf(lxmin), (int)floorf(lymin), 0, 0);
+    if (ninside == 4) return 1;
+    if (nfront == 0) return 0;
+    if (nfront == 4 && (gxmax <= -1e-3f || gxmin >= qwf + 1e-3f || gymax <= -1e-3f || gymin >= qhf + 1e-3f)) return 0;
+    return 2;
+}
+
 __device__ __forceinline__ float sgn2(float c, float a, float b) {   // sign(c-a) + sign(c-b)
     return ((c > a ? 1.f : 0.f) - (c < a ? 1.f : 0.f)) + ((c > b ? 1.f : 0.f) - (c < b ? 1.f : 0.f));
 }
@@ -202,9 +277,17 @@ __device__ __forceinline__ float4 shfl_up4(const float4& v) {
     return r;
 }
 
-template <int TF, bool SMOOTH>
-__global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(const __grid_constant__ CompositeParams p) {
+// MODE 0: every tile.  With VL3D_VIEW_RECT_PLANES the launch is split in two: MODE 2 takes the tiles whose pixels all
+// hit the same planes (slot k == k-th plane for every pixel, so the planes can be walked in lockstep) and stages
+// each plane's atlas footprint with TMA exactly like composite_render_tma_kernel — thread 0 issues the box of
+// plane k+2 right after the exchange barrier of slot k, which is also what frees that stage; MODE 1 takes the
+// remaining (image-border) tiles with the per-thread loads.  Both evaluate the same tile_plane_class().
+template <int TF, bool SMOOTH, int MODE>
+__global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(const __grid_constant__ TmaRenderParams P) {
+    const CompositeParams& p = P.p;
+    static_assert(MODE == 0 || SMOOTH, "the split launch is only built for the regulariser tiling");
     constexpr int SX = SMOOTH ? BX - 1 : BX, SY = SMOOTH ? BY - 1 : BY;
+    constexpr int NST = 3;                                          // TMA stages (MODE 2)
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int px0 = blockIdx.x * SX + tx, py0 = blockIdx.y * SY + ty;
     const int H = p.view.H, W = p.view.W;
@@ -215,6 +298,35 @@ __global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(
     const float u = (float)px + 0.5f - p.view.cx, v = (float)py + 0.5f - p.view.cy;
 
     __shared__ float4 s_ex[SMOOTH ? 2 : 1][SMOOTH ? TF : 1][SMOOTH ? BY : 1][SMOOTH ? BX : 1];
+    __shared__ int s_cls[2];                                        // (planes hit by every pixel, any mixed plane)
+    __shared__ int4 s_box[MODE == 2 ? VL3D_MAX_PLANES : 1];
+    __shared__ __align__(8) uint64_t s_full[MODE == 2 ? NST : 1];
+    extern __shared__ __align__(128) unsigned char bwd_dyn_smem[];  // MODE 2: [NST][TF][TMA_BH][TMA_BW] texels
+    unsigned in_mask = 0u;
+    if (MODE != 0) {
+        if (ty == 0) {
+            int cls = 0;
+            int4 box = make_int4(0, 0, 0, 0);
+            if (tx < p.view.D)
+                cls = tile_plane_class(p, tx, blockIdx.x * SX, min(blockIdx.x * SX + BX - 1, W - 1), blockIdx.y * SY,
+                                       min(blockIdx.y * SY + BY - 1, H - 1), box);
+            const unsigned m_in = __ballot_sync(0xffffffffu, cls == 1), m_mixed = __ballot_sync(0xffffffffu, cls == 2);
+            if (MODE == 2 && tx < p.view.D) s_box[tx] = box;
+            if (tx == 0) {
+                s_cls[0] = (int)m_in; s_cls[1] = (int)m_mixed;
+                if (MODE == 2) {
+#pragma unroll
+                    for (int s = 0; s < NST; ++s) mbar_init(&s_full[s], 1);
+                    mbar_fence_init();
+                }
+            }
+        }
+        __syncthreads();
+        const bool uniform = s_cls[1] == 0;
+        if (MODE == 1 && uniform) return;                           // taken by the TMA launch
+        if (MODE == 2 && !uniform) return;                          // taken by the per-thread-load launch
+        in_mask = (unsigned)s_cls[0];
+    }
 
     const size_t dyn_frame = (size_t)p.view.dyn_h * p.view.dyn_w;
     const float4* ab[TF];
@@ -258,37 +370,91 @@ __global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(
     const int D = p.view.D;
     const float qwf = (float)p.view.qw, qhf = (float)p.view.qh;
     int d = 0;                                                    // next plane to test
+    // MODE 2: planes of this tile in order, TMA issue state of thread 0
+    const int nplanes = __popc(in_mask);
+    unsigned rem_planes = in_mask, rem_issue = in_mask;
+    int k_issue = 0;
+    float4* tiles = reinterpret_cast<float4*>(bwd_dyn_smem);
+    auto issue_plane = [&]() {                                      // thread 0 only
+        const int di = __ffs(rem_issue) - 1;
+        rem_issue &= rem_issue - 1u;
+        const int s = k_issue % NST;
+        const int4 bi = s_box[di];
+        mbar_arrive_expect_tx(&s_full[s], TF * TMA_BOX_BYTES);
+#pragma unroll
+        for (int f = 0; f < TF; ++f)
+            tma_load_3d(tiles + (size_t)(s * TF + f) * (TMA_BOX_BYTES / 16), &P.tmap, &s_full[s], bi.x * 4, bi.y, t0 + f);
+        ++k_issue;
+    };
+    if (MODE == 2 && tx == 0 && ty == 0) {
+        if (nplanes > 0) issue_plane();
+        if (nplanes > 1) issue_plane();
+    }
     for (int k = 0;; ++k) {
-        // slot k of this pixel = its k-th hit plane along the ray (utils.py:64-69): advance to the next plane
-        // whose quad under the ray exists.  Nothing is known in advance; the loop ends when no thread of the
-        // tile (warp, without the regulariser) has a slot left.
         Geo tp;
         tp.kind = 0; tp.o00 = tp.o10 = tp.o01 = tp.o11 = 0u;
         tp.w00 = tp.w10 = tp.w01 = tp.w11 = 0.f;
-        while (d < D) {
-            float gx, gy;
-            const bool hit = plane_grid_lean(&p.view.hom[d * 9], u, v, qwf, qhf, gx, gy);
-            const int dd = d++;
-            if (!hit) continue;
-            int qx, qy;
-            const float4* qp = quad_at(p, dd, gx, gy, qx, qy);
-            const int4 qb = __ldg(reinterpret_cast<const int4*>(qp + 1));
-            if (qb.z == 0) continue;
-            tp = geo_from_quad(p, qp, qb, qx, qy, gx, gy);
-            break;
-        }
-        const bool has = tp.kind != 0;
         float4 val[TF];
 #pragma unroll
         for (int f = 0; f < TF; ++f) val[f] = make_float4(0.f, 0.f, 0.f, 0.f);   // zero canvas (MPV.py:441)
-        if (tp.kind == 2) {
+        if (MODE == 2) {
+            // every pixel of the tile (replicas included) hits exactly the planes of in_mask: slot k = k-th plane
+            if (k >= nplanes) break;
+            const int dd = __ffs(rem_planes) - 1;
+            rem_planes &= rem_planes - 1u;
+            const int s = k % NST;
+            float gx, gy;
+            plane_grid_lean(&p.view.hom[dd * 9], u, v, qwf, qhf, gx, gy);
+            int qx, qy;
+            const float4* qp = quad_at(p, dd, gx, gy, qx, qy);
+            const int4 qb = __ldg(reinterpret_cast<const int4*>(qp + 1));
+            const GeoXY t = geoxy_from_quad(p, qp, qb, qx, qy, gx, gy);
+            tp = t.g;
+            const int4 bi = s_box[dd];
+            const int lx0 = t.cx0 - bi.x, lx1 = t.cx1 - bi.x, ly0 = t.cy0 - bi.y, ly1 = t.cy1 - bi.y;
+            mbar_wait(&s_full[s], (unsigned)(k / NST) & 1u);        // the plane's boxes have landed
+            if (tp.kind == 2 && lx0 >= 0 && lx1 < TMA_BW && ly0 >= 0 && ly1 < TMA_BH) {
+                const float4* tb = tiles + (size_t)(s * TF) * (TMA_BOX_BYTES / 16);
+                const int a00 = ly0 * TMA_BW + lx0, a10 = ly0 * TMA_BW + lx1, a01 = ly1 * TMA_BW + lx0, a11 = ly1 * TMA_BW + lx1;
 #pragma unroll
-            for (int f = 0; f < TF; ++f) val[f] = sample_lean(ab[f], tp);
-        } else if (tp.kind == 1) {
-            const float4 s = sample_lean(sb, tp);
+                for (int f = 0; f < TF; ++f) {
+                    const float4* tf = tb + f * (TMA_BOX_BYTES / 16);
+                    val[f] = filter_taps(tf[a00], tf[a10], tf[a01], tf[a11], tp);
+                }
+            } else if (tp.kind == 2) {
 #pragma unroll
-            for (int f = 0; f < TF; ++f) val[f] = s;
+                for (int f = 0; f < TF; ++f) val[f] = sample_lean(ab[f], tp);
+            } else if (tp.kind == 1) {
+                const float4 sv = sample_lean(sb, tp);
+#pragma unroll
+                for (int f = 0; f < TF; ++f) val[f] = sv;
+            }
+        } else {
+            // slot k of this pixel = its k-th hit plane along the ray (utils.py:64-69): advance to the next plane
+            // whose quad under the ray exists.  Nothing is known in advance; the loop ends when no thread of the
+            // tile (warp, without the regulariser) has a slot left.
+            while (d < D) {
+                float gx, gy;
+                const bool hit = plane_grid_lean(&p.view.hom[d * 9], u, v, qwf, qhf, gx, gy);
+                const int dd = d++;
+                if (!hit) continue;
+                int qx, qy;
+                const float4* qp = quad_at(p, dd, gx, gy, qx, qy);
+                const int4 qb = __ldg(reinterpret_cast<const int4*>(qp + 1));
+                if (qb.z == 0) continue;
+                tp = geo_from_quad(p, qp, qb, qx, qy, gx, gy);
+                break;
+            }
+            if (tp.kind == 2) {
+#pragma unroll
+                for (int f = 0; f < TF; ++f) val[f] = sample_lean(ab[f], tp);
+            } else if (tp.kind == 1) {
+                const float4 sv = sample_lean(sb, tp);
+#pragma unroll
+                for (int f = 0; f < TF; ++f) val[f] = sv;
+            }
         }
+        const bool has = tp.kind != 0;
         if (!SMOOTH) {
             if (!__any_sync(0xffffffffu, has)) break;
         }
@@ -299,7 +465,10 @@ __global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(
             float4* ex = &s_ex[k & 1][0][0][0];
 #pragma unroll
             for (int f = 0; f < TF; ++f) ex[f * (BX * BY) + o_c] = val[f];
-            if (!__syncthreads_or(has)) break;                    // (block-uniform)
+            if (MODE == 2) {
+                __syncthreads();                                    // also: everybody is done with the stage of slot k-1
+                if (tx == 0 && ty == 0 && k + 2 < nplanes) issue_plane();
+            } else if (!__syncthreads_or(has)) break;              // (block-uniform)
 #pragma unroll
             for (int f = 0; f < TF; ++f) {
                 const float4 c = val[f];

@@ -13,88 +13,7 @@
 // the output is bit-identical to composite_render_kernel.
 #pragma once
 
-#include <cuda.h>
-
 namespace vl3d {
-
-constexpr int TMA_BW = 40, TMA_BH = 12;
-constexpr int TMA_BOX_BYTES = TMA_BW * TMA_BH * 16;
-constexpr int TMA_THREADS = BX * BY + 32;                          // 8 consumer warps + 1 producer warp
-
-struct alignas(64) TmaRenderParams {
-    CUtensorMap tmap;                                               // (x4 = dyn_w*4 floats, y = dyn_h, t = frames)
-    CompositeParams p;
-};
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-
-// composite_lean's geo_from_quad plus the clamped integer tap coordinates (same arithmetic, same results)
-struct GeoXY {
-    Geo g;
-    int cx0, cx1, cy0, cy1;
-};
-
-__device__ __forceinline__ GeoXY geoxy_from_quad(const CompositeParams& p, const float4* qp, const int4 qb, int qx, int qy,
-                                                 float gx, float gy) {
-    GeoXY r;
-    const float4 qa = __ldg(qp);
-    const float a = gx - (float)qx, b = gy - (float)qy;
-    const float lx = fmaf(a, qa.z, qa.x), ly = fmaf(b, qa.w, qa.y);
-    const float flx = floorf(lx), fly = floorf(ly);
-    const float fx = lx - flx, fy = ly - fly;
-    const int ix = qb.x + (int)flx, iy = qb.y + (int)fly;
-    r.g.kind = qb.z;
-    const int aw = (r.g.kind == 2) ? p.view.dyn_w : p.view.sta_w;
-    const int ah = (r.g.kind == 2) ? p.view.dyn_h : p.view.sta_h;
-    r.cx0 = min(ix, aw - 1); r.cx1 = min(ix + 1, aw - 1);
-    r.cy0 = min(iy, ah - 1); r.cy1 = min(iy + 1, ah - 1);
-    const float gx1 = (ix + 1 < aw) ? fx : 0.f, gx0 = (ix < aw) ? 1.f - fx : 0.f;
-    const float gy1 = (iy + 1 < ah) ? fy : 0.f, gy0 = (iy < ah) ? 1.f - fy : 0.f;
-    const int r0 = r.cy0 * aw, r1 = r.cy1 * aw;
-    r.g.o00 = (unsigned)(r0 + r.cx0); r.g.o10 = (unsigned)(r0 + r.cx1);
-    r.g.o01 = (unsigned)(r1 + r.cx0); r.g.o11 = (unsigned)(r1 + r.cx1);
-    r.g.w00 = gx0 * gy0; r.g.w10 = gx1 * gy0; r.g.w01 = gx0 * gy1; r.g.w11 = gx1 * gy1;
-    return r;
-}
-
-__device__ __forceinline__ float4 filter_taps(const float4 a, const float4 b, const float4 c, const float4 d, const Geo& t) {
-    float4 r;
-    r.x = a.x * t.w00 + b.x * t.w10 + c.x * t.w01 + d.x * t.w11;
-    r.y = a.y * t.w00 + b.y * t.w10 + c.y * t.w01 + d.y * t.w11;
-    r.z = a.z * t.w00 + b.z * t.w10 + c.z * t.w01 + d.z * t.w11;
-    r.w = a.w * t.w00 + b.w * t.w10 + c.w * t.w01 + d.w * t.w11;
-    r.x = sigmoid_lean(r.x); r.y = sigmoid_lean(r.y); r.z = sigmoid_lean(r.z); r.w = sigmoid_lean(r.w);
-    return r;
-}
 
 template <int TF, int TMA_STAGES>
 __global__ void __launch_bounds__(TMA_THREADS, (TMA_STAGES * TF * TMA_BOX_BYTES <= 70 * 1024) ? 3 : 2) composite_render_tma_kernel(const __grid_constant__ TmaRenderParams P) {
@@ -242,43 +161,13 @@ __global__ void __launch_bounds__(TMA_THREADS, (TMA_STAGES * TF * TMA_BOX_BYTES 
     }
 }
 
-typedef CUresult (*vl3d_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
-static vl3d_encode_tiled_fn tma_encoder() {
-    static vl3d_encode_tiled_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<vl3d_encode_tiled_fn>(ptr);
-        (void)cudaGetLastError();
-    }
-    return fn;
-}
-
 // Launches the TMA render for frames [0, TF * (T / TF)); returns false (nothing launched) if TMA is unavailable.
 template <int TF, int TMA_STAGES>
 static bool launch_render_tma(const CompositeParams& p, const float* atlas_dyn, int T, cudaStream_t st) {
     const int nz = T / TF;
     if (nz == 0) return false;
-    vl3d_encode_tiled_fn enc = tma_encoder();
-    if (enc == nullptr) return false;
     TmaRenderParams P;
-    const cuuint64_t gdim[3] = {(cuuint64_t)p.view.dyn_w * 4, (cuuint64_t)p.view.dyn_h, (cuuint64_t)T};
-    const cuuint64_t gstr[2] = {(cuuint64_t)p.view.dyn_w * 16, (cuuint64_t)p.view.dyn_w * p.view.dyn_h * 16};
-    const cuuint32_t box[3] = {TMA_BW * 4, TMA_BH, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    if (gstr[1] >= ((cuuint64_t)1 << 40)) return false;
-    const CUresult r = enc(&P.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(atlas_dyn), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return false;
+    if (!make_atlas_tmap(&P.tmap, p.view, atlas_dyn, T)) return false;
     P.p = p;
     P.p.tb = 0;
     const size_t smem = (size_t)TMA_STAGES * TF * TMA_BOX_BYTES + 2 * TMA_STAGES * sizeof(uint64_t) + VL3D_MAX_PLANES * sizeof(int4) + 64;
