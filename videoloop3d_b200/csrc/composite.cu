@@ -738,14 +738,13 @@ static void launch_bwd(const CompositeParams& p0, int T, dim3 grid2, dim3 block,
         P.p.tb = 0;
         bool split = false;
         if constexpr (SMOOTH && TF == 2) {
-            // dense layout: tiles whose pixels all hit the same planes take the TMA-staged variant, the rest
-            // (image border) the per-thread loads; VL3D_TMA_BWD=0: tuning aid
+            // dense layout: tiles whose pixels all hit the same planes stage their texels with TMA, the rest (image
+            // border) keep the per-thread loads — decided per tile inside one launch; VL3D_TMA_BWD=0: tuning aid
             if (rect_planes && P.p.ts == nullptr && env_int("VL3D_TMA_BWD", 1) != 0 && make_atlas_tmap(&P.tmap, P.p.view, atlas_dyn, T)) {
                 const size_t smem = (size_t)3 * TF * TMA_BOX_BYTES;
-                if (cudaFuncSetAttribute(composite_bwd_kernel<TF, SMOOTH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) ==
+                if (cudaFuncSetAttribute(composite_bwd_kernel<TF, SMOOTH, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) ==
                     cudaSuccess) {
-                    composite_bwd_kernel<TF, SMOOTH, 2><<<dim3(grid2.x, grid2.y, nz), block, smem, st>>>(P);
-                    composite_bwd_kernel<TF, SMOOTH, 1><<<dim3(grid2.x, grid2.y, nz), block, 0, st>>>(P);
+                    composite_bwd_kernel<TF, SMOOTH, 3><<<dim3(grid2.x, grid2.y, nz), block, smem, st>>>(P);
                     split = true;
                 } else {
                     (void)cudaGetLastError();

@@ -277,11 +277,11 @@ __device__ __forceinline__ float4 shfl_up4(const float4& v) {
     return r;
 }
 
-// MODE 0: every tile.  With VL3D_VIEW_RECT_PLANES the launch is split in two: MODE 2 takes the tiles whose pixels all
-// hit the same planes (slot k == k-th plane for every pixel, so the planes can be walked in lockstep) and stages
-// each plane's atlas footprint with TMA exactly like composite_render_tma_kernel — thread 0 issues the box of
-// plane k+2 right after the exchange barrier of slot k, which is also what frees that stage; MODE 1 takes the
-// remaining (image-border) tiles with the per-thread loads.  Both evaluate the same tile_plane_class().
+// MODE 0: per-thread loads for every tile.  MODE 3 (VL3D_VIEW_RECT_PLANES): each tile decides at run time — if
+// all its pixels hit the same planes (slot k == k-th plane for every pixel, so the planes can be walked in
+// lockstep) it stages each plane's atlas footprint with TMA exactly like composite_render_tma_kernel: thread 0
+// issues the box of plane k+2 right after the exchange barrier of slot k, which is also what frees that stage;
+// the remaining (image-border) tiles use the per-thread loads.
 template <int TF, bool SMOOTH, int MODE>
 __global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(const __grid_constant__ TmaRenderParams P) {
     const CompositeParams& p = P.p;
@@ -299,10 +299,11 @@ __global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(
 
     __shared__ float4 s_ex[SMOOTH ? 2 : 1][SMOOTH ? TF : 1][SMOOTH ? BY : 1][SMOOTH ? BX : 1];
     __shared__ int s_cls[2];                                        // (planes hit by every pixel, any mixed plane)
-    __shared__ int4 s_box[MODE == 2 ? VL3D_MAX_PLANES : 1];
-    __shared__ __align__(8) uint64_t s_full[MODE == 2 ? NST : 1];
+    __shared__ int4 s_box[MODE >= 2 ? VL3D_MAX_PLANES : 1];
+    __shared__ __align__(8) uint64_t s_full[MODE >= 2 ? NST : 1];
     extern __shared__ __align__(128) unsigned char bwd_dyn_smem[];  // MODE 2: [NST][TF][TMA_BH][TMA_BW] texels
     unsigned in_mask = 0u;
+    bool use_tma = false;
     if (MODE != 0) {
         if (ty == 0) {
             int cls = 0;
@@ -311,10 +312,10 @@ __global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(
                 cls = tile_plane_class(p, tx, blockIdx.x * SX, min(blockIdx.x * SX + BX - 1, W - 1), blockIdx.y * SY,
                                        min(blockIdx.y * SY + BY - 1, H - 1), box);
             const unsigned m_in = __ballot_sync(0xffffffffu, cls == 1), m_mixed = __ballot_sync(0xffffffffu, cls == 2);
-            if (MODE == 2 && tx < p.view.D) s_box[tx] = box;
+            if (MODE >= 2 && tx < p.view.D) s_box[tx] = box;
             if (tx == 0) {
                 s_cls[0] = (int)m_in; s_cls[1] = (int)m_mixed;
-                if (MODE == 2) {
+                if (MODE >= 2) {
 #pragma unroll
                     for (int s = 0; s < NST; ++s) mbar_init(&s_full[s], 1);
                     mbar_fence_init();
@@ -323,9 +324,8 @@ __global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(
         }
         __syncthreads();
         const bool uniform = s_cls[1] == 0;
-        if (MODE == 1 && uniform) return;                           // taken by the TMA launch
-        if (MODE == 2 && !uniform) return;                          // taken by the per-thread-load launch
         in_mask = (unsigned)s_cls[0];
+        use_tma = MODE >= 2 && uniform;
     }
 
     const size_t dyn_frame = (size_t)p.view.dyn_h * p.view.dyn_w;
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(
             tma_load_3d(tiles + (size_t)(s * TF + f) * (TMA_BOX_BYTES / 16), &P.tmap, &s_full[s], bi.x * 4, bi.y, t0 + f);
         ++k_issue;
     };
-    if (MODE == 2 && tx == 0 && ty == 0) {
+    if (use_tma && tx == 0 && ty == 0) {
         if (nplanes > 0) issue_plane();
         if (nplanes > 1) issue_plane();
     }
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(
         float4 val[TF];
 #pragma unroll
         for (int f = 0; f < TF; ++f) val[f] = make_float4(0.f, 0.f, 0.f, 0.f);   // zero canvas (MPV.py:441)
-        if (MODE == 2) {
+        if (MODE >= 2 && use_tma) {
             // every pixel of the tile (replicas included) hits exactly the planes of in_mask: slot k = k-th plane
             if (k >= nplanes) break;
             const int dd = __ffs(rem_planes) - 1;
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(
             float4* ex = &s_ex[k & 1][0][0][0];
 #pragma unroll
             for (int f = 0; f < TF; ++f) ex[f * (BX * BY) + o_c] = val[f];
-            if (MODE == 2) {
+            if (MODE >= 2 && use_tma) {
                 __syncthreads();                                    // also: everybody is done with the stage of slot k-1
                 if (tx == 0 && ty == 0 && k + 2 < nplanes) issue_plane();
             } else if (!__syncthreads_or(has)) break;              // (block-uniform)
