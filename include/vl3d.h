@@ -123,6 +123,12 @@ int vl3d_composite_bwd(const vl3d_view* view, const vl3d_quad* quads, const floa
 int vl3d_scale_partials(void);
 int vl3d_scale_invariant(const float* rgb, int32_t T, const float* res, int32_t F, int32_t H, int32_t W,
                          double* partials, float* out, void* stream);
+/* Sharded form of the same gain: vl3d_frame_sum gives out[i] = sum_f v[f*chw + i] over a rank's block
+ * of target frames; after an all-reduce(SUM) of those (3,H,W) sums, vl3d_scale_invariant_presum evaluates
+ * MPV.py:499-504 with mean_F res = res_sum / F. */
+int vl3d_frame_sum(const float* v, int32_t n_frames, int64_t chw, float* out, void* stream);
+int vl3d_scale_invariant_presum(const float* rgb, int32_t T, const float* res_sum, int32_t F, int32_t H, int32_t W,
+                                double* partials, float* out, void* stream);
 /* out[i] = x[i] * xscale[0] for n contiguous floats (rgb_pad * scale, MPV.py:504). */
 int vl3d_scale_video(const float* x, const float* xscale, float* out, int64_t n, void* stream);
 

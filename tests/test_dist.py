@@ -48,9 +48,16 @@ def _worker(rank, world, port, q):
         dist.all_reduce(nn)
         sums = torch.tensor([1.0, 2.0, 3.0, 4.0, float(rank + 1)], dtype=torch.float64)
         dist.all_reduce(sums)
+        # scale-invariant gain: block-wise sums of the target frames, all-reduced
+        F_ = 5
+        fb = partition(F_, world)
+        target = torch.arange(F_ * 3 * h * w, dtype=torch.float32).reshape(F_, 3, h, w) / 7
+        rsum = target[fb[rank]:fb[rank + 1]].sum(0)
+        dist.all_reduce(rsum)
         ok = torch.equal(video[:T], truth) and torch.equal(video[T:], truth[:pad])
         ok &= all(int(nn[r, 0, 0]) == 7 + (0 if r < rows[1] else 1) for r in range(ho))
         ok &= sums.tolist() == [2.0, 4.0, 6.0, 8.0, 3.0]
+        ok &= torch.allclose(rsum, target.sum(0), rtol=1e-6)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

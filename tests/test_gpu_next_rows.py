@@ -61,3 +61,20 @@ def test_lod_and_state_dict_roundtrip():
     opt = m.get_optimizer(step=0)
     assert len(opt.param_groups) == 2 and opt.param_groups[0]["eps"] == 6e-8
     assert abs(m.get_lrate(1000)[0][1] - m.args.lrate * 0.1 ** (1000 / (m.args.lrate_decay * 1000))) < 1e-12
+
+
+def test_sharded_scale_invariant_matches_direct():
+    """block-wise frame sums + vl3d_scale_invariant_presum == vl3d_scale_invariant (MPV.py:499-504)."""
+    from videoloop3d_b200 import ops
+    g = torch.Generator(device="cuda:0").manual_seed(3)
+    T, F_, H, W = 5, 11, 19, 23
+    rgb = torch.rand((T + 2, 3, H, W), device="cuda:0", generator=g)
+    res = torch.rand((F_, 3, H, W), device="cuda:0", generator=g)
+    direct = float(ops.scale_invariant(rgb, T, res))
+    ref = float((torch.exp(torch.log((res.double().mean(0) + 0.01) / (rgb[:T].double().mean(0) + 0.01)).mean()) + 3) / 4)
+    assert abs(direct - ref) < 1e-5 * abs(ref)
+    for world in (2, 3):
+        b = [(F_ * r) // world for r in range(world + 1)]
+        total = sum(ops.frame_sum(res[b[r]:b[r + 1]].contiguous()) for r in range(world))
+        got = float(ops.scale_invariant_presum(rgb, T, total.contiguous(), F_))
+        assert abs(got - direct) < 2e-6 * abs(direct), (world, got, direct)

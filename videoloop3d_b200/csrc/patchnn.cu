@@ -632,6 +632,38 @@ __global__ void __launch_bounds__(SCALE_THREADS) scale_partial_kernel(const floa
     }
 }
 
+// sharded variant: every rank sums its block of target frames, the (3,H,W) partial sums are
+// all-reduced, and the gain is evaluated from the summed target
+__global__ void __launch_bounds__(SCALE_THREADS) frame_sum_kernel(const float* __restrict__ v, int n, size_t chw,
+                                                                   float* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * SCALE_THREADS + threadIdx.x; i < chw; i += (size_t)gridDim.x * SCALE_THREADS) {
+        float s = 0.f;
+        for (int f = 0; f < n; ++f) s += __ldg(v + (size_t)f * chw + i);
+        out[i] = s;
+    }
+}
+
+__global__ void __launch_bounds__(SCALE_THREADS) scale_partial_presum_kernel(const float* __restrict__ rgb, int T,
+                                                                              const float* __restrict__ res_sum, int F,
+                                                                              size_t chw, double* partials) {
+    float acc = 0.f;
+    for (size_t i = (size_t)blockIdx.x * SCALE_THREADS + threadIdx.x; i < chw; i += (size_t)gridDim.x * SCALE_THREADS) {
+        float sx = 0.f;
+        for (int t = 0; t < T; ++t) sx += __ldg(rgb + (size_t)t * chw + i);
+        acc += __logf((__ldg(res_sum + i) / (float)F + 0.01f) / (sx / (float)T + 0.01f));
+    }
+    __shared__ float s_part[SCALE_THREADS / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < SCALE_THREADS / 32; ++i) a += (double)s_part[i];
+        partials[blockIdx.x] = a;
+    }
+}
+
 __global__ void __launch_bounds__(1024) scale_finalize_kernel(const double* partials, int n, double denom, float* out) {
     __shared__ double s[32];
     double acc = 0.0;
@@ -892,6 +924,29 @@ extern "C" int vl3d_scale_video(const float* x, const float* xscale, float* out,
     if (blocks > 148 * 16) blocks = 148 * 16;
     scale_video_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, xscale, out, (size_t)n);
     return check_launch("scale_video");
+}
+
+extern "C" int vl3d_frame_sum(const float* v, int32_t n_frames, int64_t chw, float* out, void* stream) {
+    VL3D_REQUIRE(v && out, VL3D_ENULL, "frame_sum: NULL pointer");
+    VL3D_REQUIRE(n_frames >= 0 && chw >= 1, VL3D_EINVAL, "frame_sum: bad sizes");
+    int blocks = (int)(((size_t)chw + SCALE_THREADS - 1) / SCALE_THREADS);
+    if (blocks > SCALE_BLOCKS) blocks = SCALE_BLOCKS;
+    frame_sum_kernel<<<blocks, SCALE_THREADS, 0, (cudaStream_t)stream>>>(v, n_frames, (size_t)chw, out);
+    return check_launch("frame_sum");
+}
+
+extern "C" int vl3d_scale_invariant_presum(const float* rgb, int32_t T, const float* res_sum, int32_t F, int32_t H, int32_t W,
+                                           double* partials, float* out, void* stream) {
+    VL3D_REQUIRE(rgb && res_sum && partials && out, VL3D_ENULL, "required pointer is NULL");
+    VL3D_REQUIRE(T >= 1 && F >= 1 && H >= 1 && W >= 1, VL3D_EINVAL, "bad sizes");
+    const size_t chw = (size_t)3 * H * W;
+    int blocks = (int)((chw + SCALE_THREADS - 1) / SCALE_THREADS);
+    if (blocks > SCALE_BLOCKS) blocks = SCALE_BLOCKS;
+    cudaStream_t st = (cudaStream_t)stream;
+    scale_partial_presum_kernel<<<blocks, SCALE_THREADS, 0, st>>>(rgb, T, res_sum, F, chw, partials);
+    if (int e = check_launch("scale_partial_presum")) return e;
+    scale_finalize_kernel<<<1, 1024, 0, st>>>(partials, blocks, (double)chw, out);
+    return check_launch("scale_finalize");
 }
 
 extern "C" int vl3d_scale_invariant(const float* rgb, int32_t T, const float* res, int32_t F, int32_t H, int32_t W,

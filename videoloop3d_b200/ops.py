@@ -123,6 +123,31 @@ def scale_invariant(rgb, T, res, out=None, partials=None):
     return out
 
 
+def frame_sum(v, out=None):
+    """sum over the leading (frame) axis of a contiguous (n,3,H,W) block -> (3,H,W)."""
+    _require_cuda(v, "v")
+    assert v.is_contiguous()
+    if out is None:
+        out = torch.empty(v.shape[1:], dtype=torch.float32, device=v.device)
+    _lib.call("vl3d_frame_sum", _lib.ptr(v), int(v.shape[0]), int(v[0].numel()) if v.shape[0] else int(out.numel()),
+              _lib.ptr(out), _lib.stream_ptr())
+    return out
+
+
+def scale_invariant_presum(rgb, T, res_sum, F_, out=None, partials=None):
+    """MPV.py:499-504 from the frame-summed target `res_sum` (3,H,W) (the sharded step all-reduces it)."""
+    _require_cuda(rgb, "rgb"); _require_cuda(res_sum, "res_sum")
+    _, H, W = res_sum.shape
+    assert rgb.is_contiguous() and res_sum.is_contiguous() and tuple(rgb.shape[1:]) == (3, H, W)
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device=rgb.device)
+    if partials is None:
+        partials = torch.empty(_lib.load().vl3d_scale_partials(), dtype=torch.float64, device=rgb.device)
+    _lib.call("vl3d_scale_invariant_presum", _lib.ptr(rgb), int(T), _lib.ptr(res_sum), int(F_), int(H), int(W),
+              _lib.ptr(partials), _lib.ptr(out), _lib.stream_ptr())
+    return out
+
+
 def _fit(size, p, st, name):
     """fit_patch of utils_vid.py:307-313."""
     if size < p:

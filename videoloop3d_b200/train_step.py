@@ -253,9 +253,17 @@ class FusedLoopStep:
         xscale = None
         if args.scale_invariant:
             with self._timed("scale_invariant"):
-                xscale = ops.scale_invariant(rgb_pad, T, res0, out=self._get("xscale", (1,), torch.float32),
-                                             partials=self._get("scale_part", (ops._lib.load().vl3d_scale_partials(),),
-                                                                torch.float64))
+                out = self._get("xscale", (1,), torch.float32)
+                part = self._get("scale_part", (ops._lib.load().vl3d_scale_partials(),), torch.float64)
+                if self.world == 1:
+                    xscale = ops.scale_invariant(rgb_pad, T, res0, out=out, partials=part)
+                else:
+                    # the mean over the F target frames is the expensive part (the whole target video is read):
+                    # every rank sums its block of frames, one all-reduce of the (3,h,w) sums
+                    fb = partition(res0.shape[0], self.world)
+                    rsum = ops.frame_sum(res0[fb[self.rank]:fb[self.rank + 1]], out=self._get("res_sum", (3, h, w), torch.float32))
+                    dist.all_reduce(rsum, group=self.group)
+                    xscale = ops.scale_invariant_presum(rgb_pad, T, rsum, res0.shape[0], out=out, partials=part)
         desc = ops.make_loss_desc(rgb_pad.shape, (rgb_pad.stride(0), rgb_pad.stride(1), rgb_pad.stride(2)), res0.shape,
                                   (res0.stride(0), res0.stride(1), res0.stride(2)), cfg["patch_size"],
                                   cfg["patcht_size"], cfg["stride"], cfg["stridet"], cfg.get("alpha", 1e10),
