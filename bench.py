@@ -146,9 +146,9 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
-# `ncu --set full` capture of this same command (profiles/r01b_ncu_full_step720p.md); None if not captured.
-NCU_TRAFFIC_BYTES = {("step720p", 1, "composite_bwd"): 42.263852e9 + 20.460910e9,
-                     ("step720p", 1, "composite_fwd"): 20.688009e9 + 0.552415e9}
+# `ncu --set full` capture of this same command (profiles/r01c_ncu_full_step720p.md); None if not captured.
+NCU_TRAFFIC_BYTES = {("step720p", 1, "composite_bwd"): 42.817052e9 + 20.455665e9,
+                     ("step720p", 1, "composite_fwd"): 21.071395e9 + 0.553144e9}
 
 
 def algorithmic_bytes(wl, frames):
