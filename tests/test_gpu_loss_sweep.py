@@ -1,8 +1,8 @@
 """GPU: the looping-loss kernels across BASELINE config 5's axes (patch 7/11/15, T up to 96, up to 1024
 candidates, both alpha modes) plus the odd corners (temporal stride 2, pt = 1, patches that do not overlap,
 the un-fitted direct loss, non-contiguous inputs) — each against the CPU oracle on a small spatial extent.
-Every kernel variant is hit: strip kernel M = 0..3, 16-byte and 4-byte staging, the one-patch-per-CTA
-fallback (more than 64 query frames)."""
+Every kernel variant is hit: strip kernel M = 0..3, 16-byte and 4-byte staging, the 4x8-tile strip kernel with
+TMA and with LDGSTS staging, the one-patch-per-CTA fallback (more than 64 query frames)."""
 import pytest
 import torch
 
@@ -24,6 +24,11 @@ CASES = [
     ("pt1_s1",        4,  6,   9,  11, 3, 1, 1, 1, 0.0, "-2", "lm"),
     ("direct_unfit",  9,  14,  24, 30, 7, 2, 4, 2, 0.3, "0", "direct"),
     ("p8_M2_even",    6,  15,  28, 32, 8, 2, 4, 1, 1e4, "-2", "lm"),
+    # >= 40 query frames and a candidate set covered in <= 2 sweeps: the 4x8-tile strip kernel
+    ("p11_tile8_tma", 44, 100, 27, 36, 11, 3, 4, 1, 0.0, "-2", "lm"),      # 9 groups (odd): TMA staging, 2 row groups
+    ("p7_tile8",      42, 70,  23, 32, 7, 3, 4, 1, 1e4, "-2", "lm"),       # 6 groups: LDGSTS staging, 1 row group
+    ("p8_tile8_rem0", 41, 300, 28, 36, 8, 2, 4, 1, 0.0, "0", "lm"),        # no padding lane, two sweeps, p == 2 s
+    ("p4_tile8_tma",  43, 60,  16, 24, 4, 3, 4, 1, 1e4, "abs", "lm"),      # 3 groups: TMA staging, p == s
 ]
 
 

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include "vl3d_common.cuh"
+#include "tma_ptx.cuh"
 
 namespace vl3d {
 
@@ -780,8 +781,12 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
                     if (best_ntb == 0 || cost < best_cost) { best_ntb = ntb; best_cost = cost; }
                 }
                 const int rows = row_end - row_begin;
-                int SL = 16;
+                // strip length: long strips share more rows between patches (measured at 720p: 8 / 16 / 24 / 32 patches
+                // per strip = 21.3 / 20.2 / 19.8 / 22.0 ms), balanced so that the last strip is not a stub
+                int SL = 24;
+                { const char* e = getenv("VL3D_NN_SL"); if (e && atoi(e) >= 2) SL = atoi(e); }   // tuning aid
                 while (SL > 2 && (long long)desc->wo * ((rows + SL - 1) / SL) < 148 * 6) SL >>= 1;
+                SL = (rows + (rows + SL - 1) / SL - 1) / ((rows + SL - 1) / SL);
                 if (SL > rows) SL = rows;
                 P.ntb = best_ntb; P.SL = SL;
                 const size_t smem = best_ntb ? strip8_smem_bytes(desc, P.nta, P.ntb, SL) : (size_t)1 << 30;
@@ -792,15 +797,24 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
                 const bool few_sweeps = (desc->n2 + cands8 - 1) / cands8 <= 2 && tx_used >= 40;
                 if (few_sweeps && smem <= 110 * 1024 && desc->n1 <= S8_TI * P.nta) {
                     const int tail = desc->p - (P4 - 4);
-                    void (*kern)(StripParams) =
-                        M == 1 ? (tail == 1 ? patchnn_strip8_kernel<1, 1> : tail == 2 ? patchnn_strip8_kernel<1, 2>
-                                : tail == 3 ? patchnn_strip8_kernel<1, 3> : patchnn_strip8_kernel<1, 4>)
-                               : (tail == 1 ? patchnn_strip8_kernel<2, 1> : tail == 2 ? patchnn_strip8_kernel<2, 2>
-                                : tail == 3 ? patchnn_strip8_kernel<2, 3> : patchnn_strip8_kernel<2, 4>);
+                    const int nch = P4 / 4;
+                    Strip8Params PP;
+                    PP.P = P;
+                    // TMA staging needs the [frame][3*nch] box layout to be the conflict-free one (odd group count)
+                    const char* tenv = getenv("VL3D_NN_TMA");
+                    const bool tma = ((3 * nch) & 1) && !(tenv && atoi(tenv) == 0) &&
+                                     make_video_tmap(&PP.tx, x, desc->x_sf, desc->x_sc, desc->x_sr, tx_used, nch, S8_TI * P.nta) &&
+                                     make_video_tmap(&PP.ty, y, desc->y_sf, desc->y_sc, desc->y_sr,
+                                                     (desc->n2 - 1) * desc->st + desc->pt, nch, S8_TJ * P.ntb);
+                    void (*kern)(Strip8Params) = nullptr;
+#define VL3D_S8(MM, TT) (tma ? patchnn_strip8_kernel<MM, TT, true> : patchnn_strip8_kernel<MM, TT, false>)
+                    if (M == 1) kern = tail == 1 ? VL3D_S8(1, 1) : tail == 2 ? VL3D_S8(1, 2) : tail == 3 ? VL3D_S8(1, 3) : VL3D_S8(1, 4);
+                    else kern = tail == 1 ? VL3D_S8(2, 1) : tail == 2 ? VL3D_S8(2, 2) : tail == 3 ? VL3D_S8(2, 3) : VL3D_S8(2, 4);
+#undef VL3D_S8
                     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
                     if (ce != cudaSuccess) return set_err((int)ce, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
                     dim3 grid(desc->wo, (rows + SL - 1) / SL);
-                    kern<<<grid, P.nta * P.ntb, smem, st>>>(P);
+                    kern<<<grid, P.nta * P.ntb, smem, st>>>(PP);
                     return check_launch("patchnn_search(strip8)");
                 }
             }

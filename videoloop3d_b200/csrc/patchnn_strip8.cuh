@@ -29,19 +29,32 @@ __device__ __forceinline__ void sqdiff_tail(const float4& a, const float4& b, fl
     if (TAIL > 3) { d = a.w - b.w; acc = fmaf(d, d, acc); }
 }
 
-// M = p / s in {1, 2} (complete row groups per patch), TAIL = p - 4*(ceil(p/4) - 1) in 1..4
-template <int M, int TAIL>
-__global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __grid_constant__ StripParams P) {
-    extern __shared__ __align__(16) float smem[];
+struct alignas(64) Strip8Params {
+    CUtensorMap tx, ty;                                             // (w, h, c, frame) views of x and y (TMA staging only)
+    StripParams P;
+};
+
+// M = p / s in {1, 2} (complete row groups per patch), TAIL = p - 4*(ceil(p/4) - 1) in 1..4.
+// TMA: a pixel row of the window (3 channels x all frames of the chunk) is fetched by ONE bulk-tensor copy for x and
+// one for y — box (4*nch pixels, 1 row, 3 channels, frames), which lands in exactly the [frame][group] layout the
+// arithmetic reads (needs the group count 3*nch to be odd already) — instead of ~1700 16-byte LDGSTS per row
+// (26 % of the kernel's LSU wavefronts).  The 16-byte tail chunk then holds real pixels beyond the patch instead
+// of zeros, which is why the arithmetic skips the padding lane (TAIL) rather than relying on zero fill; frames
+// beyond the video and pixels beyond the image are zero-filled by the TMA unit.
+template <int M, int TAIL, bool TMA>
+__global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __grid_constant__ Strip8Params PP) {
+    extern __shared__ __align__(128) float smem[];
+    const StripParams& P = PP.P;
     const vl3d_loss_desc& L = P.d;
     constexpr int NBUF = 2;
     const int G4 = P.groups, NTA = P.nta, NTB = P.ntb, XF = S8_TI * NTA, CF = S8_TJ * NTB;
     const int G4S = G4 | 1;                                         // odd group stride: conflict-free operand loads
     const int nch = G4 / 3;                                         // 16-byte chunks per channel run
     const int nthreads = NTA * NTB;
+    const int xbuf4 = (G4S * XF + 7) & ~7, ybuf4 = (G4S * CF + 7) & ~7;   // float4 per buffer, 128-byte multiples
     float4* xs4 = reinterpret_cast<float4*>(smem);                  // [NBUF][XF][G4S]
-    float4* ys4 = xs4 + NBUF * G4S * XF;                            // [NBUF][CF][G4S]
-    float* Gs = reinterpret_cast<float*>(ys4 + NBUF * G4S * CF);    // [XF][CF+1]; D[n1][.] is written over it
+    float4* ys4 = xs4 + NBUF * xbuf4;                               // [NBUF][CF][G4S]
+    float* Gs = reinterpret_cast<float*>(ys4 + NBUF * ybuf4);       // [XF][CF+1]; D[n1][.] is written over it
     float* part_f = Gs + XF * (CF + 1);                             // [8][CF+1] scratch of the split reductions
     float* colmin = part_f + 8 * (CF + 1);                          // [CF]
     float* best_val = colmin + CF;                                  // [SL][n1]
@@ -61,7 +74,7 @@ __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __g
     for (int i = 0; i < S8_TI; ++i) xsa[i] = (unsigned)__cvta_generic_to_shared(xs4 + (size_t)(ta + NTA * i) * G4S);
 #pragma unroll
     for (int j = 0; j < S8_TJ; ++j) ysa[j] = (unsigned)__cvta_generic_to_shared(ys4 + (size_t)(tb + NTB * j) * G4S);
-    const unsigned xbuf_bytes = (unsigned)(G4S * XF) * 16u, ybuf_bytes = (unsigned)(G4S * CF) * 16u;
+    const unsigned xbuf_bytes = (unsigned)xbuf4 * 16u, ybuf_bytes = (unsigned)ybuf4 * 16u;
     const int tx_used = (L.n1 - 1) * st + pt, ty_used = (L.n2 - 1) * st + pt;
     const int nrows = (k1 - 1 - k0) * s + p;                        // pixel rows swept by this strip
     const int ybase = k0 * s;
@@ -83,7 +96,7 @@ __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __g
             const int gfc = ok ? gf : 0;
             const float* src = isy ? P.y + (size_t)gfc * L.y_sf + (size_t)c * L.y_sc + (size_t)(ybase + row) * L.y_sr + x0
                                    : P.x + (size_t)gfc * L.x_sf + (size_t)c * L.x_sc + (size_t)(ybase + row) * L.x_sr + x0;
-            float4* d4 = (isy ? ys4 + (size_t)buf * G4S * CF : xs4 + (size_t)buf * G4S * XF) + (size_t)fr * G4S + c * nch;
+            float4* d4 = (isy ? ys4 + (size_t)buf * ybuf4 : xs4 + (size_t)buf * xbuf4) + (size_t)fr * G4S + c * nch;
             for (int j = 0; j < nch; ++j) {
                 const int nval = ok ? min(4, p - 4 * j) * 4 : 0;
                 const unsigned d = (unsigned)__cvta_generic_to_shared(d4 + j);
@@ -91,6 +104,19 @@ __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __g
             }
         }
         cp_async_commit();
+    };
+
+    __shared__ __align__(8) uint64_t s_full[2];
+    if (TMA && tid == 0) {
+        mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+        mbar_fence_init();
+    }
+    unsigned it = 0;                                                // row iterations so far (TMA: buffer = it & 1, phase = it >> 1)
+    auto stage_tma = [&](int c0, int row, unsigned slot) {          // thread 0 only
+        const int buf = (int)(slot & 1u);
+        mbar_arrive_expect_tx(&s_full[buf], (unsigned)(XF + CF) * 3u * (unsigned)nch * 16u);
+        tma_load_4d(xs4 + (size_t)buf * xbuf4, &PP.tx, &s_full[buf], x0, ybase + row, 0, 0);
+        tma_load_4d(ys4 + (size_t)buf * ybuf4, &PP.ty, &s_full[buf], x0, ybase + row, 0, c0);
     };
 
     float hist[M][S8_TI * S8_TJ];                                   // ring of complete row groups (local memory)
@@ -107,13 +133,20 @@ __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __g
 #pragma unroll
             for (int j = 0; j < S8_TJ; ++j) cur[i][j] = 0.f;
 
-        __syncthreads();                                            // previous chunk's readers are done
-        stage(c0, 0, 0);
-        for (int row = 0; row < nrows; ++row) {
-            const int buf = row & 1;
-            cp_async_wait_all();
-            __syncthreads();                                        // row `row` landed; buffer buf^1 is free
-            if (row + 1 < nrows) stage(c0, row + 1, buf ^ 1);       // overlaps the arithmetic below
+        __syncthreads();                                            // previous chunk's readers are done (and the barriers exist)
+        if (TMA) { if (tid == 0) stage_tma(c0, 0, it); }
+        else stage(c0, 0, 0);
+        for (int row = 0; row < nrows; ++row, ++it) {
+            const int buf = TMA ? (int)(it & 1u) : (row & 1);
+            if (TMA) {
+                __syncthreads();                                    // everybody is done with row-1: its buffer is free
+                if (tid == 0 && row + 1 < nrows) stage_tma(c0, row + 1, it + 1);   // overlaps the arithmetic below
+                mbar_wait(&s_full[buf], (it >> 1) & 1u);            // row `row` has landed
+            } else {
+                cp_async_wait_all();
+                __syncthreads();                                    // row `row` landed; buffer buf^1 is free
+                if (row + 1 < nrows) stage(c0, row + 1, buf ^ 1);   // overlaps the arithmetic below
+            }
             const int grp = row / s, rin = row - grp * s;           // group of s rows, row inside the group
             {
                 unsigned xa_[S8_TI], ya_[S8_TJ];
@@ -270,8 +303,23 @@ __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __g
 
 static size_t strip8_smem_bytes(const vl3d_loss_desc* L, int nta, int ntb, int SL) {
     const int G4S = (3 * ((L->p + 3) / 4)) | 1, XF = S8_TI * nta, CF = S8_TJ * ntb;
-    size_t fl = (size_t)4 * 2 * G4S * (XF + CF) + (size_t)XF * (CF + 1) + (size_t)8 * (CF + 1) + CF + 2 * (size_t)SL * L->n1;
+    size_t fl = (size_t)4 * 2 * (((G4S * XF + 7) & ~7) + ((G4S * CF + 7) & ~7)) + (size_t)XF * (CF + 1) + (size_t)8 * (CF + 1) + CF + 2 * (size_t)SL * L->n1;
     return fl * sizeof(float);
+}
+
+// (w, h, c, frame) tensor map of a planar video with element strides (frame, channel, row); box = (4*nch, 1, 3, nframes)
+static bool make_video_tmap(CUtensorMap* out, const float* base, long long sf, long long sc, long long sr, int frames, int nch,
+                            int box_frames) {
+    vl3d_encode_tiled_fn enc = tma_encoder();
+    if (enc == nullptr || box_frames > 256 || frames < 1 || sr < 4 * nch || sc < sr || sf < 3 * sc) return false;
+    const cuuint64_t gdim[4] = {(cuuint64_t)sr, (cuuint64_t)(sc / sr), 3, (cuuint64_t)frames};
+    const cuuint64_t gstr[3] = {(cuuint64_t)sr * 4, (cuuint64_t)sc * 4, (cuuint64_t)sf * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)(4 * nch), 1, 3, (cuuint32_t)box_frames};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (gstr[2] >= ((cuuint64_t)1 << 40)) return false;
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace vl3d
