@@ -43,7 +43,8 @@ struct alignas(64) Strip8Params {
 // beyond the video and pixels beyond the image are zero-filled by the TMA unit.
 template <int M, int TAIL, bool TMA>
 __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __grid_constant__ Strip8Params PP) {
-    extern __shared__ __align__(128) float smem[];
+    extern __shared__ __align__(128) float smem8[];                 // (own symbol: TMA destinations need 128-byte alignment)
+    float* smem = smem8;
     const StripParams& P = PP.P;
     const vl3d_loss_desc& L = P.d;
     constexpr int NBUF = 2;
