@@ -29,6 +29,7 @@ CASES = [
     ("p7_tile8",      42, 70,  23, 32, 7, 3, 4, 1, 1e4, "-2", "lm"),       # 6 groups: LDGSTS staging, 1 row group
     ("p8_tile8_rem0", 41, 300, 28, 36, 8, 2, 4, 1, 0.0, "0", "lm"),        # no padding lane, two sweeps, p == 2 s
     ("p4_tile8_tma",  43, 60,  16, 24, 4, 3, 4, 1, 1e4, "abs", "lm"),      # 3 groups: TMA staging, p == s
+    ("p15_tile8_M3",  20, 45,  31, 40, 15, 3, 4, 1, 0.0, "-2", "lm"),      # 3 row groups in the local-memory ring, few frames
 ]
 
 

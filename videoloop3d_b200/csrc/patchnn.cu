@@ -766,20 +766,12 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
             const bool vec = desc->s % 4 == 0 && (3 * desc->p + 3) / 4 == 3 * P4 / 4 &&
                              ((desc->x_sf | desc->x_sc | desc->x_sr | desc->y_sf | desc->y_sc | desc->y_sr) & 3) == 0 &&
                              (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
-            if (vec && (M == 1 || M == 2) && !(t8 && atoi(t8) == 0)) {
+            if (vec && M >= 1 && M <= 3 && !(t8 && atoi(t8) == 0)) {
                 StripParams P{};
                 P.d = *desc; P.x = x; P.y = y; P.nn = nn_out; P.groups = 3 * (P4 / 4);
                 P.row0 = row_begin; P.row1 = row_end;
                 P.nta = (tx_used + S8_TI - 1) / S8_TI;
                 if (P.nta < 2) P.nta = 2;
-                int best_ntb = 0; long long best_cost = 0;
-                for (int ntb = (desc->pt + S8_TJ - 1) / S8_TJ + 1; ntb <= NN_THREADS / P.nta; ++ntb) {
-                    const int cands = (S8_TJ * ntb - desc->pt) / desc->st + 1;
-                    const int chunks = (desc->n2 + cands - 1) / cands;
-                    const long long cost = (long long)chunks * S8_TJ * ntb * 64 + 4000LL * chunks;
-                    if (P.nta * ntb < 64) continue;
-                    if (best_ntb == 0 || cost < best_cost) { best_ntb = ntb; best_cost = cost; }
-                }
                 const int rows = row_end - row_begin;
                 // strip length: long strips share more rows between patches (measured at 720p: 8 / 16 / 24 / 32 patches
                 // per strip = 21.3 / 20.2 / 19.8 / 22.0 ms), balanced so that the last strip is not a stub
@@ -788,28 +780,39 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
                 while (SL > 2 && (long long)desc->wo * ((rows + SL - 1) / SL) < 148 * 6) SL >>= 1;
                 SL = (rows + (rows + SL - 1) / SL - 1) / ((rows + SL - 1) / SL);
                 if (SL > rows) SL = rows;
+                // candidate chunk width 8*ntb: fewest sweeps that still leave two CTAs per SM
+                int best_ntb = 0; long long best_cost = 0;
+                for (int ntb = (desc->pt + S8_TJ - 1) / S8_TJ + 1; ntb <= NN_THREADS / P.nta; ++ntb) {
+                    const int cands = (S8_TJ * ntb - desc->pt) / desc->st + 1;
+                    const int chunks = (desc->n2 + cands - 1) / cands;
+                    const long long cost = (long long)chunks * S8_TJ * ntb * 64 + 4000LL * chunks;
+                    if (P.nta * ntb < 64 || strip8_smem_bytes(desc, P.nta, ntb, SL) > 110 * 1024) continue;
+                    if (best_ntb == 0 || cost < best_cost) { best_ntb = ntb; best_cost = cost; }
+                }
                 P.ntb = best_ntb; P.SL = SL;
                 const size_t smem = best_ntb ? strip8_smem_bytes(desc, P.nta, P.ntb, SL) : (size_t)1 << 30;
-                // measured on B200 (scripts/tune_search.py): the wide chunk pays when the whole candidate set is
-                // covered in at most two sweeps over the query rows (n2 = 256: 20.2 vs 22.0 ms at 720p); with more
-                // sweeps (n2 = 1024: 88 vs 79 ms) or few query frames (T = 24) the 4 x 4 kernel is faster.
+                const int nch = P4 / 4;
+                Strip8Params PP;
+                // TMA staging (VL3D_NN_TMA=0: tuning aid); the box carries nch | 1 chunks per channel
+                const char* tenv = getenv("VL3D_NN_TMA");
+                const bool fits = best_ntb && smem <= 110 * 1024 && desc->n1 <= S8_TI * P.nta;
+                const bool tma = fits && !(tenv && atoi(tenv) == 0) &&
+                                 make_video_tmap(&PP.tx, x, desc->x_sf, desc->x_sc, desc->x_sr, tx_used, nch | 1, S8_TI * P.nta) &&
+                                 make_video_tmap(&PP.ty, y, desc->y_sf, desc->y_sc, desc->y_sr,
+                                                 (desc->n2 - 1) * desc->st + desc->pt, nch | 1, S8_TJ * P.ntb);
+                // measured on B200 at 720p (scripts/tune_search.py), 4x8 vs 4x4 tiles.  With TMA staging: p=11 n2=256
+                // 17.1 vs 22.0 ms, p=7 14.4 vs 15.8, n2=1024 60.4 vs 78.3, T=24 35.9 vs 35.8 -> always.  With LDGSTS staging
+                // the wide chunk only pays when <= 2 sweeps cover the candidates (20.2 vs 22.0; n2=1024: 88 vs 79).
                 const int cands8 = best_ntb ? (S8_TJ * best_ntb - desc->pt) / desc->st + 1 : 1;
                 const bool few_sweeps = (desc->n2 + cands8 - 1) / cands8 <= 2 && tx_used >= 40;
-                if (few_sweeps && smem <= 110 * 1024 && desc->n1 <= S8_TI * P.nta) {
+                if (fits && (tma || few_sweeps)) {
                     const int tail = desc->p - (P4 - 4);
-                    const int nch = P4 / 4;
-                    Strip8Params PP;
                     PP.P = P;
-                    // TMA staging needs the [frame][3*nch] box layout to be the conflict-free one (odd group count)
-                    const char* tenv = getenv("VL3D_NN_TMA");
-                    const bool tma = ((3 * nch) & 1) && !(tenv && atoi(tenv) == 0) &&
-                                     make_video_tmap(&PP.tx, x, desc->x_sf, desc->x_sc, desc->x_sr, tx_used, nch, S8_TI * P.nta) &&
-                                     make_video_tmap(&PP.ty, y, desc->y_sf, desc->y_sc, desc->y_sr,
-                                                     (desc->n2 - 1) * desc->st + desc->pt, nch, S8_TJ * P.ntb);
                     void (*kern)(Strip8Params) = nullptr;
 #define VL3D_S8(MM, TT) (tma ? patchnn_strip8_kernel<MM, TT, true> : patchnn_strip8_kernel<MM, TT, false>)
                     if (M == 1) kern = tail == 1 ? VL3D_S8(1, 1) : tail == 2 ? VL3D_S8(1, 2) : tail == 3 ? VL3D_S8(1, 3) : VL3D_S8(1, 4);
-                    else kern = tail == 1 ? VL3D_S8(2, 1) : tail == 2 ? VL3D_S8(2, 2) : tail == 3 ? VL3D_S8(2, 3) : VL3D_S8(2, 4);
+                    else if (M == 2) kern = tail == 1 ? VL3D_S8(2, 1) : tail == 2 ? VL3D_S8(2, 2) : tail == 3 ? VL3D_S8(2, 3) : VL3D_S8(2, 4);
+                    else kern = tail == 1 ? VL3D_S8(3, 1) : tail == 2 ? VL3D_S8(3, 2) : tail == 3 ? VL3D_S8(3, 3) : VL3D_S8(3, 4);
 #undef VL3D_S8
                     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
                     if (ce != cudaSuccess) return set_err((int)ce, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));

@@ -34,10 +34,10 @@ struct alignas(64) Strip8Params {
     StripParams P;
 };
 
-// M = p / s in {1, 2} (complete row groups per patch), TAIL = p - 4*(ceil(p/4) - 1) in 1..4.
+// M = p / s in {1, 2, 3} (complete row groups per patch), TAIL = p - 4*(ceil(p/4) - 1) in 1..4.
 // TMA: a pixel row of the window (3 channels x all frames of the chunk) is fetched by ONE bulk-tensor copy for x and
-// one for y — box (4*nch pixels, 1 row, 3 channels, frames), which lands in exactly the [frame][group] layout the
-// arithmetic reads (needs the group count 3*nch to be odd already) — instead of ~1700 16-byte LDGSTS per row
+// one for y — box (4*nchS pixels, 1 row, 3 channels, frames), which lands in exactly the [frame][channel][chunk]
+// layout the arithmetic reads (nchS = nch | 1 chunks per channel keep the group stride odd) — instead of ~1700 16-byte LDGSTS per row
 // (26 % of the kernel's LSU wavefronts).  The 16-byte tail chunk then holds real pixels beyond the patch instead
 // of zeros, which is why the arithmetic skips the padding lane (TAIL) rather than relying on zero fill; frames
 // beyond the video and pixels beyond the image are zero-filled by the TMA unit.
@@ -49,8 +49,9 @@ __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __g
     const vl3d_loss_desc& L = P.d;
     constexpr int NBUF = 2;
     const int G4 = P.groups, NTA = P.nta, NTB = P.ntb, XF = S8_TI * NTA, CF = S8_TJ * NTB;
-    const int G4S = G4 | 1;                                         // odd group stride: conflict-free operand loads
     const int nch = G4 / 3;                                         // 16-byte chunks per channel run
+    const int nchS = nch | 1;                                       // chunks staged per channel (one spare if nch is even)
+    const int G4S = 3 * nchS;                                       // odd group stride: conflict-free operand loads
     const int nthreads = NTA * NTB;
     const int xbuf4 = (G4S * XF + 7) & ~7, ybuf4 = (G4S * CF + 7) & ~7;   // float4 per buffer, 128-byte multiples
     float4* xs4 = reinterpret_cast<float4*>(smem);                  // [NBUF][XF][G4S]
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __g
             const int gfc = ok ? gf : 0;
             const float* src = isy ? P.y + (size_t)gfc * L.y_sf + (size_t)c * L.y_sc + (size_t)(ybase + row) * L.y_sr + x0
                                    : P.x + (size_t)gfc * L.x_sf + (size_t)c * L.x_sc + (size_t)(ybase + row) * L.x_sr + x0;
-            float4* d4 = (isy ? ys4 + (size_t)buf * ybuf4 : xs4 + (size_t)buf * xbuf4) + (size_t)fr * G4S + c * nch;
+            float4* d4 = (isy ? ys4 + (size_t)buf * ybuf4 : xs4 + (size_t)buf * xbuf4) + (size_t)fr * G4S + c * nchS;
             for (int j = 0; j < nch; ++j) {
                 const int nval = ok ? min(4, p - 4 * j) * 4 : 0;
                 const unsigned d = (unsigned)__cvta_generic_to_shared(d4 + j);
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __g
     unsigned it = 0;                                                // row iterations so far (TMA: buffer = it & 1, phase = it >> 1)
     auto stage_tma = [&](int c0, int row, unsigned slot) {          // thread 0 only
         const int buf = (int)(slot & 1u);
-        mbar_arrive_expect_tx(&s_full[buf], (unsigned)(XF + CF) * 3u * (unsigned)nch * 16u);
+        mbar_arrive_expect_tx(&s_full[buf], (unsigned)(XF + CF) * (unsigned)G4S * 16u);
         tma_load_4d(xs4 + (size_t)buf * xbuf4, &PP.tx, &s_full[buf], x0, ybase + row, 0, 0);
         tma_load_4d(ys4 + (size_t)buf * ybuf4, &PP.ty, &s_full[buf], x0, ybase + row, 0, c0);
     };
@@ -181,10 +182,11 @@ __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __g
                         for (int i = 0; i < S8_TI; ++i)
 #pragma unroll
                             for (int j = 0; j < S8_TJ; ++j) sqdiff_tail<TAIL>(xa[i], ya[j], cur[i][j]);
+                        const unsigned adv = 16u * (unsigned)(1 + nchS - nch);      // (skips the spare chunk)
 #pragma unroll
-                        for (int i = 0; i < S8_TI; ++i) xa_[i] += 16;
+                        for (int i = 0; i < S8_TI; ++i) xa_[i] += adv;
 #pragma unroll
-                        for (int j = 0; j < S8_TJ; ++j) ya_[j] += 16;
+                        for (int j = 0; j < S8_TJ; ++j) ya_[j] += adv;
                     }
                 }
             }
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __g
 }
 
 static size_t strip8_smem_bytes(const vl3d_loss_desc* L, int nta, int ntb, int SL) {
-    const int G4S = (3 * ((L->p + 3) / 4)) | 1, XF = S8_TI * nta, CF = S8_TJ * ntb;
+    const int G4S = 3 * (((L->p + 3) / 4) | 1), XF = S8_TI * nta, CF = S8_TJ * ntb;
     size_t fl = (size_t)4 * 2 * (((G4S * XF + 7) & ~7) + ((G4S * CF + 7) & ~7)) + (size_t)XF * (CF + 1) + (size_t)8 * (CF + 1) + CF + 2 * (size_t)SL * L->n1;
     return fl * sizeof(float);
 }
