@@ -236,14 +236,23 @@ class FusedLoopStep:
             else:
                 ops.composite_fwd(view, pack, dyn_local, atlas.data, None, Tl, 0, rgb_out=rgb_pad[t0:t1],
                                   smooth_sums=fwd_sums)
+        gather = None
         if self.world > 1:
-            with self._timed("allgather_rgb"):
+            # asynchronous: the target-frame sums of the scale-invariant gain (which do not need the rendered video)
+            # run on the compute stream while NVLink moves the frames; waited for right before the gain is evaluated
+            with self._timed("allgather_rgb_issue"):
                 sizes = {b - a for a, b in zip(self.bounds[:-1], self.bounds[1:])}
                 if len(sizes) == 1:
-                    dist.all_gather_into_tensor(rgb_pad[:T], rgb_pad[t0:t1], group=self.group)
+                    gather = dist.all_gather_into_tensor(rgb_pad[:T], rgb_pad[t0:t1], group=self.group, async_op=True)
                 else:
                     parts = [rgb_pad[a:b] for a, b in zip(self.bounds[:-1], self.bounds[1:])]
-                    dist.all_gather(parts, rgb_pad[t0:t1].clone(), group=self.group)
+                    gather = dist.all_gather(parts, rgb_pad[t0:t1].clone(), group=self.group, async_op=True)
+
+        def finish_gather():
+            nonlocal gather
+            if gather is not None:
+                gather.wait()
+                gather = None
                 if pad:
                     rgb_pad[T:T + pad].copy_(rgb_pad[:pad])          # loop pad (MPV.py:490-492)
 
@@ -263,7 +272,9 @@ class FusedLoopStep:
                     fb = partition(res0.shape[0], self.world)
                     rsum = ops.frame_sum(res0[fb[self.rank]:fb[self.rank + 1]], out=self._get("res_sum", (3, h, w), torch.float32))
                     dist.all_reduce(rsum, group=self.group)
+                    finish_gather()
                     xscale = ops.scale_invariant_presum(rgb_pad, T, rsum, res0.shape[0], out=out, partials=part)
+        finish_gather()
         desc = ops.make_loss_desc(rgb_pad.shape, (rgb_pad.stride(0), rgb_pad.stride(1), rgb_pad.stride(2)), res0.shape,
                                   (res0.stride(0), res0.stride(1), res0.stride(2)), cfg["patch_size"],
                                   cfg["patcht_size"], cfg["stride"], cfg["stridet"], cfg.get("alpha", 1e10),
@@ -277,12 +288,17 @@ class FusedLoopStep:
             # patch positions are independent (utils_vid.py:211-215): each rank searches a band of patch rows,
             # then the int32 index map is summed across ranks (disjoint rows, zeros elsewhere)
             rows = partition(desc.ho, self.world)
-            nn.zero_()
+            equal_bands = len({b - a for a, b in zip(rows[:-1], rows[1:])}) == 1
+            if not equal_bands:
+                nn.zero_()
             with self._timed("patchnn_search"):
                 ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn, rows=(rows[self.rank], rows[self.rank + 1]),
                                    scaled_ws=x_scaled)
-            with self._timed("allreduce_nn"):
-                dist.all_reduce(nn, group=self.group)
+            with self._timed("exchange_nn"):
+                if equal_bands:
+                    dist.all_gather_into_tensor(nn, nn[rows[self.rank]:rows[self.rank + 1]], group=self.group)
+                else:
+                    dist.all_reduce(nn, group=self.group)            # disjoint rows, zeros elsewhere
         grad_rgb = self._get("grad_rgb", (T + pad, 3, h, w), torch.float32)
         n_part = ops._lib.load().vl3d_vote_partials(T + pad, h, w)
         vote_part = self._get("vote_part", (n_part,), torch.float64)
