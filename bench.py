@@ -196,10 +196,99 @@ def cpu_reference_step(sample, threads, steps, warmup=1):
     return float(np.mean(times[warmup:]))
 
 
+def gpu_torch_reference_step(wl, dev, steps):
+    """The reference's torch operator sequence (oracle/torch_ref_ops.py) on the GPU, SURVEY §8(d) "reference GPU
+    baseline": the frame is covered by non-overlapping patches of the reference's own step shape (180x320,
+    configs/mpv_base.txt:21-24), gradients accumulated, one Adam step = one full-frame-equivalent step.
+    The rasteriser stand-in runs on the host beforehand and is NOT timed.  Adam is timed after the patches (its
+    state is allocated only then, so that the patches' autograd temporaries and the optimiser state never
+    coexist: 5 x 22.6 GB during a patch, 6 x 22.6 GB during Adam at 720p).  Returns (ms patches, ms adam, n)."""
+    from oracle import mpv_oracle as MO
+    from oracle import torch_ref_ops as RO
+    H, W, D, T = wl["H"], wl["W"], wl["D"], wl["T"]
+    ph, pw = min(H, 180), min(W, 320)
+    st = MO.dense_state(H, W, D, wl["hv"], wl["wv"], 4 if D % 4 == 0 else 1, 1, 1.0, 10.0, 1.0, 1.0, seed=2)
+    hd, wd = st.atlas_dyn.shape[-2:]
+    st.atlas = st.atlas[:, :, :1, :1].clone()
+    ext, intr = view_for(wl)
+    tiles = []
+    for hs in range(0, H - ph + 1, ph):
+        for ws in range(0, W - pw + 1, pw):
+            k = intr.clone()
+            k[0, 0, 2] -= ws                                        # get_new_intrin, utils.py:196-200
+            k[0, 1, 2] -= hs
+            tiles.append((hs, ws, RO.raster_tables(st, ph, pw, ext, k, dev)))
+    g = torch.Generator(device=dev).manual_seed(2)
+    atlas_dyn = torch.empty((T, 4, hd, wd), dtype=torch.float32, device=dev)
+    for t in range(T):
+        atlas_dyn[t].normal_(generator=g)
+    atlas_dyn[:, 3] -= 1.0
+    atlas_dyn.requires_grad_(True)
+    atlas = torch.zeros((1, 4, 1, 1), device=dev, requires_grad=True)
+    res = make_target(wl, dev)
+    cfg = dict(loss_name="gpnn_lm", loss_gain=3.5, patch_size=11, patcht_size=3, stride=4, stridet=1, alpha=0.0,
+               rou="-2", scaling=0.1, dist_fn="mse", macro_block=65, factor=1)
+    opt = torch.optim.Adam([atlas_dyn], lr=1e-4, betas=(0.9, 0.999), eps=6e-8, foreach=False)
+
+    def patches(which):
+        for hs, ws, tabs in which:
+            crop = res[..., hs:hs + ph, ws:ws + pw]
+            total, _, _ = RO.forward_train_ops(atlas, atlas_dyn, tabs, ph, pw, crop, cfg, D)
+            total.backward()
+
+    patches(tiles[:1])                                              # warm-up (allocator, cuBLAS handles)
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    e[0].record()
+    for _ in range(steps):
+        patches(tiles)
+    e[1].record()
+    torch.cuda.synchronize()
+    opt.step()                                                      # allocates exp_avg / exp_avg_sq
+    torch.cuda.synchronize()
+    e[2].record()
+    for _ in range(steps):
+        opt.step()
+    e[3].record()
+    torch.cuda.synchronize()
+    return e[0].elapsed_time(e[1]) / steps, e[2].elapsed_time(e[3]) / steps, len(tiles), (ph, pw)
+
+
+def run_reference_cuda(args):
+    """`--impl reference --ref-device cuda`: not the driver's reference arm (that one is the host-CPU run below),
+    but the comparison BASELINE.json's north_star names: the reference's PyTorch step on the same single B200."""
+    wl = WORKLOADS[args.workload]
+    base = {"impl": "reference", "metric": METRIC, "unit": "steps/s", "n_gpus": 1, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "device": "cuda:0 (torch eager, allow_tf32=False)"}}
+    if not torch.cuda.is_available():
+        print(json.dumps({**base, "unavailable": "--ref-device cuda needs a GPU"}))
+        return
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    steps = max(1, min(args.steps, 2))
+    try:
+        ms_p, ms_a, n, (ph, pw) = gpu_torch_reference_step(wl, torch.device("cuda", 0), steps)
+    except torch.cuda.OutOfMemoryError as ex:
+        print(json.dumps({**base, "unavailable": f"out of memory: {str(ex)[:120]}"}))
+        return
+    ms = ms_p + ms_a
+    print(json.dumps({**base, "value": 1000.0 / ms, "steps": steps, "warmup": 1, "ms_per_step": ms,
+                      "parts_ms": {"patches_fwd_bwd": ms_p, "adam": ms_a},
+                      "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9,
+                      "sample": f"{n} patches of {ph}x{pw} (the reference's step shape) covering {wl['H']}x{wl['W']}, "
+                                f"gradients accumulated, one torch.optim.Adam step; reference operator sequence "
+                                f"(grid_sample / masked_scatter / cumprod / unfold / bmm / index_add), host "
+                                f"rasteriser stand-in not timed",
+                      "gpu_launches": 0}))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.ref_device == "cuda":
+        return run_reference_cuda(args)
     threads = os.cpu_count() or 1
     wl = WORKLOADS[args.workload]
     sample = dict(CPU_SAMPLE) if args.workload == "step720p" else dict(wl)
@@ -394,6 +483,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="step720p", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference: host CPU (the reference arm) or the reference's torch operators on cuda:0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-smooth", action="store_true", help="tuning aid: drop the smoothness regularisers")
     ap.add_argument("--overlap-chunks", type=int, default=1, help="frame chunks of the backward/Adam pipeline (1 = off)")

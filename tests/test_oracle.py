@@ -100,3 +100,25 @@ def test_nnerr_matches_reference():
             p, s, pt, st = (int(v) for v in g[f"cfg{i}"])
             e = LL.compute_nnerr(src, tar, p, s, pt, st, macro_block=25)
             assert abs(e - float(g[f"err{i}"])) < 1e-6 * float(g[f"err{i}"])
+
+
+@pytest.mark.parametrize("name", ["step_dense_refcfg", "step_sparse_othercfg"])
+def test_reference_operator_sequence_matches_reference(name):
+    """oracle/torch_ref_ops.py (the timed `bench.py --impl reference --ref-device cuda` baseline: grid_sample /
+    masked_scatter / cumprod / unfold / bmm / index_add in the reference's order, fp32) reproduces the unmodified
+    reference's losses and gradients of a whole stage-2 step."""
+    from oracle import torch_ref_ops as RO
+    g = load_golden(name)
+    st = state_from_golden(g)
+    cfg = cfg_from_golden(g)
+    H, W = int(g["H"]), int(g["W"])
+    tabs = RO.raster_tables(st, H, W, torch.as_tensor(g["tar_extrin"]), torch.as_tensor(g["tar_intrin"]), "cpu")
+    a = st.atlas.float().requires_grad_(True)
+    ad = st.atlas_dyn.float().requires_grad_(True)
+    total, extra, _ = RO.forward_train_ops(a, ad, tabs, H, W, torch.as_tensor(g["res"]), cfg, st.mpi_d,
+                                           rgb_smooth_w=float(g["rgb_smooth_w"]), a_smooth_w=float(g["a_smooth_w"]))
+    for k, v in extra.items():
+        assert abs(float(v) - float(g["extra_" + k].reshape(-1)[0])) < 1e-5 * max(1.0, abs(float(v))), k
+    assert abs(float(total) - float(g["loss"])) < 1e-5
+    total.backward()
+    assert relerr(ad.grad, g["grad_atlas_dyn"]) < 1e-3
