@@ -223,12 +223,72 @@ def golden_nnerr(name):
     print(name, [float(out[f"err{i}"]) for i in range(3)])
 
 
+def golden_lod(name, H=32, W=48, D=4, hv=5, wv=7, T=3, tile=8, seed=3):
+    """the unmodified reference's `MPMeshVid.lod` (MPV.py:140-198) on a tile-culled model —
+    full -> 0.5 (down-sampling) -> 1.0 (up-sampling from the half-size tiles, as the pyramid schedule does,
+    train_3dvid.py:259-272) — and on the dense layout.
+    torchvision boundary: the reference pins torch==1.10 (torchvision 0.11), where `Resize(size)(tensor)` never
+    anti-aliases; the torchvision installed here defaults to antialias=True for tensors.  For the DOWN-sampling
+    call only, `Resize` is therefore constructed with the pinned version's behaviour (antialias=False) through a
+    default-argument shim around the reference's call; the as-installed (anti-aliased) result is stored next to
+    it (`*_aa`) to document the difference.  Up-sampling is identical under both."""
+    import torchvision
+    real_resize = torchvision.transforms.Resize
+
+    class PinnedResize(real_resize):
+        def __init__(self, size, *a, **k):
+            k.setdefault("antialias", False)
+            super().__init__(size, *a, **k)
+
+    def grids(m, st):
+        m.atlas_grid_h, m.atlas_grid_w = st.atlas.shape[-2] // tile, st.atlas.shape[-1] // tile
+        m.atlas_full_h, m.atlas_full_w = st.atlas.shape[-2:]
+        m.atlas_grid_dyn_h, m.atlas_grid_dyn_w = st.atlas_dyn.shape[-2] // tile, st.atlas_dyn.shape[-1] // tile
+        m.atlas_full_dyn_h, m.atlas_full_dyn_w = st.atlas_dyn.shape[-2:]
+
+    out = {}
+    for tag, resize in (("", PinnedResize), ("_aa", real_resize)):
+        m, st, _ = make_model("sparse", H, W, D, hv, wv, T, seed, tile=tile, occ=0.8, scale=1.3)
+        grids(m, st)
+        torchvision.transforms.Resize = resize
+        try:
+            m.lod(0.5)
+            half = dict(atlas=m.atlas.data.clone(), atlas_dyn=m.atlas_dyn.data.clone(), uvs=m.uvs.data.clone(),
+                        uvs_dyn=m.uvs_dyn.data.clone())
+            m.lod(1.0)
+        finally:
+            torchvision.transforms.Resize = real_resize
+        out.update({f"half{tag}_{k}": v for k, v in half.items()})
+        out.update({f"full{tag}_atlas": m.atlas.data, f"full{tag}_atlas_dyn": m.atlas_dyn.data, f"full{tag}_uvs": m.uvs.data,
+                    f"full{tag}_uvs_dyn": m.uvs_dyn.data})
+        if tag == "":
+            out.update(_state_arrays(st))
+    # dense layout: 0.5 of the full atlas (pinned Resize), then back up to 1.0
+    md, std, _ = make_model("dense", H, W, D, hv, wv, T, seed + 1, grid_h=2, scale=1.2)
+    md.is_sparse = False
+    torchvision.transforms.Resize = PinnedResize
+    try:
+        md.lod(0.5)
+        out["dense_half_atlas_dyn"] = md.atlas_dyn.data.clone()
+        md.lod(1.0)
+        out["dense_full_atlas_dyn"] = md.atlas_dyn.data.clone()
+    finally:
+        torchvision.transforms.Resize = real_resize
+    out["dense_atlas_dyn"] = std.atlas_dyn
+    out.update(H=H, W=W, tile=tile, dense_grid_h=2, dense_scale=1.2, dense_seed=seed + 1)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(out))
+    print(name, "half tiles", tuple(out["half_atlas_dyn"].shape), "aa differs by",
+          float((out["half_atlas_dyn"] - out["half_aa_atlas_dyn"]).abs().max()),
+          "| up-sampled", tuple(out["full_atlas_dyn"].shape))
+
+
 def main():
     assert ref_env.reference_available(), "needs /root/reference"
     ref_env.enable()
     os.makedirs(OUT, exist_ok=True)
     golden_pointwise("pointwise")
     golden_nnerr("nnerr")
+    golden_lod("lod")
     golden_render("render_dense", "dense", seed=0)
     golden_render("render_sparse", "sparse", seed=1, D=6, hv=6, wv=9, T=2)
     golden_step("step_dense_refcfg", "dense", LOSS_CFG_REF, seed=2)

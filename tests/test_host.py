@@ -125,3 +125,58 @@ def test_product_refuses_cpu_tensors():
     x, y = torch.rand(1, 3, 5, 9, 9), torch.rand(1, 3, 6, 9, 9)
     with pytest.raises(Vl3dError):
         Patch3DGPNNLowMemLoss()(x, y, patch_size=3, stride=2, patcht_size=3, stridet=1)
+
+
+def _lod_model(g, dense=False):
+    from videoloop3d_b200.testing import model_from_tensors
+    from videoloop3d_b200 import MPMeshVid, default_args
+    H, W, tile = int(g["H"]), int(g["W"]), int(g["tile"])
+    if dense:
+        args = default_args(mpi_d=int(g["mpi_d"]), mpi_h_verts=int(g["hv"]), mpi_w_verts=int(g["wv"]),
+                            atlas_grid_h=int(g["dense_grid_h"]), mpv_frm_num=g["dense_atlas_dyn"].shape[0],
+                            mpi_h_scale=float(g["dense_scale"]), mpi_w_scale=float(g["dense_scale"]))
+        f = 0.8 * W
+        m = MPMeshVid(args, H, W, np.eye(4, dtype=np.float32),
+                      np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32), 1.0, 10.0)
+        m.atlas_dyn.data = torch.as_tensor(g["dense_atlas_dyn"]).clone()
+        return m
+    m = model_from_tensors(g, H, W, torch.device("cpu"))
+    m.atlas_grid_h, m.atlas_grid_w = g["atlas"].shape[-2] // tile, g["atlas"].shape[-1] // tile
+    m.atlas_full_h, m.atlas_full_w = g["atlas"].shape[-2:]
+    m.atlas_grid_dyn_h, m.atlas_grid_dyn_w = g["atlas_dyn"].shape[-2] // tile, g["atlas_dyn"].shape[-1] // tile
+    m.atlas_full_dyn_h, m.atlas_full_dyn_w = g["atlas_dyn"].shape[-2:]
+    return m
+
+
+def test_lod_matches_reference():
+    """SURVEY §8(f) N2: `MPMeshVid.lod` against the unmodified reference's (MPV.py:140-198;
+    oracle/make_golden.py::golden_lod): per-tile bilinear resize + uv re-alignment of a tile-culled model,
+    full -> 0.5 -> 1.0, and the dense layout.  The down-sampling golden uses torchvision's behaviour at the
+    reference's pinned version (no anti-aliasing for tensors); up-sampling does not depend on it."""
+    from util import load_golden
+    g = load_golden("lod")
+    m = _lod_model(g)
+    m.lod(0.5)
+    for k in ("atlas", "atlas_dyn", "uvs", "uvs_dyn"):
+        got, ref = getattr(m, k).data, torch.as_tensor(g["half_" + k])
+        assert tuple(got.shape) == tuple(ref.shape), k
+        assert float((got - ref).abs().max()) < 2e-6, k
+    assert m.atlas_dyn.data.is_contiguous(memory_format=torch.channels_last)
+    m.lod(1.0)
+    for k in ("atlas", "atlas_dyn", "uvs", "uvs_dyn"):
+        got, ref = getattr(m, k).data, torch.as_tensor(g["full_" + k])
+        assert tuple(got.shape) == tuple(ref.shape), k
+        assert float((got - ref).abs().max()) < 2e-6, k
+    # up-sampling alone, from the reference's anti-aliased half-size state: independent of the torchvision default
+    m2 = _lod_model(g)
+    m2.lod(0.5)
+    for k in ("atlas", "atlas_dyn"):
+        getattr(m2, k).data.copy_(torch.as_tensor(g["half_aa_" + k]))
+    m2.lod(1.0)
+    for k in ("atlas", "atlas_dyn", "uvs", "uvs_dyn"):
+        assert float((getattr(m2, k).data - torch.as_tensor(g["full_aa_" + k])).abs().max()) < 2e-6, k
+    md = _lod_model(g, dense=True)
+    md.lod(0.5)
+    assert float((md.atlas_dyn.data - torch.as_tensor(g["dense_half_atlas_dyn"])).abs().max()) < 2e-6
+    md.lod(1.0)
+    assert float((md.atlas_dyn.data - torch.as_tensor(g["dense_full_atlas_dyn"])).abs().max()) < 2e-6
