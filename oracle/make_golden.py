@@ -282,6 +282,85 @@ def golden_lod(name, H=32, W=48, D=4, hv=5, wv=7, T=3, tile=8, seed=3):
           "| up-sampled", tuple(out["full_atlas_dyn"].shape))
 
 
+def golden_ckpt(name, H=32, W=48, D=4, hv=5, wv=7, T=3, tile=8, seed=5):
+    """SURVEY §8(f) N2, checkpoint format.  A stage-1 state dict as `MPI.MPMesh.state_dict` writes it after
+    `sparsify_faces` (static tiles + ONE frame of dynamic tiles, MPI.py:207-221, 425-439) is loaded by the
+    unmodified reference's `MPMeshVid.init_from_mpi` ("self.has_dyn" branch, MPV.py:241-262: the dynamic frame is
+    replicated over T), run through the pyramid's `lod(0.5)` and `lod(1.0)` (train_3dvid.py:263-264), rendered
+    through the eval branch of `forward` after each, saved with `state_dict()` and loaded again.  The static-only
+    branch (MPV.py:264-288: the static MPI becomes the dynamic part) is rendered as well.  `lod(0.5)` runs under
+    the same pinned-torchvision `Resize` default as golden_lod."""
+    import MPV  # reference
+    import torchvision
+    real_resize = torchvision.transforms.Resize
+
+    class PinnedResize(real_resize):
+        def __init__(self, size, *a, **k):
+            k.setdefault("antialias", False)
+            super().__init__(size, *a, **k)
+
+    st = MO.sparse_state(H, W, D, hv, wv, 1, 1.0, 10.0, tile=tile, occupancy=0.8, dyn_frac=0.5, h_scale=1.3,
+                         w_scale=1.3, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    grid = lambda a: (int(a.shape[-2] // tile), int(a.shape[-1] // tile))
+    stage1 = {"_verts": st.verts, "ref_extrin": st.ref_extrin, "ref_intrin": st.ref_intrin, "planedepth": st.planedepth,
+              "uvs": st.uvs, "atlas": st.atlas, "uvfaces": st.uvfaces, "faces": st.faces, "self.is_sparse": True,
+              "self.atlas_full_w": int(st.atlas.shape[-1]), "self.atlas_full_h": int(st.atlas.shape[-2]),
+              "self.atlas_grid_h": grid(st.atlas)[0], "self.atlas_grid_w": grid(st.atlas)[1],
+              "self.has_dyn": True, "uvs_dyn": st.uvs_dyn, "atlas_dyn": st.atlas_dyn, "uvfaces_dyn": st.uvfaces_dyn,
+              "faces_dyn": st.faces_dyn, "self.atlas_full_dyn_w": int(st.atlas_dyn.shape[-1]),
+              "self.atlas_full_dyn_h": int(st.atlas_dyn.shape[-2]), "self.atlas_grid_dyn_h": grid(st.atlas_dyn)[0],
+              "self.atlas_grid_dyn_w": grid(st.atlas_dyn)[1]}
+    args = ref_env.make_args(mpi_d=D, mpi_h_verts=hv, mpi_w_verts=wv, atlas_grid_h=2, mpv_frm_num=T, mpi_h_scale=1.3,
+                             mpi_w_scale=1.3, add_intrin_noise=False)
+    f = 0.8 * W
+    new_model = lambda: MPV.MPMeshVid(args, H, W, np.eye(4, dtype=np.float32),
+                                      np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32), 1.0, 10.0)
+    copy = lambda d: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in d.items()}
+    torch.manual_seed(seed)
+    m = new_model()
+    m.init_from_mpi(copy(stage1))
+    noise = 0.3 * torch.randn(m.atlas_dyn.shape, generator=g)
+    m.atlas_dyn.data = m.atlas_dyn.data.clone() + noise           # un-alias the T expanded frames, make them differ
+    ext, intr = _view(seed, H, W)
+    m.eval()
+    with torch.no_grad():
+        rgb_full, _ = m(H, W, ext, intr, ts=[0, T - 1])
+    torchvision.transforms.Resize = PinnedResize
+    try:
+        m.lod(0.5)
+    finally:
+        torchvision.transforms.Resize = real_resize
+    with torch.no_grad():
+        rgb_half, _ = m(H, W, ext, intr, ts=[T - 1, 1])
+    m.lod(1.0)
+    with torch.no_grad():
+        rgb_up, _ = m(H, W, ext, intr, ts=[1])
+    sd = m.state_dict()
+    m2 = new_model()
+    m2.init_from_mpi(copy(sd))
+    m2.eval()
+    with torch.no_grad():
+        rgb_again, _ = m2(H, W, ext, intr, ts=[1])
+    assert torch.equal(rgb_again, rgb_up)
+    # static-only checkpoint (no "self.has_dyn"): the static MPI is loaded as the dynamic part
+    static_only = {k: v for k, v in stage1.items() if "dyn" not in k}
+    m3 = new_model()
+    m3.init_from_mpi(copy(static_only))
+    m3.eval()
+    with torch.no_grad():
+        rgb_static, _ = m3(H, W, ext, intr, ts=[0, T - 1])
+    sd3 = m3.state_dict()
+    key = lambda k: k.replace("self.", "self_")
+    out = {"stage1_" + key(k): v for k, v in stage1.items()}
+    out.update({"sd_" + key(k): v for k, v in sd.items()})
+    out.update({"sd3_" + key(k): v for k, v in sd3.items()})
+    out.update(H=H, W=W, T=T, D=D, hv=hv, wv=wv, tar_extrin=ext, tar_intrin=intr, noise=noise, rgb_full=rgb_full,
+               rgb_half=rgb_half, rgb_up=rgb_up, rgb_static=rgb_static)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(out))
+    print(name, "keys", sorted(sd.keys()), "rgb", tuple(rgb_half.shape), float(rgb_half.mean()), float(rgb_static.mean()))
+
+
 def main():
     assert ref_env.reference_available(), "needs /root/reference"
     ref_env.enable()
@@ -289,6 +368,7 @@ def main():
     golden_pointwise("pointwise")
     golden_nnerr("nnerr")
     golden_lod("lod")
+    golden_ckpt("ckpt")
     golden_render("render_dense", "dense", seed=0)
     golden_render("render_sparse", "sparse", seed=1, D=6, hv=6, wv=9, T=2)
     golden_step("step_dense_refcfg", "dense", LOSS_CFG_REF, seed=2)

@@ -78,3 +78,37 @@ def test_sharded_scale_invariant_matches_direct():
         total = sum(ops.frame_sum(res[b[r]:b[r + 1]].contiguous()) for r in range(world))
         got = float(ops.scale_invariant_presum(rgb, T, total.contiguous(), F_))
         assert abs(got - direct) < 2e-6 * abs(direct), (world, got, direct)
+
+
+def test_checkpoint_load_lod_render_matches_reference():
+    """N2 + N1 end to end through the C ABI: the unmodified reference loaded a stage-1 checkpoint with
+    `init_from_mpi`, rendered frames through the eval branch of `forward`, applied `lod(0.5)` / `lod(1.0)` and
+    rendered again, and loaded the static-only branch (oracle/make_golden.py::golden_ckpt); the same calls on
+    the CUDA path give the same frames (1e-4 relative)."""
+    from util import ckpt_dict, ckpt_model, relerr
+    g = load_golden("ckpt")
+    dev = torch.device("cuda:0")
+    H, W, T = int(g["H"]), int(g["W"]), int(g["T"])
+    ext, intr = torch.as_tensor(g["tar_extrin"]).to(dev), torch.as_tensor(g["tar_intrin"]).to(dev)
+    m = ckpt_model(g, dev)
+    m.init_from_mpi(ckpt_dict(g, "stage1_"))
+    m.atlas_dyn.data = m.atlas_dyn.data + torch.as_tensor(g["noise"]).to(dev)
+    m.eval()
+    with torch.no_grad():
+        rgb, _ = m(H, W, ext, intr, ts=[0, T - 1])
+        assert relerr(rgb.cpu(), g["rgb_full"]) < 1e-4
+        m.lod(0.5)
+        rgb, _ = m(H, W, ext, intr, ts=[T - 1, 1])
+        assert relerr(rgb.cpu(), g["rgb_half"]) < 1e-4
+        m.lod(1.0)
+        rgb, _ = m(H, W, ext, intr, ts=[1])
+        assert relerr(rgb.cpu(), g["rgb_up"]) < 1e-4
+        m2 = ckpt_model(g, dev)
+        m2.init_from_mpi(m.state_dict())
+        m2.eval()
+        assert torch.equal(m2(H, W, ext, intr, ts=[1])[0], rgb)
+        m3 = ckpt_model(g, dev)
+        m3.init_from_mpi({k: v for k, v in ckpt_dict(g, "stage1_").items() if "dyn" not in k})
+        m3.eval()
+        rgb, _ = m3(H, W, ext, intr, ts=[0, T - 1])
+        assert relerr(rgb.cpu(), g["rgb_static"]) < 1e-4

@@ -180,3 +180,36 @@ def test_lod_matches_reference():
     assert float((md.atlas_dyn.data - torch.as_tensor(g["dense_half_atlas_dyn"])).abs().max()) < 2e-6
     md.lod(1.0)
     assert float((md.atlas_dyn.data - torch.as_tensor(g["dense_full_atlas_dyn"])).abs().max()) < 2e-6
+
+
+def test_checkpoint_format_matches_reference():
+    """a stage-1 checkpoint goes through `init_from_mpi` -> `lod(0.5)` -> `lod(1.0)` ->
+    `state_dict()` exactly as in the unmodified reference (oracle/make_golden.py::golden_ckpt): same keys,
+    same scalars, same tensors (the atlases are stored in the reference's logical NCHW shape whatever the
+    memory format), and the static-only branch of `init_from_mpi`."""
+    from util import ckpt_dict, ckpt_model, load_golden
+    g = load_golden("ckpt")
+    m = ckpt_model(g, torch.device("cpu"))
+    m.init_from_mpi(ckpt_dict(g, "stage1_"))
+    assert m.atlas_dyn.shape[0] == int(g["T"]) and m.frm_num == int(g["T"])
+    m.atlas_dyn.data = m.atlas_dyn.data + torch.as_tensor(g["noise"])
+    m.lod(0.5)
+    m.lod(1.0)
+    sd, ref = m.state_dict(), ckpt_dict(g, "sd_")
+    assert set(sd.keys()) == set(ref.keys())
+    for k, v in ref.items():
+        if torch.is_tensor(v):
+            assert tuple(sd[k].shape) == tuple(v.shape), k
+            assert float((sd[k].double() - v.double()).abs().max()) < 2e-6, k
+        else:
+            assert sd[k] == v, k
+    m3 = ckpt_model(g, torch.device("cpu"))
+    m3.init_from_mpi({k: v for k, v in ckpt_dict(g, "stage1_").items() if "dyn" not in k})
+    sd3, ref3 = m3.state_dict(), ckpt_dict(g, "sd3_")
+    assert set(sd3.keys()) == set(ref3.keys())
+    for k, v in ref3.items():
+        if torch.is_tensor(v):
+            assert tuple(sd3[k].shape) == tuple(v.shape), k
+            assert torch.allclose(sd3[k].double(), v.double(), rtol=0, atol=1e-7), k
+        else:
+            assert sd3[k] == v, k
