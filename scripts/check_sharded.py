@@ -33,7 +33,18 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    H, W, D, T, F = 46, 83, 8, 7, 13
+    ok = True
+    # ragged blocks (T=7, odd number of patch rows: list all-gather / all-reduce of the NN map) and equal blocks
+    # (T=8, patch rows divisible by the world size up to 4: the in-place all_gather_into_tensor exchanges)
+    for H, W, D, T, F in ((46, 83, 8, 7, 13), (43, 83, 8, 8, 13)):
+        ok &= run_case(H, W, D, T, F, rank, world, dev)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag) == 1 else 1)
+
+
+def run_case(H, W, D, T, F, rank, world, dev):
     st = MO.sparse_state(H, W, D, 6, 9, T, 1.0, 10.0, tile=6, occupancy=0.7, dyn_frac=0.5, h_scale=1.2, w_scale=1.2, seed=4)
     ext = torch.eye(4)[None]
     ext[0, 0, 3] = 0.05
@@ -67,12 +78,9 @@ def main():
             nn_eq = bool(torch.equal(nn_sh, s1._buf["nn"]))
             good = dp < 2e-5 and ds < 2e-5 and dl < 1e-5 and nn_eq
             ok &= good
-            print(f"[{variant}] world={world}: max|d atlas_dyn|={dp:.2e} max|d atlas|={ds:.2e} rel d loss={dl:.2e} "
+            print(f"[{variant}] T={T} H={H} world={world}: max|d atlas_dyn|={dp:.2e} max|d atlas|={ds:.2e} rel d loss={dl:.2e} "
                   f"nn identical={nn_eq} -> {'OK' if good else 'MISMATCH'}", flush=True)
-    flag = torch.tensor([1 if ok else 0], device=dev)
-    dist.broadcast(flag, 0)
-    dist.destroy_process_group()
-    sys.exit(0 if int(flag) == 1 else 1)
+    return ok
 
 
 if __name__ == "__main__":

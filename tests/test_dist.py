@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from videoloop3d_b200.train_step import owned_frame_ranges, partition
+from videoloop3d_b200.train_step import exchange_row_bands, gather_frames, owned_frame_ranges, partition, rows_equal
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -54,7 +54,29 @@ def _worker(rank, world, port, q):
         target = torch.arange(F_ * 3 * h * w, dtype=torch.float32).reshape(F_, 3, h, w) / 7
         rsum = target[fb[rank]:fb[rank + 1]].sum(0)
         dist.all_reduce(rsum)
-        ok = torch.equal(video[:T], truth) and torch.equal(video[T:], truth[:pad])
+        # the step's own exchange helpers (in-place all_gather_into_tensor for equal blocks, list all-gather /
+        # band sum for ragged ones), synchronous and asynchronous
+        ok = True
+        for T2, ho2 in ((6, 4), (7, 5)):
+            b2 = partition(T2, world)
+            vid = torch.full((T2 + pad, 3, h, w), -1.0)
+            tr = torch.arange(T2 * 3 * h * w, dtype=torch.float32).reshape(T2, 3, h, w)
+            vid[b2[rank]:b2[rank + 1]] = tr[b2[rank]:b2[rank + 1]]
+            if T2 % world == 0:                    # (gloo has no ragged list all-gather; NCCL does: check_sharded.py)
+                for use_async in (False, True):
+                    v = vid.clone()
+                    work = gather_frames(v, b2, rank, T2, None, async_op=use_async)
+                    if use_async:
+                        work.wait()
+                    ok &= torch.equal(v[:T2], tr)
+            rows2 = partition(ho2, world)
+            nn2 = torch.zeros(ho2, 2, 3, dtype=torch.int32)
+            if rows_equal(rows2):
+                nn2.fill_(-5)                      # stale contents of the other bands must be overwritten
+            nn2[rows2[rank]:rows2[rank + 1]] = 11 + rank
+            exchange_row_bands(nn2, rows2, rank, None)
+            ok &= all(int(nn2[r, 1, 2]) == 11 + (0 if r < rows2[1] else 1) for r in range(ho2))
+        ok &= torch.equal(video[:T], truth) and torch.equal(video[T:], truth[:pad])
         ok &= all(int(nn[r, 0, 0]) == 7 + (0 if r < rows[1] else 1) for r in range(ho))
         ok &= sums.tolist() == [2.0, 4.0, 6.0, 8.0, 3.0]
         ok &= torch.allclose(rsum, target.sum(0), rtol=1e-6)

@@ -107,6 +107,33 @@ def owned_frame_ranges(bounds, rank, T, pad):
     return out
 
 
+def gather_frames(video, bounds, rank, T, group, async_op=False):
+    """All-gather of the frame blocks of `video[:T]` (rank r holds video[bounds[r]:bounds[r+1]] and receives the
+    rest in place).  Equal blocks: one in-place `all_gather_into_tensor`; ragged blocks: list all-gather.
+    Returns the work handle when `async_op`."""
+    import torch.distributed as dist
+    t0, t1 = bounds[rank], bounds[rank + 1]
+    if len({b - a for a, b in zip(bounds[:-1], bounds[1:])}) == 1:
+        return dist.all_gather_into_tensor(video[:T], video[t0:t1], group=group, async_op=async_op)
+    parts = [video[a:b] for a, b in zip(bounds[:-1], bounds[1:])]
+    return dist.all_gather(parts, video[t0:t1].clone(), group=group, async_op=async_op)
+
+
+def exchange_row_bands(nn, rows, rank, group):
+    """Every rank filled the rows [rows[rank], rows[rank+1]) of the NN index map `nn` (ho, wo, n1); afterwards
+    all ranks hold the whole map.  Equal bands: in-place all-gather; ragged bands: the caller zeroed the rest
+    and the disjoint bands are summed."""
+    import torch.distributed as dist
+    if rows_equal(rows):
+        dist.all_gather_into_tensor(nn, nn[rows[rank]:rows[rank + 1]], group=group)
+    else:
+        dist.all_reduce(nn, group=group)
+
+
+def rows_equal(rows):
+    return len({b - a for a, b in zip(rows[:-1], rows[1:])}) == 1
+
+
 class FusedLoopStep:
     """render + looping loss + backward + Adam for one (view, patch) item, fused and sync-free.
 
@@ -241,12 +268,7 @@ class FusedLoopStep:
             # asynchronous: the target-frame sums of the scale-invariant gain (which do not need the rendered video)
             # run on the compute stream while NVLink moves the frames; waited for right before the gain is evaluated
             with self._timed("allgather_rgb_issue"):
-                sizes = {b - a for a, b in zip(self.bounds[:-1], self.bounds[1:])}
-                if len(sizes) == 1:
-                    gather = dist.all_gather_into_tensor(rgb_pad[:T], rgb_pad[t0:t1], group=self.group, async_op=True)
-                else:
-                    parts = [rgb_pad[a:b] for a, b in zip(self.bounds[:-1], self.bounds[1:])]
-                    gather = dist.all_gather(parts, rgb_pad[t0:t1].clone(), group=self.group, async_op=True)
+                gather = gather_frames(rgb_pad, self.bounds, self.rank, T, self.group, async_op=True)
 
         def finish_gather():
             nonlocal gather
@@ -288,17 +310,13 @@ class FusedLoopStep:
             # patch positions are independent (utils_vid.py:211-215): each rank searches a band of patch rows,
             # then the int32 index map is summed across ranks (disjoint rows, zeros elsewhere)
             rows = partition(desc.ho, self.world)
-            equal_bands = len({b - a for a, b in zip(rows[:-1], rows[1:])}) == 1
-            if not equal_bands:
+            if not rows_equal(rows):
                 nn.zero_()
             with self._timed("patchnn_search"):
                 ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn, rows=(rows[self.rank], rows[self.rank + 1]),
                                    scaled_ws=x_scaled)
             with self._timed("exchange_nn"):
-                if equal_bands:
-                    dist.all_gather_into_tensor(nn, nn[rows[self.rank]:rows[self.rank + 1]], group=self.group)
-                else:
-                    dist.all_reduce(nn, group=self.group)            # disjoint rows, zeros elsewhere
+                exchange_row_bands(nn, rows, self.rank, self.group)
         grad_rgb = self._get("grad_rgb", (T + pad, 3, h, w), torch.float32)
         n_part = ops._lib.load().vl3d_vote_partials(T + pad, h, w)
         vote_part = self._get("vote_part", (n_part,), torch.float64)
