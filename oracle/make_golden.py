@@ -361,6 +361,40 @@ def golden_ckpt(name, H=32, W=48, D=4, hv=5, wv=7, T=3, tile=8, seed=5):
     print(name, "keys", sorted(sd.keys()), "rgb", tuple(rgb_half.shape), float(rgb_half.mean()), float(rgb_static.mean()))
 
 
+def golden_dataset(name, V=2, F=5, h_raw=20, w_raw=30, seed=7):
+    """the unmodified reference's `MVVidPatchDataset` (train_3dvid.py:22-66) and
+    `generate_patchinfo` (utils.py:115-134): every item of a small two-view capture, (a) resized + padded
+    (16x24 target, 8x12 patches on a 6x8 stride grid) and (b) the small-frame branch (frame smaller than a patch)."""
+    import train_3dvid as T3  # reference
+    rng = np.random.default_rng(seed)
+    videos = [rng.integers(0, 256, (F, h_raw, w_raw, 3), dtype=np.uint8) for _ in range(V)]
+    poses = torch.tensor(rng.normal(size=(V, 3, 4)).astype(np.float32))
+    intr = torch.tensor([[[25., 0, 15.], [0, 25., 10.], [0, 0, 1.]]]).repeat(V, 1, 1)
+    intr[1, 0, 2] += 0.7
+    cfgs = [dict(LOSS_CFG_REF), dict(LOSS_CFG_OTHER)]
+    out = dict(V=V, poses=poses, intrins=intr, **{f"video{i}": v for i, v in enumerate(videos)})
+    for tag, hw, psz, pst in (("a", (16, 24), (8, 12), (6, 8)), ("b", (10, 15), (16, 24), (8, 8)), ("c", (17, 26), (8, 12), (6, 8))):
+        ds = T3.MVVidPatchDataset(hw, videos, psz, pst, poses, intr, loss_configs=cfgs)
+        out.update({f"{tag}_hw": np.array(hw), f"{tag}_patch_size": np.array(psz), f"{tag}_patch_stride": np.array(pst),
+                    f"{tag}_len": len(ds)})
+        for i in range(len(ds)):
+            w0, h0, pose, k, crops, cfg = ds[i]
+            out.update({f"{tag}_{i}_wh": np.array([int(w0), int(h0)]), f"{tag}_{i}_pose": pose, f"{tag}_{i}_intrin": k,
+                        f"{tag}_{i}_crops": crops, f"{tag}_{i}_loss_name": cfg["loss_name"],
+                        f"{tag}_{i}_patch_size": cfg["patch_size"]})
+        if tag != "b":
+            wh, pad = T3.generate_patchinfo(hw[0], hw[1], psz, pst)
+            out.update({f"{tag}_patch_wh_start": wh, f"{tag}_pad_info": np.array(pad)})
+    # what DataLoader(dataset, 1) hands to run_iter for item 0 of (a) (shapes of the batched item)
+    from torch.utils.data import DataLoader
+    ds = T3.MVVidPatchDataset((16, 24), videos, (8, 12), (6, 8), poses, intr, loss_configs=cfgs)
+    b = next(iter(DataLoader(ds, 1, shuffle=False)))
+    out.update(batch_shapes=np.array([len(b[0].shape), len(b[1].shape), *b[2].shape, *b[3].shape, *b[4].shape]),
+               batch_cfg_kinds=np.array([f"{k}:{'tensor' if torch.is_tensor(v) else 'list'}" for k, v in b[5].items()]))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(out))
+    print(name, {t: int(out[t + "_len"]) for t in "abc"}, out["batch_cfg_kinds"])
+
+
 def main():
     assert ref_env.reference_available(), "needs /root/reference"
     ref_env.enable()
@@ -369,6 +403,7 @@ def main():
     golden_nnerr("nnerr")
     golden_lod("lod")
     golden_ckpt("ckpt")
+    golden_dataset("dataset")
     golden_render("render_dense", "dense", seed=0)
     golden_render("render_sparse", "sparse", seed=1, D=6, hv=6, wv=9, T=2)
     golden_step("step_dense_refcfg", "dense", LOSS_CFG_REF, seed=2)

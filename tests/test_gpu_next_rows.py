@@ -112,3 +112,61 @@ def test_checkpoint_load_lod_render_matches_reference():
         m3.eval()
         rgb, _ = m3(H, W, ext, intr, ts=[0, T - 1])
         assert relerr(rgb.cpu(), g["rgb_static"]) < 1e-4
+
+
+def test_run_iter_on_dataset_items_matches_reference_step():
+    """S1 + S3 (train_3dvid.py:214-255 fed by MVVidPatchDataset items): `make_run_iter` driven by a batch in the
+    DataLoader format reproduces the unmodified reference's step (golden `step_dense_refcfg`: total loss 1e-4,
+    parameter update in the same direction), and `FusedLoopStep` fed from a GPU-resident dataset (crops are
+    strided views of the resident video) computes the same loss for every item."""
+    from util import cfg_from_golden
+    from test_gpu_parity import model_from_golden
+    from videoloop3d_b200 import FusedLoopStep, MVVidPatchDataset, make_run_iter
+    g = load_golden("step_dense_refcfg")
+    cfg = cfg_from_golden(g)
+    dev = torch.device("cuda:0")
+    kw = dict(rgb_smooth_loss_weight=float(g["rgb_smooth_w"]), a_smooth_loss_weight=float(g["a_smooth_w"]),
+              swd_patcht_size=int(cfg["patcht_size"]), add_intrin_noise=False)
+    m = model_from_golden(g, **kw)
+    H, W = int(g["H"]), int(g["W"])
+    ext = torch.as_tensor(g["tar_extrin"])
+    pose = torch.linalg.inv(ext)[:, :3, :4]                               # run_iter inverts it again (utils.py:211-219)
+    batched = {k: ([v] if isinstance(v, str) else torch.tensor([v])) for k, v in cfg.items()}
+    item = (torch.tensor([0]), torch.tensor([0]), pose, torch.as_tensor(g["tar_intrin"]), torch.as_tensor(g["res"]), batched)
+    opt = m.get_optimizer(step=0)
+    for grp in opt.param_groups:
+        grp["lr"] = float(g["lr"])
+    p0 = m.atlas_dyn.data.clone()
+    loss = make_run_iter(m.args, m, dev)(0, opt, item)
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    d_ours = (m.atlas_dyn.data - p0).cpu().contiguous()
+    d_ref = torch.as_tensor(g["new_atlas_dyn"]) - torch.as_tensor(g["atlas_dyn"])
+    big = torch.as_tensor(g["grad_atlas_dyn"]).abs() > 1e-6              # Adam(eps=6e-8) amplifies noise on ~zero gradients
+    assert float((d_ours[big] - d_ref[big]).abs().max()) < 2e-3 * float(g["lr"])
+    assert int(big.sum()) > 1000
+
+    # GPU-resident dataset -> fused step, crops are views
+    rng = np.random.default_rng(0)
+    F_ = g["res"].shape[1]
+    videos = [rng.integers(0, 256, (F_, 2 * H, 2 * W, 3), dtype=np.uint8)]
+    poses = pose.clone()
+    intr = torch.as_tensor(g["tar_intrin"]).clone()
+    intr[0, 0, 2] += W / 2
+    intr[0, 1, 2] += H / 2
+    plain = {k: v for k, v in cfg.items()}
+    ds = MVVidPatchDataset((2 * H, 2 * W), videos, (H, W), (H, W), poses, intr, loss_configs=[plain], device=dev)
+    assert len(ds) == 4 and ds.videos[0].is_cuda
+    m2 = model_from_golden(g, **kw)
+    step = FusedLoopStep(m2)
+    m3 = model_from_golden(g, **kw)
+    m3.train()
+    for b in ds.batches(shuffle=False):
+        w0, h0, b_pose, b_intr, crops, bcfg = b
+        assert crops.is_cuda and not crops.is_contiguous()
+        from videoloop3d_b200 import pose2extrin_torch
+        b_ext = pose2extrin_torch(b_pose)
+        out = step.step(H, W, b_ext, b_intr, crops, plain, lr=0.0, optimise=False)
+        _, extra = m3(H, W, b_ext.to(dev), b_intr.to(dev), res=crops, losscfg=bcfg)
+        ref = extra["swd"].mean() + extra["rgb_smooth"].mean() * kw["rgb_smooth_loss_weight"] \
+            + extra["a_smooth"].mean() * kw["a_smooth_loss_weight"]
+        assert abs(float(out["loss"]) - float(ref)) < 1e-4 * abs(float(ref))

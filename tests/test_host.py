@@ -213,3 +213,41 @@ def test_checkpoint_format_matches_reference():
             assert torch.allclose(sd3[k].double(), v.double(), rtol=0, atol=1e-7), k
         else:
             assert sd3[k] == v, k
+
+
+def test_dataset_matches_reference():
+    """`MVVidPatchDataset` / `generate_patchinfo` give the unmodified reference's items
+    (train_3dvid.py:22-66, utils.py:115-134; oracle/make_golden.py::golden_dataset): patch origins and order,
+    shifted intrinsics, crops of the resized + padded videos bit for bit, loss config per view — and `batches()`
+    yields what `DataLoader(dataset, 1)` yields."""
+    from util import load_golden
+    from videoloop3d_b200 import MVVidPatchDataset, generate_patchinfo
+    g = load_golden("dataset")
+    V = int(g["V"])
+    videos = [g[f"video{i}"] for i in range(V)]
+    poses, intr = torch.as_tensor(g["poses"]), torch.as_tensor(g["intrins"])
+    cfgs = [dict(loss_name="gpnn_lm", patch_size=5), dict(loss_name="gpnn_lm", patch_size=3)]
+    for tag in "abc":
+        hw, psz, pst = tuple(g[f"{tag}_hw"]), tuple(g[f"{tag}_patch_size"]), tuple(g[f"{tag}_patch_stride"])
+        ds = MVVidPatchDataset(hw, videos, psz, pst, poses, intr, loss_configs=cfgs)
+        assert len(ds) == int(g[f"{tag}_len"])
+        for i in range(len(ds)):
+            w0, h0, pose, k, crops, cfg = ds[i]
+            assert [int(w0), int(h0)] == g[f"{tag}_{i}_wh"].tolist()
+            assert torch.equal(pose, torch.as_tensor(g[f"{tag}_{i}_pose"]))
+            assert torch.equal(k, torch.as_tensor(g[f"{tag}_{i}_intrin"])) and k.dtype == torch.float32
+            assert torch.equal(crops, torch.as_tensor(g[f"{tag}_{i}_crops"]))
+            assert cfg["patch_size"] == int(g[f"{tag}_{i}_patch_size"])
+            cfg["patch_size"] = -1                                        # items own a deep copy of the config
+        assert cfgs[0]["patch_size"] == 5
+        if tag != "b":
+            wh, pad = generate_patchinfo(hw[0], hw[1], psz, pst)
+            assert torch.equal(wh, torch.as_tensor(g[f"{tag}_patch_wh_start"])) and list(pad) == g[f"{tag}_pad_info"].tolist()
+    ds = MVVidPatchDataset((16, 24), videos, (8, 12), (6, 8), poses, intr, loss_configs=cfgs, pin_memory=False)
+    b = next(iter(ds.batches(shuffle=False)))
+    shapes = [b[0].dim(), b[1].dim(), *b[2].shape, *b[3].shape, *b[4].shape]
+    assert shapes == g["batch_shapes"].tolist()
+    assert b[5]["loss_name"] == ["gpnn_lm"] and torch.is_tensor(b[5]["patch_size"]) and int(b[5]["patch_size"][0]) == 5
+    assert b[4].untyped_storage().data_ptr() == ds.videos[0].untyped_storage().data_ptr()     # a view, not a copy
+    seen = sorted((int(x[0]), int(x[1]), float(x[3][0, 0, 2])) for x in ds.batches(shuffle=True, generator=torch.Generator().manual_seed(1)))
+    assert len(seen) == len(ds) and len(set(seen)) > 1

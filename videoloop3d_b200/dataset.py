@@ -1,0 +1,116 @@
+"""The caller side of the stage-2 step: which (view, patch) items exist and what one item is.
+
+Mirrors, with the same names / arguments / return values,
+  generate_patchinfo   utils.py:115-134      patch origins on a stride grid + the right/bottom padding that makes the
+                                             last patch fit
+  MVVidPatchDataset    train_3dvid.py:22-66  item = (w_start, h_start, pose (3,4), intrin shifted to the patch origin
+                                             (utils.py:196-200), crops (F,3,ph,pw) in [0,1], deep copy of the view's
+                                             loss config)
+
+B200 design: the reference keeps the resized fp32 videos in pageable host memory and pays a synchronous
+host-to-device copy of every crop (`datainfo_.to(device)`, train_3dvid.py:215).  Here the videos can live
+  * on the GPU (`device="cuda"`): a whole capture (10 views x 258 frames at 720p = 28.5 GB fp32) fits next to the
+    90 GB model state in the 180 GB of one B200, so an item is a strided VIEW of resident memory — no copy at all;
+  * in pinned host memory (`pin_memory=True`): the crop copy is an asynchronous DMA that `FusedLoopStep.step(...,
+    res_ready=event)` overlaps with the render (bench.py's e2e arm).
+`batches()` yields exactly what `DataLoader(dataset, 1, shuffle=True)` yields (batch dimension of 1, loss config
+values batched the way `default_collate` batches them) without worker processes or collate copies.
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+
+import numpy as np
+import torch
+import torch.nn.functional as torchf
+
+from .mpv import get_new_intrin
+
+
+def generate_patchinfo(H_, W_, patch_size_, patch_stride_):
+    """utils.py:115-134.  Returns (patch_wh_start (N,2) int64 rows of (w_start, h_start), pad_info [0,Wpad,0,Hpad])."""
+    ph, pw = patch_size_
+    sh, sw = patch_stride_
+    h0 = np.arange(0, H_ - ph + sh, sh)
+    w0 = np.arange(0, W_ - pw + sw, sw)
+    # reference order: w varies slowest (np.meshgrid(h, w) is indexed [w, h]), columns swapped to (w, h)
+    wh = np.stack(np.meshgrid(h0, w0)[::-1], axis=-1).reshape(-1, 2)
+    H_pad = int(h0.max() + ph - H_)
+    W_pad = int(w0.max() + pw - W_)
+    assert sh > H_pad >= 0 and sw > W_pad >= 0, "bug occurs!"
+    return torch.tensor(wh), [0, W_pad, 0, H_pad]
+
+
+def _resize_frames(video, w, h):
+    """cv2.resize(img, (w, h)) per frame (train_3dvid.py:52), skipped when the size already matches."""
+    video = np.asarray(video)
+    if video.shape[1] == h and video.shape[2] == w:
+        return video
+    try:
+        import cv2
+    except ImportError as e:  # pragma: no cover
+        raise RuntimeError("MVVidPatchDataset needs OpenCV to resize the input videos (as the reference does)") from e
+    return np.array([cv2.resize(img, (w, h)) for img in video])
+
+
+class MVVidPatchDataset(torch.utils.data.Dataset):
+    """train_3dvid.py:22-66.  `videos`: list of V arrays (F,H,W,3) uint8; `poses` (V,3,4+), `intrins` (V,3,3) at the
+    raw resolution; `loss_configs`: one dict per view.  Extra (B200) arguments: `device` — where the padded fp32
+    videos are kept (None = host); `pin_memory` — page-lock the host copies."""
+
+    def __init__(self, resize_hw, videos, patch_size, patch_stride, poses, intrins, loss_configs=None, device=None,
+                 pin_memory=False):
+        super().__init__()
+        h_raw, w_raw, _ = videos[0][0].shape[-3:]
+        self.h, self.w = resize_hw
+        self.v = len(videos)
+        self.poses = poses.clone().cpu()
+        self.intrins = intrins.clone().cpu()
+        self.intrins[:, :2] *= torch.tensor([self.w / w_raw, self.h / h_raw]).reshape(1, 2, 1).type_as(intrins)
+        self.patch_h_size, self.patch_w_size = patch_size
+        if self.h * self.w < self.patch_h_size * self.patch_w_size:
+            patch_wh_start = torch.tensor([[0, 0]]).long().reshape(-1, 2)
+            pad_info = [0, 0, 0, 0]
+            self.patch_h_size, self.patch_w_size = self.h, self.w
+        else:
+            patch_wh_start, pad_info = generate_patchinfo(self.h, self.w, patch_size, patch_stride)
+        n_patch = patch_wh_start.shape[0]
+        self.patch_wh_start = patch_wh_start[None].expand(self.v, -1, 2).reshape(-1, 2).cpu()
+        self.view_index = np.repeat(np.arange(self.v), n_patch).tolist()
+        self.loss_configs = loss_configs
+        assert len(self.loss_configs) == self.v
+        self.device = torch.device(device) if device is not None else None
+        self.videos = []
+        for video in videos:
+            vid = torch.tensor(_resize_frames(video, self.w, self.h), device='cpu')
+            vid = (vid / 255).permute(0, 3, 1, 2)
+            vid = torchf.pad(vid, pad_info).contiguous()
+            if self.device is not None and self.device.type != "cpu":
+                vid = vid.to(self.device)
+            elif pin_memory:
+                vid = vid.pin_memory()
+            self.videos.append(vid)
+        self.pad_info = pad_info
+
+    def __len__(self):
+        return len(self.patch_wh_start)
+
+    def __getitem__(self, item):
+        w_start, h_start = self.patch_wh_start[item]
+        view_idx = self.view_index[item]
+        pose = self.poses[view_idx]
+        intrin = get_new_intrin(self.intrins[view_idx], h_start, w_start).float()
+        crops = self.videos[view_idx][..., h_start: h_start + self.patch_h_size, w_start: w_start + self.patch_w_size]
+        return w_start, h_start, pose, intrin, crops, deepcopy(self.loss_configs[view_idx])
+
+    def batches(self, shuffle=True, generator=None):
+        """What `DataLoader(self, 1, shuffle=shuffle)` yields, item by item: every tensor with a leading batch
+        dimension of 1 (the crops stay a view of the resident video), numbers of the loss config as 1-element
+        tensors and strings as 1-element lists (`MPMeshVid.forward` un-batches them, MPV.py:494-497)."""
+        n = len(self)
+        order = torch.randperm(n, generator=generator).tolist() if shuffle else range(n)
+        for i in order:
+            w_start, h_start, pose, intrin, crops, cfg = self[i]
+            cfg = {k: (torch.tensor([v]) if isinstance(v, (int, float)) and not isinstance(v, bool) else [v])
+                   for k, v in cfg.items()}
+            yield w_start[None], h_start[None], pose[None], intrin[None], crops[None], cfg
