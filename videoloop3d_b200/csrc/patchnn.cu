@@ -591,6 +591,97 @@ __global__ void __launch_bounds__(VOTE_THREADS) vote_loss_kernel(const __grid_co
     }
 }
 
+// Same computation with the gathers batched: the loop nest above waits twice per covering patch (NN index, then
+// the three target texels it points to: 75 % of its stall samples are on those two scoreboards, issue 36 %).  Here
+// the covering patches of one patch row — at most NX columns x NK temporal offsets, compile-time bounds — are
+// handled together: all their NN indices are requested first (predicated loads, nothing is fetched for
+// combinations that do not exist), then all 3*NX*NK target texels, then the sums.  Up to 9 / 27 loads in flight
+// per thread instead of 1 / 3.  The host picks the instantiation from ceil(p/s) and ceil(pt/st).
+template <int NY, int NX, int NK>
+__global__ void __launch_bounds__(VOTE_THREADS) vote_loss_batched_kernel(const __grid_constant__ VoteParams P) {
+    const vl3d_loss_desc& L = P.d;
+    const int tf = P.f0 + blockIdx.x;
+    const int px = blockIdx.y * 32 + (threadIdx.x & 31);
+    const int py = blockIdx.z * 8 + (threadIdx.x >> 5);
+    float lsum = 0.f;
+    if (px < P.Wfull && py < P.Hfull) {
+        const bool inside = px < L.w && py < L.h && tf < L.t;
+        float g[3] = {0.f, 0.f, 0.f};
+        if (inside) {
+            const int p = L.p, s = L.s, pt = L.pt, st = L.st;
+            int iy0 = (py - p + s) / s; if (py - p + 1 <= 0) iy0 = 0;
+            int ix0 = (px - p + s) / s; if (px - p + 1 <= 0) ix0 = 0;
+            int k0 = (tf - pt + st) / st; if (tf - pt + 1 <= 0) k0 = 0;
+            const int iy1 = min(py / s, L.ho - 1), ix1 = min(px / s, L.wo - 1), k1 = min(tf / st, L.n1 - 1);
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+            const int cnt = max(iy1 - iy0 + 1, 0) * max(ix1 - ix0 + 1, 0) * max(k1 - k0 + 1, 0);
+            const float* yb = P.y + (size_t)py * L.y_sr + px;
+            const int* nn0 = P.nn + ((size_t)iy0 * L.wo + ix0) * L.n1 + k0;
+            const size_t nn_row = (size_t)L.wo * L.n1;
+#pragma unroll
+            for (int jy = 0; jy < NY; ++jy) {
+                const bool vy = iy0 + jy <= iy1;
+                int fr[NX][NK];
+#pragma unroll
+                for (int jx = 0; jx < NX; ++jx)
+#pragma unroll
+                    for (int jk = 0; jk < NK; ++jk) {
+                        const bool ok = vy && ix0 + jx <= ix1 && k0 + jk <= k1;
+                        int nnv = 0;
+                        if (ok) nnv = __ldg(nn0 + jy * nn_row + jx * L.n1 + jk);
+                        fr[jx][jk] = ok ? nnv * st + (tf - (k0 + jk) * st) : -1;
+                    }
+                float a0[NX][NK], a1[NX][NK], a2[NX][NK];
+#pragma unroll
+                for (int jx = 0; jx < NX; ++jx)
+#pragma unroll
+                    for (int jk = 0; jk < NK; ++jk) {
+                        a0[jx][jk] = a1[jx][jk] = a2[jx][jk] = 0.f;
+                        if (fr[jx][jk] >= 0) {
+                            const float* src = yb + (size_t)fr[jx][jk] * L.y_sf;
+                            a0[jx][jk] = __ldg(src); a1[jx][jk] = __ldg(src + L.y_sc); a2[jx][jk] = __ldg(src + 2 * L.y_sc);
+                        }
+                    }
+#pragma unroll
+                for (int jx = 0; jx < NX; ++jx)
+#pragma unroll
+                    for (int jk = 0; jk < NK; ++jk) { v0 += a0[jx][jk]; v1 += a1[jx][jk]; v2 += a2[jx][jk]; }
+            }
+            const float wgt = fmaxf((float)cnt, 1e-10f);                       // clamp_min(1e-10) (utils_vid.py:228)
+            const float m[3] = {v0 / wgt, v1 / wgt, v2 / wgt};
+            const float xsc = P.xscale ? __ldg(P.xscale) : 1.f;
+            const float n_inv = 1.f / ((float)L.t * (float)L.h * (float)L.w * 3.f);
+            const size_t fit_plane = (size_t)L.h * L.w;
+            const size_t fit_pix = (size_t)py * L.w + px;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float xv = __ldg(P.x + (size_t)tf * L.x_sf + (size_t)c * L.x_sc + (size_t)py * L.x_sr + px) * xsc;
+                float val, der;
+                robust(xv - m[c], P.rou_kind, P.rou, P.scaling, val, der);
+                lsum += val;
+                g[c] = P.gcoef * xsc * der * n_inv;
+                if (P.y2x) P.y2x[((size_t)c * L.t + tf) * fit_plane + fit_pix] = m[c];
+            }
+            if (P.weight) P.weight[(size_t)tf * fit_plane + fit_pix] = wgt;
+        }
+        if (P.grad && tf < P.Tx_full) {
+            const size_t plane = (size_t)P.Hfull * P.Wfull;
+            float* gp = P.grad + (size_t)tf * 3 * plane + (size_t)py * P.Wfull + px;
+            gp[0] = g[0]; gp[plane] = g[1]; gp[2 * plane] = g[2];
+        }
+    }
+    __shared__ float s_part[VOTE_THREADS / 32];
+    lsum = warp_sum(lsum);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < VOTE_THREADS / 32; ++i) acc += (double)s_part[i];
+        P.partials[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = acc;
+    }
+}
+
 __global__ void __launch_bounds__(1024) finalize_mean_kernel(const double* partials, int n, double denom, float* out) {
     __shared__ double s[32];
     double acc = 0.0;
@@ -905,7 +996,13 @@ extern "C" int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const 
     P.Tx_full = Tx_full; P.Hfull = Hfull; P.Wfull = Wfull; P.f0 = frame_begin;
     P.y2x = y2x_out; P.weight = weight_out; P.grad = grad_out; P.partials = partials; P.loss = loss_out;
     cudaStream_t st = (cudaStream_t)stream;
-    vote_loss_kernel<<<grid, VOTE_THREADS, 0, st>>>(P);
+    // covering patches per axis: at most ceil(p/s) (space) and ceil(pt/st) (time)
+    const int ms = (desc->p + desc->s - 1) / desc->s, mt = (desc->pt + desc->st - 1) / desc->st;
+    const char* v1 = getenv("VL3D_VOTE_V1");                         // tuning aid: the one-gather-at-a-time kernel
+    const bool batched = !(v1 && atoi(v1) != 0);
+    if (batched && ms <= 2 && mt <= 3) vote_loss_batched_kernel<2, 2, 3><<<grid, VOTE_THREADS, 0, st>>>(P);
+    else if (batched && ms <= 3 && mt <= 3) vote_loss_batched_kernel<3, 3, 3><<<grid, VOTE_THREADS, 0, st>>>(P);
+    else vote_loss_kernel<<<grid, VOTE_THREADS, 0, st>>>(P);
     if (int e = check_launch("vote_loss")) return e;
     const double denom = (double)desc->t * desc->h * desc->w * 3.0;
     finalize_mean_kernel<<<1, 1024, 0, st>>>(partials, nblocks, denom, loss_out);

@@ -207,28 +207,34 @@ __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __g
                 __syncthreads();
                 // diagonal sums D[il][jl] = sum_dt G[il*st+dt][jl*st+dt] / d, built in registers and written over G
                 constexpr int DMAX = 32;                            // entries per thread per pass
+                // entry id = base + u*nthreads + tid <-> (il, jl) = divmod(id, cj), advanced incrementally: a step of
+                // nthreads entries is (dq rows, dr columns) with one carry (an integer division per entry cost more
+                // than the three shared-memory reads it addresses)
+                const int dq_step = nthreads / cj, dr_step = nthreads - dq_step * cj;   // divmod(nthreads, cj)
+                int il_b = tid / cj, jl_b = tid - il_b * cj;                             // divmod(tid, cj)
                 for (int base = 0; base < L.n1 * cj; base += nthreads * DMAX) {
                     float dv[DMAX];
+                    int il = il_b, jl = jl_b;
 #pragma unroll
                     for (int u = 0; u < DMAX; ++u) {
-                        const int id = base + u * nthreads + tid;
                         float sum = 0.f;
-                        if (id < L.n1 * cj) {
-                            const int il = id / cj, jl = id - il * cj;
-                            const int gx = il * st, gy = jl * st;
-                            for (int dt = 0; dt < pt; ++dt) sum += Gs[(gx + dt) * (CF + 1) + gy + dt];
+                        if (il < L.n1) {
+                            const float* gp = Gs + (il * st) * (CF + 1) + jl * st;
+                            for (int dt = 0; dt < pt; ++dt) sum += gp[dt * (CF + 2)];
                         }
                         dv[u] = sum * inv_d;
+                        jl += dr_step; il += dq_step;
+                        if (jl >= cj) { jl -= cj; ++il; }
                     }
                     __syncthreads();                                // every G entry of this pass has been read
+                    il = il_b; jl = jl_b;
 #pragma unroll
                     for (int u = 0; u < DMAX; ++u) {
-                        const int id = base + u * nthreads + tid;
-                        if (id < L.n1 * cj) {
-                            const int il = id / cj, jl = id - il * cj;
-                            Gs[(size_t)il * (CF + 1) + jl] = dv[u];
-                        }
+                        if (il < L.n1) Gs[il * (CF + 1) + jl] = dv[u];
+                        jl += dr_step; il += dq_step;
+                        if (jl >= cj) { jl -= cj; ++il; }
                     }
+                    il_b = il; jl_b = jl;
                     __syncthreads();
                 }
                 float* Ds = Gs;
