@@ -66,7 +66,8 @@ class Vl3dError(RuntimeError):
 
 
 def lib_path():
-    return _build.LIB_PATH
+    """In-tree library; VL3D_LIB=/path/to/other.so loads a different build of the same ABI (A/B measurements)."""
+    return os.environ.get("VL3D_LIB") or _build.LIB_PATH
 
 
 def load():

@@ -399,12 +399,18 @@ __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip_kernel(const __gr
                         Gs[(ta + NTA * i) * (CF + 1) + tb + NTB * j] = gsum;
                     }
                 __syncthreads();
-                for (int id = tid; id < L.n1 * cj; id += nthreads) {
-                    const int il = id / cj, jl = id - il * cj;
-                    const int gx = il * st, gy = jl * st;
-                    float sum = 0.f;
-                    for (int dt = 0; dt < pt; ++dt) sum += Gs[(gx + dt) * (CF + 1) + gy + dt];
-                    Ds[(size_t)il * (CF + 1) + jl] = sum * inv_d;
+                {   // entries id = tid, tid + nthreads, ... <-> (il, jl) = divmod(id, cj), advanced incrementally (a step
+                    // of nthreads entries is dq rows + dr columns with one carry) instead of a division per entry
+                    const int dq = nthreads / cj, dr = nthreads - dq * cj;
+                    int il = tid / cj, jl = tid - il * cj;
+                    while (il < L.n1) {
+                        const float* gp = Gs + (il * st) * (CF + 1) + jl * st;
+                        float sum = 0.f;
+                        for (int dt = 0; dt < pt; ++dt) sum += gp[dt * (CF + 2)];
+                        Ds[il * (CF + 1) + jl] = sum * inv_d;
+                        jl += dr; il += dq;
+                        if (jl >= cj) { jl -= cj; ++il; }
+                    }
                 }
                 __syncthreads();
                 // The normaliser and the argmin are short reductions over n1 x cj numbers; done by one thread per
