@@ -163,6 +163,13 @@ int vl3d_patch_l1(const vl3d_loss_desc* desc, const float* x, const float* y, co
                   void* stream);
 int vl3d_to8b(const float* rgb, uint8_t* out, int32_t T, int32_t H, int32_t W, void* stream);
 
+/* S3 (train_3dvid.py:54 `vid / 255` of MVVidPatchDataset): uint8 frames -> fp32 in [0,1] on the device (IEEE division:
+ * bit-identical to the host conversion), so that target videos cross PCIe / NVLink as bytes.
+ * src: `planes` images (frames x channels) of H x W bytes, plane / row strides in bytes (a crop of a larger video);
+ * dst: contiguous (planes, H, W) floats. */
+int vl3d_u8_to_unit(const uint8_t* src, float* dst, int32_t planes, int32_t H, int32_t W, int64_t plane_stride,
+                    int64_t row_stride, void* stream);
+
 /* ---- optimiser (MPV.py:200-218: torch.optim.Adam(betas=(0.9,0.999), eps=6e-8), one tensor) ------
  * p, g, m, v: n floats each; step >= 1.  lr etc. are host scalars. */
 int vl3d_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr,

@@ -170,3 +170,44 @@ def test_run_iter_on_dataset_items_matches_reference_step():
         ref = extra["swd"].mean() + extra["rgb_smooth"].mean() * kw["rgb_smooth_loss_weight"] \
             + extra["a_smooth"].mean() * kw["a_smooth_loss_weight"]
         assert abs(float(out["loss"]) - float(ref)) < 1e-4 * abs(float(ref))
+
+
+def test_u8_targets_convert_on_device_bit_exactly():
+    """S3: `vid / 255` (train_3dvid.py:54) on the device (`vl3d_u8_to_unit`) gives the host conversion's bits for
+    every byte value, for contiguous videos and for strided crops (aligned and unaligned), and the fused step fed
+    with byte crops computes exactly what it computes from the float crops."""
+    from videoloop3d_b200 import FusedLoopStep, ops
+    from test_gpu_parity import model_from_golden
+    from util import cfg_from_golden
+    dev = torch.device("cuda:0")
+    allv = torch.arange(256, dtype=torch.uint8).reshape(1, 1, 16, 16).expand(2, 3, 16, 16).contiguous()
+    assert torch.equal(ops.u8_to_unit(allv.to(dev)).cpu(), allv / 255)
+    g = torch.Generator().manual_seed(0)
+    vid = torch.randint(0, 256, (5, 3, 37, 64), dtype=torch.uint8, generator=g)
+    for crop in (vid, vid[..., 4:28, 8:48], vid[..., 3:30, 5:42], vid[1:4, :, :, 1:]):
+        assert torch.equal(ops.u8_to_unit(_same_crop(vid.to(dev), vid, crop)).cpu(), crop / 255)
+    gold = load_golden("step_dense_refcfg")
+    cfg = cfg_from_golden(gold)
+    H, W = int(gold["H"]), int(gold["W"])
+    kw = dict(rgb_smooth_loss_weight=float(gold["rgb_smooth_w"]), a_smooth_loss_weight=float(gold["a_smooth_w"]),
+              swd_patcht_size=int(cfg["patcht_size"]))
+    F_ = gold["res"].shape[1]
+    big = torch.randint(0, 256, (F_, 3, H + 6, W + 8), dtype=torch.uint8, generator=g).to(dev)
+    crop_u8 = big[..., 2:2 + H, 4:4 + W]
+    ext, intr = torch.as_tensor(gold["tar_extrin"]).to(dev), torch.as_tensor(gold["tar_intrin"]).to(dev)
+    as_float = (crop_u8.cpu().float() / 255).to(dev)
+    outs = []
+    for res in (crop_u8[None], as_float[None]):
+        step = FusedLoopStep(model_from_golden(gold, **kw))
+        o = step.step(H, W, ext, intr, res, dict(cfg), lr=0.01)
+        outs.append((float(o["loss"]), float(o["swd"]), step._buf["nn"].clone()))
+        if res.dtype == torch.uint8:
+            assert torch.equal(step._buf["res_f32"], as_float)
+    # (the updated parameters are not compared bit for bit: the backward accumulates with float atomics)
+    assert outs[0][:2] == outs[1][:2] and torch.equal(outs[0][2], outs[1][2])
+
+
+def _same_crop(dev_vid, host_vid, host_crop):
+    """The view of `dev_vid` that corresponds to `host_crop`, a basic-slicing view of `host_vid`."""
+    off = host_crop.storage_offset() - host_vid.storage_offset()
+    return dev_vid.as_strided(host_crop.shape, host_crop.stride(), dev_vid.storage_offset() + off)

@@ -814,6 +814,28 @@ __global__ void __launch_bounds__(256) patch_l1_kernel(const vl3d_loss_desc L, c
     if (lane == 0) err[pair] = acc / (float)d;
 }
 
+// uint8 video -> fp32 in [0,1]: `vid / 255` of MVVidPatchDataset (train_3dvid.py:54), done on the device so that only a
+// quarter of the bytes cross PCIe.  IEEE division (nvcc default -prec-div=true) = torch's true_divide bit for bit.
+// src: `planes` images of H x W bytes with plane / row strides (a crop of a resident video); dst contiguous.
+template <bool VEC4>
+__global__ void __launch_bounds__(256) u8_to_unit_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, int H,
+                                                         int W, long long plane_stride, long long row_stride, size_t total) {
+    const int Wq = VEC4 ? W / 4 : W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = i / Wq;
+        const int xq = (int)(i - row * Wq);
+        const size_t pl = row / H;
+        const int y = (int)(row - pl * H);
+        const unsigned char* sp = src + pl * plane_stride + (size_t)y * row_stride;
+        if (VEC4) {
+            const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(sp) + xq);
+            reinterpret_cast<float4*>(dst)[i] = make_float4((float)v.x / 255.f, (float)v.y / 255.f, (float)v.z / 255.f, (float)v.w / 255.f);
+        } else {
+            dst[i] = (float)__ldg(sp + xq) / 255.f;
+        }
+    }
+}
+
 // to8b (utils.py:17): (255 * clip(x, 0, 1)).astype(uint8), planar (T,3,H,W) float -> (T,H,W,3) uint8
 __global__ void __launch_bounds__(256) to8b_kernel(const float* __restrict__ rgb, unsigned char* __restrict__ out, size_t hw,
                                                    size_t total) {
@@ -1022,6 +1044,20 @@ extern "C" int vl3d_patch_l1(const vl3d_loss_desc* desc, const float* x, const f
     const long long npairs = (long long)desc->ho * desc->wo * desc->n1;
     patch_l1_kernel<<<(unsigned)((npairs + 7) / 8), 256, 0, (cudaStream_t)stream>>>(*desc, x, y, nn, err_out);
     return check_launch("patch_l1");
+}
+
+extern "C" int vl3d_u8_to_unit(const uint8_t* src, float* dst, int32_t planes, int32_t H, int32_t W, int64_t plane_stride,
+                               int64_t row_stride, void* stream) {
+    VL3D_REQUIRE(src && dst, VL3D_ENULL, "u8_to_unit: NULL pointer");
+    VL3D_REQUIRE(planes >= 1 && H >= 1 && W >= 1 && row_stride >= W && plane_stride >= (int64_t)(H - 1) * row_stride + W,
+                 VL3D_EINVAL, "u8_to_unit: bad sizes / strides");
+    const bool vec = W % 4 == 0 && row_stride % 4 == 0 && plane_stride % 4 == 0 && ((uintptr_t)src & 3) == 0 &&
+                     ((uintptr_t)dst & 15) == 0;
+    const size_t total = (size_t)planes * H * (vec ? W / 4 : W);
+    const size_t blocks = (total + 255) / 256 < (size_t)148 * 32 ? (total + 255) / 256 : (size_t)148 * 32;
+    if (vec) u8_to_unit_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, plane_stride, row_stride, total);
+    else u8_to_unit_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, plane_stride, row_stride, total);
+    return check_launch("u8_to_unit");
 }
 
 extern "C" int vl3d_to8b(const float* rgb, uint8_t* out, int32_t T, int32_t H, int32_t W, void* stream) {

@@ -12,7 +12,11 @@ host-to-device copy of every crop (`datainfo_.to(device)`, train_3dvid.py:215). 
   * on the GPU (`device="cuda"`): a whole capture (10 views x 258 frames at 720p = 28.5 GB fp32) fits next to the
     90 GB model state in the 180 GB of one B200, so an item is a strided VIEW of resident memory — no copy at all;
   * in pinned host memory (`pin_memory=True`): the crop copy is an asynchronous DMA that `FusedLoopStep.step(...,
-    res_ready=event)` overlaps with the render (bench.py's e2e arm).
+    res_ready=event)` overlaps with the render (bench.py's e2e arm);
+  * as bytes (`storage="uint8"`): the frames stay uint8 — a quarter of the memory and of the PCIe / NVLink traffic —
+    and `vid / 255` (train_3dvid.py:54) happens on the device right before the loss (`vl3d_u8_to_unit`, IEEE division:
+    the same bits as the host conversion).  Items then carry uint8 crops; `FusedLoopStep.step` and `make_run_iter`
+    accept them.
 `batches()` yields exactly what `DataLoader(dataset, 1, shuffle=True)` yields (batch dimension of 1, loss config
 values batched the way `default_collate` batches them) without worker processes or collate copies.
 """
@@ -56,10 +60,11 @@ def _resize_frames(video, w, h):
 class MVVidPatchDataset(torch.utils.data.Dataset):
     """train_3dvid.py:22-66.  `videos`: list of V arrays (F,H,W,3) uint8; `poses` (V,3,4+), `intrins` (V,3,3) at the
     raw resolution; `loss_configs`: one dict per view.  Extra (B200) arguments: `device` — where the padded fp32
-    videos are kept (None = host); `pin_memory` — page-lock the host copies."""
+    videos are kept (None = host); `pin_memory` — page-lock the host copies; `storage` — "float32" (items as in the
+    reference) or "uint8" (items carry byte crops, converted on the device by the step)."""
 
     def __init__(self, resize_hw, videos, patch_size, patch_stride, poses, intrins, loss_configs=None, device=None,
-                 pin_memory=False):
+                 pin_memory=False, storage="float32"):
         super().__init__()
         h_raw, w_raw, _ = videos[0][0].shape[-3:]
         self.h, self.w = resize_hw
@@ -80,10 +85,17 @@ class MVVidPatchDataset(torch.utils.data.Dataset):
         self.loss_configs = loss_configs
         assert len(self.loss_configs) == self.v
         self.device = torch.device(device) if device is not None else None
+        if storage not in ("float32", "uint8"):
+            raise ValueError(f"storage must be 'float32' or 'uint8', got {storage!r}")
+        self.storage = storage
         self.videos = []
         for video in videos:
             vid = torch.tensor(_resize_frames(video, self.w, self.h), device='cpu')
-            vid = (vid / 255).permute(0, 3, 1, 2)
+            if storage == "uint8":
+                assert vid.dtype == torch.uint8, "storage='uint8' needs uint8 frames"
+                vid = vid.permute(0, 3, 1, 2)                       # zero padding: 0 / 255 == 0
+            else:
+                vid = (vid / 255).permute(0, 3, 1, 2)
             vid = torchf.pad(vid, pad_info).contiguous()
             if self.device is not None and self.device.type != "cpu":
                 vid = vid.to(self.device)

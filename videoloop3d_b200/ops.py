@@ -183,6 +183,23 @@ def make_loss_desc(x_tchw_shape, x_strides, y_fchw_shape, y_strides, patch_size,
     return d
 
 
+def u8_to_unit(v, out=None):
+    """uint8 frames (F,3,h,w) — contiguous or a spatial crop of a contiguous video — -> float32 `v / 255`
+    (train_3dvid.py:54), bit-identical to the host conversion."""
+    if not v.is_cuda:
+        raise _lib.Vl3dError("v must be a CUDA tensor: the vl3d hot path has no CPU implementation")
+    if v.dtype != torch.uint8 or v.dim() != 4:
+        raise _lib.Vl3dError(f"u8_to_unit expects a (F,3,h,w) uint8 tensor, got {tuple(v.shape)} {v.dtype}")
+    F_, C_, h, w = v.shape
+    if v.stride(3) != 1 or (F_ > 1 and v.stride(0) != C_ * v.stride(1)):
+        v = v.contiguous()
+    if out is None or tuple(out.shape) != (F_, C_, h, w) or out.dtype != torch.float32 or not out.is_contiguous():
+        out = torch.empty((F_, C_, h, w), dtype=torch.float32, device=v.device)
+    _lib.call("vl3d_u8_to_unit", _lib.ptr(v), _lib.ptr(out), int(F_ * C_), int(h), int(w), int(v.stride(1)),
+              int(v.stride(2)), _lib.stream_ptr())
+    return out
+
+
 def scale_video(x, xscale, out=None):
     """x * xscale into a contiguous buffer (MPV.py:504)."""
     if not x.is_contiguous():

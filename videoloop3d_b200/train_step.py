@@ -67,6 +67,8 @@ def make_run_iter(args, nerf, device, writer=None, on_log=None):
     def run_iter(stepi, optimizer_, datainfo_):
         datainfo_ = [d.to(device) if torch.is_tensor(d) else d for d in datainfo_]
         h_starts, w_starts, b_pose, b_intrin, b_rgbs, loss_cfg = datainfo_
+        if b_rgbs.dtype == torch.uint8:                             # MVVidPatchDataset(storage="uint8"): bytes until here
+            b_rgbs = ops.u8_to_unit(b_rgbs[0])[None]
         b_extrin = pose2extrin_torch(b_pose)
         patch_h, patch_w = b_rgbs.shape[-2:]
         if args.add_intrin_noise:
@@ -242,7 +244,8 @@ class FusedLoopStep:
         if pad > T:
             raise ValueError("loop pad longer than the video")
         res0 = res[0] if res.dim() == 5 else res
-        if not res0.is_contiguous():
+        res_u8 = res0 if res0.dtype == torch.uint8 else None       # bytes from the loader: converted after `res_ready`
+        if res_u8 is None and not res0.is_contiguous():
             res0 = res0.contiguous()
         ext = tar_extrin.reshape(4, 4).double().cpu().numpy() @ np.linalg.inv(m.ref_extrin.double().cpu().numpy())
         view = m.make_view(h, w, ext, tar_intrin)
@@ -281,6 +284,9 @@ class FusedLoopStep:
         # ---- looping loss
         if res_ready is not None:
             torch.cuda.current_stream().wait_event(res_ready)
+        if res_u8 is not None:                                      # `vid / 255` of the dataset (train_3dvid.py:54), on device
+            with self._timed("target_u8_to_float"):
+                res0 = ops.u8_to_unit(res_u8, out=self._get("res_f32", tuple(res_u8.shape), torch.float32))
         xscale = None
         if args.scale_invariant:
             with self._timed("scale_invariant"):
