@@ -391,24 +391,30 @@ def run_ours(args):
     res_host = res_full_host[:, f0:f1].contiguous().pin_memory()        # this rank's share of the item
     del res_full_host
     loader_group = dist.new_group(backend="nccl") if world > 1 else None
-    bufs = [torch.empty((1, wl["F"], 3, H, W), dtype=torch.uint8, device=dev) for _ in range(2)]
+    bufs_u8 = [torch.empty((1, wl["F"], 3, H, W), dtype=torch.uint8, device=dev) for _ in range(2)]
+    bufs = [torch.empty_like(res_dev), res_dev]                         # the step's float input, double-buffered
     copy_stream = torch.cuda.Stream()
     ext_h, intr_h = ext.pin_memory(), intr.pin_memory()
     h2d = wl["F"] * 3 * H * W + 1216 * world          # target video as bytes (all ranks together) + the view descriptors
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
-    def load(buf):
-        """H2D of this rank's frames (+ NVLink all-gather of the other ranks' frames) on the copy stream."""
+    from videoloop3d_b200 import ops as vl_ops
+
+    def load(i):
+        """H2D of this rank's frames as bytes (+ NVLink all-gather of the other ranks' frames) and `/ 255` into the
+        float buffer the step reads, all on the copy stream (so it overlaps the previous step)."""
+        buf = bufs_u8[i]
         buf[:, f0:f1].copy_(res_host, non_blocking=True)
         if world > 1:
             parts = [buf[0, a:b] for a, b in zip(fb[:-1], fb[1:])]
             dist.all_gather(parts, buf[0, f0:f1], group=loader_group)
+        vl_ops.u8_to_unit(buf[0], out=bufs[i][0])
 
     def e2e_loop(n):
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         done = [torch.cuda.Event(), torch.cuda.Event()]
         with torch.cuda.stream(copy_stream):
-            load(bufs[0])
+            load(0)
             ready[0].record()
         for i in range(n):
             cur, nxt = i & 1, (i + 1) & 1
@@ -416,7 +422,7 @@ def run_ours(args):
                 with torch.cuda.stream(copy_stream):
                     if i >= 1:
                         copy_stream.wait_event(done[nxt])             # buffer `nxt` was consumed by step i-1
-                    load(bufs[nxt])
+                    load(nxt)
                     ready[nxt].record()
             # pose / intrinsics stay on the host: the view descriptor (plane homographies) is built there;
             # the step waits for the copy only where it first reads the target video (after the render)
@@ -459,7 +465,7 @@ def run_ours(args):
             "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms / args.steps,
                     "api": "FusedLoopStep.step fed from pinned host memory holding the uint8 target video (double-buffered "
-                           "H2D, /255 on the device; with N ranks each copies 1/N of the frames and they are all-gathered "
+                           "H2D and /255 (vl3d_u8_to_unit) on a copy stream; with N ranks each copies 1/N of the frames and they are all-gathered "
                            "over NVLink), loss read back"},
             "gpu_launches": int(launches),
             "clocks": clocks,
