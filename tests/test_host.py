@@ -251,3 +251,25 @@ def test_dataset_matches_reference():
     assert b[4].untyped_storage().data_ptr() == ds.videos[0].untyped_storage().data_ptr()     # a view, not a copy
     seen = sorted((int(x[0]), int(x[1]), float(x[3][0, 0, 2])) for x in ds.batches(shuffle=True, generator=torch.Generator().manual_seed(1)))
     assert len(seen) == len(ds) and len(set(seen)) > 1
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host CPU) prints ONE JSON line with the keys the driver
+    reads; the synthetic target is the same 8-bit video as bytes and as floats."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "steps/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    sys.path.insert(0, ROOT)
+    import bench
+    wl = bench.WORKLOADS["tiny"]
+    f, b = bench.make_target(wl, None), bench.make_target(wl, None, as_bytes=True)
+    assert b.dtype == torch.uint8 and torch.equal(f, b.float() / 255)
