@@ -133,9 +133,10 @@ def test_nn_search_finds_time_shifted_copy():
     assert tuple(nn.shape) == (178, 318, 48)                        # B = 56 604 patch positions
     expect = (torch.arange(48, device=dev(), dtype=torch.int32) + shift)[None, None, :]
     assert torch.equal(nn, expect.expand_as(nn))
-    # y2x is the mean of up to 27 identical samples: equal to x up to the rounding of that sum
+    # y2x is the mean of up to 27 identical samples: equal to x up to the rounding of that fp32 sum (worst case
+    # (n-1)/2 ulp of the sum, i.e. < 1.6e-6 for values below 1; observed 3.6e-7)
     assert float(loss) < 1e-9 and float(x.grad.abs().max()) < 1e-9
-    assert float((lossobj.last_y2x[0] - x.detach()[0, :, :, :719, :1279]).abs().max()) < 3e-7
+    assert float((lossobj.last_y2x[0] - x.detach()[0, :, :, :719, :1279]).abs().max()) < 1e-6
     assert float(lossobj.last_weight.min()) >= 1.0 and float(lossobj.last_weight.max()) == 27.0
 
 
