@@ -399,16 +399,20 @@ def run_ours(args):
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
     from videoloop3d_b200 import ops as vl_ops
+    # where `/ 255` runs: inside the step right before the loss (default), or on the copy stream behind the H2D
+    # (VL3D_BENCH_CONVERT=copy; measured slower: 81.4 vs 77.5 ms e2e — the conversion's 3.6 GB of traffic then
+    # lands under the HBM-bound backward / Adam of the previous step instead of next to the latency-bound loss)
+    convert_on_copy_stream = os.environ.get("VL3D_BENCH_CONVERT", "step") == "copy"
 
     def load(i):
-        """H2D of this rank's frames as bytes (+ NVLink all-gather of the other ranks' frames) and `/ 255` into the
-        float buffer the step reads, all on the copy stream (so it overlaps the previous step)."""
+        """H2D of this rank's frames as bytes (+ NVLink all-gather of the other ranks' frames) on the copy stream."""
         buf = bufs_u8[i]
         buf[:, f0:f1].copy_(res_host, non_blocking=True)
         if world > 1:
             parts = [buf[0, a:b] for a, b in zip(fb[:-1], fb[1:])]
             dist.all_gather(parts, buf[0, f0:f1], group=loader_group)
-        vl_ops.u8_to_unit(buf[0], out=bufs[i][0])
+        if convert_on_copy_stream:
+            vl_ops.u8_to_unit(buf[0], out=bufs[i][0])
 
     def e2e_loop(n):
         ready = [torch.cuda.Event(), torch.cuda.Event()]
@@ -426,7 +430,8 @@ def run_ours(args):
                     ready[nxt].record()
             # pose / intrinsics stay on the host: the view descriptor (plane homographies) is built there;
             # the step waits for the copy only where it first reads the target video (after the render)
-            o = step.step(H, W, ext_h, intr_h, bufs[cur], cfg, lr, res_ready=ready[cur])
+            o = step.step(H, W, ext_h, intr_h, bufs[cur] if convert_on_copy_stream else bufs_u8[cur], cfg, lr,
+                          res_ready=ready[cur])
             done[cur].record()
             loss_host.copy_(o["loss"].reshape(1), non_blocking=True)
         torch.cuda.synchronize()
@@ -465,7 +470,7 @@ def run_ours(args):
             "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms / args.steps,
                     "api": "FusedLoopStep.step fed from pinned host memory holding the uint8 target video (double-buffered "
-                           "H2D and /255 (vl3d_u8_to_unit) on a copy stream; with N ranks each copies 1/N of the frames and they are all-gathered "
+                           "H2D on a copy stream, /255 (vl3d_u8_to_unit) inside the step; with N ranks each copies 1/N of the frames and they are all-gathered "
                            "over NVLink), loss read back"},
             "gpu_launches": int(launches),
             "clocks": clocks,
