@@ -268,7 +268,7 @@ def run_reference_cuda(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "device": "cuda:0 (torch eager, allow_tf32=False)"}}
     if not torch.cuda.is_available():
-        print(json.dumps({**base, "unavailable": "--ref-device cuda needs a GPU"}))
+        emit_line({**base, "unavailable": "--ref-device cuda needs a GPU"})
         return
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
@@ -276,17 +276,17 @@ def run_reference_cuda(args):
     try:
         ms_p, ms_a, n, (ph, pw) = gpu_torch_reference_step(wl, torch.device("cuda", 0), steps)
     except torch.cuda.OutOfMemoryError as ex:
-        print(json.dumps({**base, "unavailable": f"out of memory: {str(ex)[:120]}"}))
+        emit_line({**base, "unavailable": f"out of memory: {str(ex)[:120]}"})
         return
     ms = ms_p + ms_a
-    print(json.dumps({**base, "value": 1000.0 / ms, "steps": steps, "warmup": 1, "ms_per_step": ms,
+    emit_line({**base, "value": 1000.0 / ms, "steps": steps, "warmup": 1, "ms_per_step": ms,
                       "parts_ms": {"patches_fwd_bwd": ms_p, "adam": ms_a},
                       "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9,
                       "sample": f"{n} patches of {ph}x{pw} (the reference's step shape) covering {wl['H']}x{wl['W']}, "
                                 f"gradients accumulated, one torch.optim.Adam step; reference operator sequence "
                                 f"(grid_sample / masked_scatter / cumprod / unfold / bmm / index_add), host "
                                 f"rasteriser stand-in not timed",
-                      "gpu_launches": 0}))
+                      "gpu_launches": 0})
 
 
 def run_reference(args):
@@ -310,7 +310,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit_line(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -492,9 +492,41 @@ def run_ours(args):
                                     "sample": f"oracle port of the reference's PyTorch CPU path on one {sample['H']}x{sample['W']} "
                                               f"patch (1/{ratio:.0f} of the frame), D={sample['D']}, T={sample['T']}, F={sample['F']}: "
                                               f"{sec:.2f} s, scaled x{ratio:.0f}"}
-        print(json.dumps(line))
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+class _OnlyJsonOnStdout:
+    """Libraries (NCCL's version banner, torchrun notices) write to file descriptor 1; the contract is ONE JSON line on
+    stdout.  Inside this context fd 1 points at stderr; `emit` writes to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self._real, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._real, 1)
+        os.close(self._real)
+        return False
+
+
+_OUT = None
+
+
+def emit_line(obj):
+    text = json.dumps(obj)
+    if _OUT is not None:
+        _OUT.emit(text)
+    else:
+        print(text, flush=True)
 
 
 def main():
@@ -510,10 +542,16 @@ def main():
     ap.add_argument("--no-smooth", action="store_true", help="tuning aid: drop the smoothness regularisers")
     ap.add_argument("--overlap-chunks", type=int, default=1, help="frame chunks of the backward/Adam pipeline (1 = off)")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    global _OUT
+    with _OnlyJsonOnStdout() as out:
+        _OUT = out
+        try:
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_ours(args)
+        finally:
+            _OUT = None
 
 
 if __name__ == "__main__":

@@ -17,7 +17,7 @@ timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 echo "ncu launches rc=$?" >> $out/${tag}_rc.log
 timeout 240 python bench.py --impl reference --ref-device cuda --steps 1 > $out/${tag}_bench_ref_cuda.json 2> $out/${tag}_bench_ref_cuda.err
 echo "ref cuda rc=$?" >> $out/${tag}_rc.log
-timeout 200 ncu --set full --clock-control none --import-source on -k 'regex:patchnn_strip|vote_loss_kernel' -c 2 \
+timeout 200 ncu --set full --clock-control none --import-source on -k 'regex:patchnn_strip|vote_loss' -c 2 \
     -o $out/${tag}_full_search_vote -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $out/${tag}_ncu_full.log 2>&1
 echo "ncu full rc=$?" >> $out/${tag}_rc.log
 cat $out/${tag}_rc.log
