@@ -273,3 +273,75 @@ def test_bench_reference_arm_prints_the_contract_line():
     wl = bench.WORKLOADS["tiny"]
     f, b = bench.make_target(wl, None), bench.make_target(wl, None, as_bytes=True)
     assert b.dtype == torch.uint8 and torch.equal(f, b.float() / 255)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_host_geometry_matches_oracle_on_random_views_and_layouts(seed):
+    """The quad table + per-plane homographies the host hands to the kernels (tiles.py) reproduce the oracle's
+    per-pixel geometry (hit mask exactly, tile kind, atlas coordinates to 1e-4 texel) for seeded random tile
+    cullings, atlas scales, rotations about all three axes, translations and principal-point shifts — including the
+    patch views of the dataset (principal point moved by a patch origin, utils.py:196-200)."""
+    rng = np.random.default_rng(100 + seed)
+    H, W = int(rng.integers(20, 40)), int(rng.integers(28, 56))
+    D, hv, wv = int(rng.integers(2, 7)), int(rng.integers(3, 7)), int(rng.integers(3, 8))
+    scale = float(rng.uniform(1.0, 1.4))
+    if seed % 2:
+        st = MO.sparse_state(H, W, D, hv, wv, 2, 1.0, 10.0, tile=int(rng.integers(3, 9)), occupancy=float(rng.uniform(0.3, 0.9)),
+                             dyn_frac=float(rng.uniform(0.2, 0.8)), h_scale=scale, w_scale=scale, seed=seed)
+    else:
+        st = MO.dense_state(H, W, D, hv, wv, 1, 2, 1.0, 10.0, scale, scale, seed=seed)
+        st.atlas = st.atlas[:, :, :1, :1].clone()
+    ang = rng.uniform(-0.06, 0.06, 3)
+    Rx = np.array([[1, 0, 0], [0, np.cos(ang[0]), -np.sin(ang[0])], [0, np.sin(ang[0]), np.cos(ang[0])]])
+    Ry = np.array([[np.cos(ang[1]), 0, np.sin(ang[1])], [0, 1, 0], [-np.sin(ang[1]), 0, np.cos(ang[1])]])
+    Rz = np.array([[np.cos(ang[2]), -np.sin(ang[2]), 0], [np.sin(ang[2]), np.cos(ang[2]), 0], [0, 0, 1]])
+    ext = np.eye(4, dtype=np.float32)
+    ext[:3, :3] = Rx @ Ry @ Rz
+    ext[:3, 3] = rng.uniform(-0.1, 0.1, 3) * [1, 1, 0.3]
+    f = 0.8 * W * float(rng.uniform(0.8, 1.3))
+    intr = np.array([[f, 0, W / 2 + rng.uniform(-6, 6)], [0, f, H / 2 + rng.uniform(-6, 6)], [0, 0, 1]], dtype=np.float32)
+    grids = tiles.plane_grids(st.verts.numpy(), D, hv, wv)
+    table = tiles.build_quad_table(D, hv, wv, st.faces.numpy(), st.uvs.numpy(), st.uvfaces.numpy(),
+                                   tuple(st.atlas.shape[-2:]), st.faces_dyn.numpy(), st.uvs_dyn.numpy(),
+                                   st.uvfaces_dyn.numpy(), tuple(st.atlas_dyn.shape[-2:]))
+    rel = ext.astype(np.float64) @ np.linalg.inv(st.ref_extrin.numpy().astype(np.float64))
+    homs, cx, cy = tiles.view_homographies(grids, hv - 1, wv - 1, rel, intr[None], np.eye(4), H, W)
+    geo = MO.geometry(st, H, W, torch.as_tensor(ext)[None], torch.as_tensor(intr)[None])
+    n_hit = 0
+    for d, (ok, kind, ax, ay) in enumerate(_emulate_kernel_geometry(st, table, homs, cx, cy, H, W)):
+        oh = geo["hit"][:, d].numpy()
+        # a pixel whose ray passes within fp32 rounding of a quad edge may legitimately fall on either side
+        gx_edge = np.zeros_like(oh)
+        if not np.array_equal(ok, oh):
+            diff = ok != oh
+            assert diff.sum() <= 2, (d, int(diff.sum()))
+            gx_edge = diff
+        keep = oh & ~gx_edge & ok
+        n_hit += int(keep.sum())
+        assert np.array_equal(kind[keep], geo["kind"][:, d].numpy()[keep])
+        assert np.abs(ax[keep] - geo["ax"][:, d].numpy()[keep]).max(initial=0) < 1e-4
+        assert np.abs(ay[keep] - geo["ay"][:, d].numpy()[keep]).max(initial=0) < 1e-4
+    assert n_hit > H * W // 4
+
+
+def test_argument_validation_of_the_data_entry_points():
+    """vl3d_u8_to_unit / vl3d_to8b / vl3d_patch_l1 / vl3d_vote_loss reject bad arguments with a VL3D_E* code and a
+    message before touching the device (runs without a GPU)."""
+    lib = _lib.load()
+    p16 = ctypes.c_void_p(16)
+    with pytest.raises(_lib.Vl3dError, match="NULL"):
+        _lib.call("vl3d_u8_to_unit", None, p16, 3, 4, 4, 16, 4, None)
+    with pytest.raises(_lib.Vl3dError, match="strides"):
+        _lib.call("vl3d_u8_to_unit", p16, p16, 3, 4, 8, 16, 4, None)          # row stride < width
+    with pytest.raises(_lib.Vl3dError, match="strides"):
+        _lib.call("vl3d_u8_to_unit", p16, p16, 3, 4, 4, 8, 4, None)           # plane stride < one image
+    with pytest.raises(_lib.Vl3dError, match="to8b"):
+        _lib.call("vl3d_to8b", p16, p16, 0, 4, 4, None)
+    d = ops.make_loss_desc((50, 3, 180, 320), (1, 1, 1), (258, 3, 180, 320), (1, 1, 1), 11, 3, 4, 1, 0.0)
+    with pytest.raises(_lib.Vl3dError, match="NULL"):
+        _lib.call("vl3d_vote_loss", ctypes.byref(d), None, None, None, None, 0, -2.0, 0.1, 1.0, 50, 180, 320, 0, 50,
+                  None, None, None, None, None, None)
+    with pytest.raises(_lib.Vl3dError, match="frame range"):
+        _lib.call("vl3d_vote_loss", ctypes.byref(d), p16, None, p16, p16, 0, -2.0, 0.1, 1.0, 50, 180, 320, 7, 3,
+                  None, None, None, p16, p16, None)
+    assert lib.vl3d_vote_partials(50, 180, 320) == 50 * 10 * 23 and lib.vl3d_vote_partials(0, 1, 1) == 0
