@@ -737,7 +737,7 @@ static void launch_bwd(const CompositeParams& p0, int T, dim3 grid2, dim3 block,
     if (nz > 0) {
         P.p.tb = 0;
         bool split = false;
-        if constexpr (SMOOTH && TF == 2) {
+        if constexpr (SMOOTH && (TF == 2 || TF == 3)) {   // (TF = 3 only through VL3D_BWD_TF=3: round-2 tuning aid)
             // dense layout: tiles whose pixels all hit the same planes stage their texels with TMA, the rest (image
             // border) keep the per-thread loads — decided per tile inside one launch; VL3D_TMA_BWD=0: tuning aid
             if (rect_planes && P.p.ts == nullptr && env_int("VL3D_TMA_BWD", 1) != 0 && make_atlas_tmap(&P.tmap, P.p.view, atlas_dyn, T)) {
