@@ -4,7 +4,7 @@ tag=${1:-check}; n=${2:-2}
 out=gpurun_out
 mkdir -p $out
 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
-    scripts/check_sharded.py > $out/${tag}_check_sharded_n$n.log 2>&1
+    tests/check_sharded.py > $out/${tag}_check_sharded_n$n.log 2>&1
 echo "check_sharded rc=$?" > $out/${tag}_rc_n$n.log
 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 \
     bench.py --gpus $n --steps 10 --warmup 3 > $out/${tag}_bench_n$n.json 2> $out/${tag}_bench_n$n.err

@@ -1,7 +1,7 @@
 """Multi-GPU check (run under torchrun): the T-sharded FusedLoopStep must reproduce the single-GPU step.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        scripts/check_sharded.py
+        tests/check_sharded.py
 
 Every rank builds the same small model; rank r optimises only its frame block (both the "full model on
 every rank" and the memory-sharded variants are exercised); after 3 steps the parameters, the losses and

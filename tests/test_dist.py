@@ -101,9 +101,9 @@ def test_collective_pattern_gloo_world2():
 @pytest.mark.gpu
 def test_sharded_step_equals_single_gpu_step():
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs (run scripts/check_sharded.py under gpurun --gpus 2)")
+        pytest.skip("needs >= 2 GPUs (run tests/check_sharded.py under gpurun --gpus 2)")
     n = min(torch.cuda.device_count(), 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
-           "127.0.0.1", "--master-port", "29544", os.path.join(ROOT, "scripts", "check_sharded.py")]
+           "127.0.0.1", "--master-port", "29544", os.path.join(ROOT, "tests", "check_sharded.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
