@@ -61,48 +61,56 @@ class MVVidPatchDataset(torch.utils.data.Dataset):
     """train_3dvid.py:22-66.  `videos`: list of V arrays (F,H,W,3) uint8; `poses` (V,3,4+), `intrins` (V,3,3) at the
     raw resolution; `loss_configs`: one dict per view.  Extra (B200) arguments: `device` — where the padded fp32
     videos are kept (None = host); `pin_memory` — page-lock the host copies; `storage` — "float32" (items as in the
-    reference) or "uint8" (items carry byte crops, converted on the device by the step)."""
+    reference) or "uint8" (items carry byte crops, converted on the device by the step).
+
+    Item order: view-major, and within a view the patch origins in `generate_patchinfo` order."""
 
     def __init__(self, resize_hw, videos, patch_size, patch_stride, poses, intrins, loss_configs=None, device=None,
                  pin_memory=False, storage="float32"):
         super().__init__()
-        h_raw, w_raw, _ = videos[0][0].shape[-3:]
-        self.h, self.w = resize_hw
-        self.v = len(videos)
-        self.poses = poses.clone().cpu()
-        self.intrins = intrins.clone().cpu()
-        self.intrins[:, :2] *= torch.tensor([self.w / w_raw, self.h / h_raw]).reshape(1, 2, 1).type_as(intrins)
-        self.patch_h_size, self.patch_w_size = patch_size
-        if self.h * self.w < self.patch_h_size * self.patch_w_size:
-            patch_wh_start = torch.tensor([[0, 0]]).long().reshape(-1, 2)
-            pad_info = [0, 0, 0, 0]
-            self.patch_h_size, self.patch_w_size = self.h, self.w
-        else:
-            patch_wh_start, pad_info = generate_patchinfo(self.h, self.w, patch_size, patch_stride)
-        n_patch = patch_wh_start.shape[0]
-        self.patch_wh_start = patch_wh_start[None].expand(self.v, -1, 2).reshape(-1, 2).cpu()
-        self.view_index = np.repeat(np.arange(self.v), n_patch).tolist()
-        self.loss_configs = loss_configs
-        assert len(self.loss_configs) == self.v
-        self.device = torch.device(device) if device is not None else None
         if storage not in ("float32", "uint8"):
             raise ValueError(f"storage must be 'float32' or 'uint8', got {storage!r}")
+        if loss_configs is None or len(loss_configs) != len(videos):
+            raise AssertionError("one loss config per view is required")
+        self.h, self.w = resize_hw
+        self.v = len(videos)
         self.storage = storage
-        self.videos = []
-        for video in videos:
-            vid = torch.tensor(_resize_frames(video, self.w, self.h), device='cpu')
-            if storage == "uint8":
-                assert vid.dtype == torch.uint8, "storage='uint8' needs uint8 frames"
-                vid = vid.permute(0, 3, 1, 2)                       # zero padding: 0 / 255 == 0
-            else:
-                vid = (vid / 255).permute(0, 3, 1, 2)
-            vid = torchf.pad(vid, pad_info).contiguous()
-            if self.device is not None and self.device.type != "cpu":
-                vid = vid.to(self.device)
-            elif pin_memory:
-                vid = vid.pin_memory()
-            self.videos.append(vid)
+        self.loss_configs = loss_configs
+        self.device = torch.device(device) if device is not None else None
+        self._pin = bool(pin_memory)
+
+        # cameras: intrinsics follow the resize from the raw frame size (rows 0 / 1 scale with width / height)
+        raw_h, raw_w = videos[0][0].shape[-3:-1]
+        self.poses = poses.clone().cpu()
+        self.intrins = intrins.clone().cpu()
+        self.intrins[:, :2] *= torch.tensor([self.w / raw_w, self.h / raw_h]).reshape(1, 2, 1).type_as(intrins)
+
+        # patch grid: one whole-frame item when the frame is smaller than a patch, else the stride grid + padding
+        self.patch_h_size, self.patch_w_size = patch_size
+        if self.h * self.w < self.patch_h_size * self.patch_w_size:
+            origins, pad_info = torch.zeros((1, 2), dtype=torch.long), [0, 0, 0, 0]
+            self.patch_h_size, self.patch_w_size = self.h, self.w
+        else:
+            origins, pad_info = generate_patchinfo(self.h, self.w, patch_size, patch_stride)
         self.pad_info = pad_info
+        self.patch_wh_start = origins.repeat(self.v, 1).cpu()                    # (V * n_patch, 2) rows of (w, h)
+        self.view_index = np.repeat(np.arange(self.v), origins.shape[0]).tolist()
+
+        self.videos = [self._prepare(frames) for frames in videos]
+
+    def _prepare(self, frames):
+        """resize -> [0,1] (or bytes) -> (F,3,h,w) -> zero padding on the right / bottom -> its home memory"""
+        vid = torch.tensor(_resize_frames(frames, self.w, self.h), device='cpu')
+        if self.storage == "uint8":
+            if vid.dtype != torch.uint8:
+                raise TypeError("storage='uint8' needs uint8 frames")
+            vid = vid.permute(0, 3, 1, 2)                                        # zero padding: 0 / 255 == 0
+        else:
+            vid = (vid / 255).permute(0, 3, 1, 2)
+        vid = torchf.pad(vid, self.pad_info).contiguous()
+        if self.device is not None and self.device.type != "cpu":
+            return vid.to(self.device)
+        return vid.pin_memory() if self._pin else vid
 
     def __len__(self):
         return len(self.patch_wh_start)
