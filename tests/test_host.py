@@ -248,6 +248,16 @@ def test_dataset_matches_reference():
     shapes = [b[0].dim(), b[1].dim(), *b[2].shape, *b[3].shape, *b[4].shape]
     assert shapes == g["batch_shapes"].tolist()
     assert b[5]["loss_name"] == ["gpnn_lm"] and torch.is_tensor(b[5]["patch_size"]) and int(b[5]["patch_size"][0]) == 5
+    from torch.utils.data import DataLoader
+    ds.loss_configs = [dict(loss_name="gpnn_lm", patch_size=5, scaling=0.1, alpha=0.0), dict(loss_name="gpnn_lm", patch_size=3)]
+    ours, theirs = next(iter(ds.batches(shuffle=False)))[5], next(iter(DataLoader(ds, 1, shuffle=False)))[5]
+    assert set(ours) == set(theirs)
+    for k in ours:                                                        # same types, dtypes and values as default_collate
+        if torch.is_tensor(theirs[k]):
+            assert ours[k].dtype == theirs[k].dtype and torch.equal(ours[k], theirs[k]), k
+        else:
+            assert ours[k] == theirs[k], k
+    assert ours["scaling"][0].item() == 0.1
     assert b[4].untyped_storage().data_ptr() == ds.videos[0].untyped_storage().data_ptr()     # a view, not a copy
     seen = sorted((int(x[0]), int(x[1]), float(x[3][0, 0, 2])) for x in ds.batches(shuffle=True, generator=torch.Generator().manual_seed(1)))
     assert len(seen) == len(ds) and len(set(seen)) > 1

@@ -57,6 +57,18 @@ def _resize_frames(video, w, h):
     return np.array([cv2.resize(img, (w, h)) for img in video])
 
 
+def _collate_scalar(v):
+    """torch's default_collate for a batch of one python scalar: float -> float64 tensor (so `.item()` returns the very
+    same number), int -> int64 tensor, anything else (strings) -> a 1-element list."""
+    if isinstance(v, bool):
+        return torch.tensor([v])
+    if isinstance(v, float):
+        return torch.tensor([v], dtype=torch.float64)
+    if isinstance(v, int):
+        return torch.tensor([v], dtype=torch.int64)
+    return [v]
+
+
 class MVVidPatchDataset(torch.utils.data.Dataset):
     """train_3dvid.py:22-66.  `videos`: list of V arrays (F,H,W,3) uint8; `poses` (V,3,4+), `intrins` (V,3,3) at the
     raw resolution; `loss_configs`: one dict per view.  Extra (B200) arguments: `device` — where the padded fp32
@@ -131,6 +143,5 @@ class MVVidPatchDataset(torch.utils.data.Dataset):
         order = torch.randperm(n, generator=generator).tolist() if shuffle else range(n)
         for i in order:
             w_start, h_start, pose, intrin, crops, cfg = self[i]
-            cfg = {k: (torch.tensor([v]) if isinstance(v, (int, float)) and not isinstance(v, bool) else [v])
-                   for k, v in cfg.items()}
+            cfg = {k: _collate_scalar(v) for k, v in cfg.items()}
             yield w_start[None], h_start[None], pose[None], intrin[None], crops[None], cfg
