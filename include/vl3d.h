@@ -175,6 +175,25 @@ int vl3d_u8_to_unit(const uint8_t* src, float* dst, int32_t planes, int32_t H, i
 int vl3d_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr,
                    float beta1, float beta2, float eps, void* stream);
 
+/* ---- fused backward + Adam (train_3dvid.py:242-244 `zero_grad / backward / step` for atlas_dyn) ----
+ * One persistent kernel: the tiles of vl3d_composite_bwd (pad = 0, ts = NULL) and Adam (vl3d_adam_step's arithmetic)
+ * on rectangles of atlas_dyn, pulled from ONE ordered work queue described by `items` (host-built, see
+ * videoloop3d_b200/schedule.py; n_items x 8 int32 = {type | flags << 4, a, b, c, wait_first, wait_count, wait_target,
+ * signal}: type 0 = tile (a, b) of chunk frames, 1 = Adam / 2 = zero-gradient on `c` rows x `b` texels starting at texel
+ * `a` of each frame of the chunk, row stride dyn_w).  The table describes one round = one chunk of 2 frames and is
+ * replayed for T/2 chunks (`n_rounds` = T/2, or T/2 + 1 when items are flagged "previous round").
+ * T must be even.  counters: n_rounds' worth of n_counters int32 (zeroed by the caller), ticket: one int32 (zeroed).
+ * grad_dyn: in schedules whose Adam items re-zero it, it must be all-zero on entry and is all-zero on exit; in
+ * zero-ahead schedules its content on entry / exit is irrelevant.  grad_sta is accumulated into as in vl3d_composite_bwd
+ * (the static atlas is optimised by the caller after its all-reduce).  atlas_dyn, adam_m, adam_v are updated in place.
+ * ctas_per_sm: 0 = as many as fit. */
+int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads, float* atlas_dyn, const float* atlas_sta,
+                        int32_t T, const float* grad_rgb, const float* rgb, const float* w_smooth,
+                        double* smooth_sums, float* grad_dyn, float* grad_sta, float* adam_m, float* adam_v,
+                        int32_t step, float lr, float beta1, float beta2, float eps, const int32_t* items,
+                        int32_t n_items, int32_t n_rounds, int32_t* counters, int32_t n_counters,
+                        int32_t* ticket, int32_t ctas_per_sm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,13 +53,16 @@ _SIGNATURES = {
     "vl3d_to8b": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "vl3d_u8_to_unit": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P]),
     "vl3d_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
+    "vl3d_fused_bwd_adam": (C.c_int, [C.POINTER(View), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32,
+                                      C.c_float, C.c_float, C.c_float, C.c_float, _P, C.c_int32, C.c_int32, _P, C.c_int32,
+                                      _P, C.c_int32, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 
 _lib = None
 LAUNCHES = 0          # kernels launched through this binding (bench.py's gpu_launches)
 _LAUNCHES_PER_CALL = {"vl3d_composite_fwd": 1, "vl3d_composite_bwd": 1, "vl3d_scale_invariant": 2, "vl3d_frame_sum": 1, "vl3d_scale_invariant_presum": 2,
-                      "vl3d_patchnn_search": 1, "vl3d_scale_video": 1, "vl3d_patch_l1": 1, "vl3d_to8b": 1, "vl3d_u8_to_unit": 1, "vl3d_vote_loss": 2, "vl3d_adam_step": 1}
+                      "vl3d_patchnn_search": 1, "vl3d_scale_video": 1, "vl3d_patch_l1": 1, "vl3d_to8b": 1, "vl3d_u8_to_unit": 1, "vl3d_vote_loss": 2, "vl3d_adam_step": 1, "vl3d_fused_bwd_adam": 1}
 
 
 class Vl3dError(RuntimeError):
@@ -103,8 +106,17 @@ def call(name, *args):
 
 
 def ptr(t):
-    """Device pointer of a torch tensor (None -> NULL)."""
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """Device pointer of a torch tensor (None -> NULL).  The kernels are launched on the CURRENT device's current
+    stream, so a tensor living on another GPU is an error here rather than an illegal address later."""
+    if t is None:
+        return None
+    if t.is_cuda:
+        import torch
+        cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise Vl3dError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: wrap the call in "
+                            f"`with torch.cuda.device(tensor.device)`")
+    return C.c_void_p(t.data_ptr())
 
 
 def stream_ptr():

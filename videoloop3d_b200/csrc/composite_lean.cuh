@@ -282,19 +282,26 @@ __device__ __forceinline__ float4 shfl_up4(const float4& v) {
 // lockstep) it stages each plane's atlas footprint with TMA exactly like composite_render_tma_kernel: thread 0
 // issues the box of plane k+2 right after the exchange barrier of slot k, which is also what frees that stage;
 // the remaining (image-border) tiles use the per-thread loads.
+//
+// bwd_tile = one (screen tile, chunk of TF frames) of the backward, as a device function: composite_bwd_kernel runs
+// it once per CTA, the persistent fused backward + Adam kernel (fused_bwd_adam.cu) once per work item.  `kbase`
+// counts the TMA stage uses of this CTA so far (the mbarrier phases carry over from tile to tile); `first` = the
+// CTA's first tile (initialises the mbarriers).  Callers separate two tiles by a __syncthreads().
+constexpr int BWD_TMA_STAGES = 3;
+
 template <int TF, bool SMOOTH, int MODE>
-__global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(const __grid_constant__ TmaRenderParams P) {
+__device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx, const int by, const int t0, unsigned& kbase,
+                                         const bool first) {
     const CompositeParams& p = P.p;
     static_assert(MODE == 0 || SMOOTH, "the split launch is only built for the regulariser tiling");
     constexpr int SX = SMOOTH ? BX - 1 : BX, SY = SMOOTH ? BY - 1 : BY;
-    constexpr int NST = 3;                                          // TMA stages (MODE 2)
+    constexpr int NST = BWD_TMA_STAGES;
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int px0 = blockIdx.x * SX + tx, py0 = blockIdx.y * SY + ty;
+    const int px0 = bx * SX + tx, py0 = by * SY + ty;
     const int H = p.view.H, W = p.view.W;
     const bool active = px0 < W && py0 < H;
     const bool owned = active && tx < SX && ty < SY;
     const int px = min(px0, W - 1), py = min(py0, H - 1);          // replicas of the border pixel
-    const int t0 = p.tb + blockIdx.z * TF;
     const float u = (float)px + 0.5f - p.view.cx, v = (float)py + 0.5f - p.view.cy;
 
     __shared__ float4 s_ex[SMOOTH ? 2 : 1][SMOOTH ? TF : 1][SMOOTH ? BY : 1][SMOOTH ? BX : 1];
@@ -309,13 +316,12 @@ __global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(
             int cls = 0;
             int4 box = make_int4(0, 0, 0, 0);
             if (tx < p.view.D)
-                cls = tile_plane_class(p, tx, blockIdx.x * SX, min(blockIdx.x * SX + BX - 1, W - 1), blockIdx.y * SY,
-                                       min(blockIdx.y * SY + BY - 1, H - 1), box);
+                cls = tile_plane_class(p, tx, bx * SX, min(bx * SX + BX - 1, W - 1), by * SY, min(by * SY + BY - 1, H - 1), box);
             const unsigned m_in = __ballot_sync(0xffffffffu, cls == 1), m_mixed = __ballot_sync(0xffffffffu, cls == 2);
             if (MODE >= 2 && tx < p.view.D) s_box[tx] = box;
             if (tx == 0) {
                 s_cls[0] = (int)m_in; s_cls[1] = (int)m_mixed;
-                if (MODE >= 2) {
+                if (MODE >= 2 && first) {
 #pragma unroll
                     for (int s = 0; s < NST; ++s) mbar_init(&s_full[s], 1);
                     mbar_fence_init();
@@ -373,12 +379,12 @@ __global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(
     // MODE 2: planes of this tile in order, TMA issue state of thread 0
     const int nplanes = __popc(in_mask);
     unsigned rem_planes = in_mask, rem_issue = in_mask;
-    int k_issue = 0;
+    unsigned k_issue = kbase;
     float4* tiles = reinterpret_cast<float4*>(bwd_dyn_smem);
     auto issue_plane = [&]() {                                      // thread 0 only
         const int di = __ffs(rem_issue) - 1;
         rem_issue &= rem_issue - 1u;
-        const int s = k_issue % NST;
+        const int s = (int)(k_issue % NST);
         const int4 bi = s_box[di];
         mbar_arrive_expect_tx(&s_full[s], TF * TMA_BOX_BYTES);
 #pragma unroll
@@ -402,7 +408,8 @@ __global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(
             if (k >= nplanes) break;
             const int dd = __ffs(rem_planes) - 1;
             rem_planes &= rem_planes - 1u;
-            const int s = k % NST;
+            const unsigned use = kbase + (unsigned)k;
+            const int s = (int)(use % NST);
             float gx, gy;
             plane_grid_lean(&p.view.hom[dd * 9], u, v, qwf, qhf, gx, gy);
             int qx, qy;
@@ -412,7 +419,7 @@ __global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(
             tp = t.g;
             const int4 bi = s_box[dd];
             const int lx0 = t.cx0 - bi.x, lx1 = t.cx1 - bi.x, ly0 = t.cy0 - bi.y, ly1 = t.cy1 - bi.y;
-            mbar_wait(&s_full[s], (unsigned)(k / NST) & 1u);        // the plane's boxes have landed
+            mbar_wait(&s_full[s], (use / NST) & 1u);                // the plane's boxes have landed
             if (tp.kind == 2 && lx0 >= 0 && lx1 < TMA_BW && ly0 >= 0 && ly1 < TMA_BH) {
                 const float4* tb = tiles + (size_t)(s * TF) * (TMA_BOX_BYTES / 16);
                 const int a00 = ly0 * TMA_BW + lx0, a10 = ly0 * TMA_BW + lx1, a01 = ly1 * TMA_BW + lx0, a11 = ly1 * TMA_BW + lx1;
@@ -518,7 +525,7 @@ __global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(
             Tr[f] *= om;
             gsta.x += gl.x; gsta.y += gl.y; gsta.z += gl.z; gsta.w += gl.w;   // static tiles: sum over frames (MPV.py:445)
             const float4 gl_up = shfl_up4(gl);
-            if (wr && tp.kind == 2 && !(p.dbg_nored & 1)) scatter_taps(gb[f], tp, gl, gl_up, wu10, wu11, sent0, sent1);
+            if (wr && tp.kind == 2) scatter_taps(gb[f], tp, gl, gl_up, wu10, wu11, sent0, sent1);
         }
         if (__any_sync(0xffffffffu, tp.kind == 1)) {
             const float4 gl_up = shfl_up4(gsta);
@@ -539,6 +546,13 @@ __global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(
             atomicAdd(&p.smooth[tx], acc);
         }
     }
+    if (use_tma) kbase += (unsigned)nplanes;
+}
+
+template <int TF, bool SMOOTH, int MODE>
+__global__ void __launch_bounds__(BX* BY, TF <= 2 ? 3 : 2) composite_bwd_kernel(const __grid_constant__ TmaRenderParams P) {
+    unsigned kbase = 0u;
+    bwd_tile<TF, SMOOTH, MODE>(P, (int)blockIdx.x, (int)blockIdx.y, P.p.tb + (int)blockIdx.z * TF, kbase, true);
 }
 
 }  // namespace vl3d

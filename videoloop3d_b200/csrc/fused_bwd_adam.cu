@@ -1,0 +1,256 @@
+// Fused composite backward + Adam for the dynamic atlas: ONE persistent kernel per optimisation step.
+//
+// Replaces (reference file:line): autograd's backward through MPV.py:413-451 / utils_mpi.py:92-107 / MPV.py:517-531
+// followed by `optimizer.zero_grad()` / `optimizer.step()` of train_3dvid.py:242-244 with
+// torch.optim.Adam(betas=(0.9,0.999), eps=6e-8) (MPV.py:200-218)  — SURVEY.md §8(f) N4.
+//
+// Why one kernel: as separate launches the texel gradient crosses HBM three times (zero-fill 22.6 GB written,
+// RED read-modify-write 43 GB, Adam read 22.6 GB at 720p / D=32 / T=48) and an issue-bound kernel (backward: 2.4 TB/s)
+// alternates with a DRAM-bound one (Adam: 6.3 TB/s).  Here resident CTAs pull work items from one ordered queue:
+//   BWD   one (screen tile, chunk of TF frames) of the backward — exactly composite_lean.cuh's bwd_tile;
+//   ADAM  Adam on a rectangle of texels (rows x width) of the chunk's frames: reads p, g, m, v; writes p, m, v; then
+//         either writes zeros back into g (the buffer is all-zero between steps: no separate fill) or, in the
+//         zero-ahead schedules, drops the gradient lines from L2 without write-back (discard.global.L2);
+//   ZERO  zero a rectangle of g shortly before the first tile that accumulates into it (full-line stores: the RED
+//         that follows hits L2 instead of fetching the line from DRAM).
+// so backward tiles (instruction issue) and Adam rectangles (DRAM) overlap on every SM, and — when the host orders the
+// items by screen band (dense layout) — a band's gradient rows are produced, consumed and dropped while L2-resident.
+//
+// The schedule is a host-built table (videoloop3d_b200/schedule.py): per item the work description, a range of
+// counters to wait for (each >= target) and a counter to bump when done.  An item only waits for items that precede
+// it in the queue, and items are claimed in queue order by running CTAs, so the waits cannot deadlock.  One table
+// describes one "round" (= one chunk of TF frames); the kernel replays it for every chunk, with per-chunk counters.
+#include "composite_common.cuh"
+#include "tma_common.cuh"
+#include "composite_lean.cuh"
+
+namespace vl3d {
+
+constexpr int FUSED_TF = 2;
+
+enum : int { ITEM_BWD = 0, ITEM_ADAM = 1, ITEM_ZERO = 2 };
+enum : int { FLAG_HAS_GRAD = 1, FLAG_REZERO = 2, FLAG_DISCARD = 4, FLAG_PREV_ROUND = 8, FLAG_ORDERED = 16 };
+
+struct alignas(64) FusedParams {
+    TmaRenderParams R;
+    const int4* items;     // [n_items][2]
+    int n_items, n_rounds, n_chunks, n_counters;
+    int* counters;         // [n_chunks][n_counters], initialised by the caller
+    int* ticket;           // queue head, zeroed by the caller
+    float4* m;
+    float4* v;
+    float b1, b2, step_size, inv_sqrt_bc2, eps;
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_inc(int* p) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ void discard_l2_128(const void* p) {
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
+
+// same arithmetic, in the same order, as adam_kernel (optim.cu)
+__device__ __forceinline__ void adam4(float4& pp, const float4 gg, float4& mm, float4& vv, const FusedParams& F) {
+#define VL3D_ADAM1(c)                                                       \
+    mm.c = F.b1 * mm.c + (1.f - F.b1) * gg.c;                               \
+    vv.c = F.b2 * vv.c + (1.f - F.b2) * gg.c * gg.c;                        \
+    pp.c -= F.step_size * (mm.c / (sqrtf(vv.c) * F.inv_sqrt_bc2 + F.eps));
+    VL3D_ADAM1(x) VL3D_ADAM1(y) VL3D_ADAM1(z) VL3D_ADAM1(w)
+#undef VL3D_ADAM1
+}
+
+// Adam on rows x width texels starting at texel `base` of frames [t0, t0 + FUSED_TF) (row stride = dyn_w).
+__device__ __forceinline__ void adam_rect(const FusedParams& F, const int t0, const int base, const int width, const int rows,
+                                          const int flags) {
+    const CompositeParams& p = F.R.p;
+    const int tid = threadIdx.y * BX + threadIdx.x;
+    const size_t frame = (size_t)p.view.dyn_h * p.view.dyn_w;
+    const int stride = p.view.dyn_w;
+    float4* const P0 = const_cast<float4*>(p.atlas_dyn) + (size_t)t0 * frame + base;
+    float4* const G0 = p.grad_dyn + (size_t)t0 * frame + base;
+    float4* const M0 = F.m + (size_t)t0 * frame + base;
+    float4* const V0 = F.v + (size_t)t0 * frame + base;
+    const bool has_grad = (flags & FLAG_HAS_GRAD) != 0;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < rows; ++r) {
+        const size_t ro = (size_t)r * stride;
+        for (int c0 = 0; c0 < width; c0 += BX * BY) {              // (warp-uniform trip count: __syncwarp below)
+            const int c = c0 + tid;
+            const bool in = c < width;
+            float4 pp[FUSED_TF], gg[FUSED_TF], mm[FUSED_TF], vv[FUSED_TF];
+#pragma unroll
+            for (int f = 0; f < FUSED_TF; ++f) {
+                const size_t o = (size_t)f * frame + ro + c;
+                pp[f] = mm[f] = vv[f] = gg[f] = zero4;
+                if (in) {
+                    pp[f] = __ldcs(P0 + o);
+                    mm[f] = __ldcs(M0 + o);
+                    vv[f] = __ldcs(V0 + o);
+                    if (has_grad) gg[f] = __ldcg(G0 + o);
+                }
+            }
+            if (has_grad && (flags & FLAG_DISCARD)) {
+                // every lane's gradient load has returned before the line is dropped (8 lanes share a 128-byte line)
+                float sink = gg[0].x + gg[FUSED_TF - 1].w;
+                asm volatile("" ::"f"(sink));
+                __syncwarp();
+                if (in && (c & 7) == 0) {
+#pragma unroll
+                    for (int f = 0; f < FUSED_TF; ++f) discard_l2_128(G0 + (size_t)f * frame + ro + c);
+                }
+            }
+            if (in) {
+#pragma unroll
+                for (int f = 0; f < FUSED_TF; ++f) {
+                    const size_t o = (size_t)f * frame + ro + c;
+                    adam4(pp[f], gg[f], mm[f], vv[f], F);
+                    __stcs(P0 + o, pp[f]);
+                    __stcs(M0 + o, mm[f]);
+                    __stcs(V0 + o, vv[f]);
+                    if (has_grad && (flags & FLAG_REZERO)) G0[o] = zero4;
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void zero_rect(const FusedParams& F, const int t0, const int base, const int width, const int rows) {
+    const CompositeParams& p = F.R.p;
+    const int tid = threadIdx.y * BX + threadIdx.x;
+    const size_t frame = (size_t)p.view.dyn_h * p.view.dyn_w;
+    const int stride = p.view.dyn_w;
+    float4* const G0 = p.grad_dyn + (size_t)t0 * frame + base;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < rows; ++r)
+        for (int c = tid; c < width; c += BX * BY) {
+#pragma unroll
+            for (int f = 0; f < FUSED_TF; ++f) G0[(size_t)f * frame + (size_t)r * stride + c] = zero4;
+        }
+}
+
+template <bool SMOOTH, int MODE>
+__global__ void __launch_bounds__(BX* BY, 3) fused_bwd_adam_kernel(const __grid_constant__ FusedParams F) {
+    __shared__ int s_item;
+    const int tid = threadIdx.y * BX + threadIdx.x;
+    const long long total = (long long)F.n_rounds * F.n_items;
+    unsigned kbase = 0u;
+    bool first = true;
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(F.ticket, 1);
+        __syncthreads();
+        const int I = s_item;
+        __syncthreads();
+        if (I >= total) break;
+        const int round = I / F.n_items, j = I - round * F.n_items;
+        const int4 a = __ldg(&F.items[2 * j]), b = __ldg(&F.items[2 * j + 1]);
+        const int type = a.x & 15, flags = a.x >> 4;
+        const int chunk = round - ((flags & FLAG_PREV_ROUND) ? 1 : 0);
+        if (chunk < 0 || chunk >= F.n_chunks) continue;
+        int* const cnt = F.counters + (size_t)chunk * F.n_counters;
+        if (b.y > 0) {                                              // wait: counters [b.x, b.x + b.y) >= b.z
+            if (tid < 32) {
+                unsigned ns = 32;
+                for (;;) {
+                    bool ok = true;
+                    for (int i = tid; i < b.y; i += 32) ok = ok && (ld_acquire_gpu(cnt + b.x + i) >= b.z);
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    __nanosleep(ns);
+                    if (ns < 1024) ns *= 2;
+                }
+            }
+            __syncthreads();
+        }
+        const int t0 = chunk * FUSED_TF;
+        if (type == ITEM_BWD) {
+            bwd_tile<FUSED_TF, SMOOTH, MODE>(F.R, a.y, a.z, t0, kbase, first);
+            first = false;
+        } else if (type == ITEM_ADAM) {
+            adam_rect(F, t0, a.y, a.z, a.w, flags);
+        } else {
+            zero_rect(F, t0, a.y, a.z, a.w);
+        }
+        if (b.w >= 0) {                                             // signal: this item's writes / REDs are visible
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                if (flags & FLAG_ORDERED) {                         // in-order commit: item number b.z of this counter
+                    while (ld_acquire_gpu(cnt + b.w) != b.z) __nanosleep(32);
+                }
+                red_release_gpu_inc(cnt + b.w);
+            }
+        }
+    }
+}
+
+template <bool SMOOTH, int MODE>
+static int launch_fused(const FusedParams& F, int ctas_per_sm, cudaStream_t st) {
+    const size_t smem = MODE >= 2 ? (size_t)BWD_TMA_STAGES * FUSED_TF * TMA_BOX_BYTES : 0;
+    auto kern = fused_bwd_adam_kernel<SMOOTH, MODE>;
+    if (smem) {
+        cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce != cudaSuccess) return set_err((int)ce, "fused_bwd_adam: cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
+    }
+    int dev = 0, sms = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BX * BY, smem);
+    if (occ < 1) return set_err(VL3D_EINVAL, "fused_bwd_adam: kernel does not fit on an SM");
+    if (ctas_per_sm >= 1 && ctas_per_sm < occ) occ = ctas_per_sm;
+    long long grid = (long long)sms * occ;
+    const long long total = (long long)F.n_rounds * F.n_items;
+    if (grid > total) grid = total;
+    kern<<<(unsigned)grid, dim3(BX, BY), smem, st>>>(F);
+    return check_launch("fused_bwd_adam");
+}
+
+}  // namespace vl3d
+
+using namespace vl3d;
+
+extern "C" int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads, float* atlas_dyn, const float* atlas_sta,
+                                   int32_t T, const float* grad_rgb, const float* rgb, const float* w_smooth,
+                                   double* smooth_sums, float* grad_dyn, float* grad_sta, float* adam_m, float* adam_v,
+                                   int32_t step, float lr, float beta1, float beta2, float eps, const int32_t* items,
+                                   int32_t n_items, int32_t n_rounds, int32_t* counters, int32_t n_counters,
+                                   int32_t* ticket, int32_t ctas_per_sm, void* stream) {
+    if (int e = validate_view(view, quads, atlas_dyn, atlas_sta)) return e;
+    VL3D_REQUIRE(grad_rgb && rgb && grad_dyn && adam_m && adam_v && atlas_dyn, VL3D_ENULL, "fused_bwd_adam: NULL pointer");
+    VL3D_REQUIRE(grad_sta != nullptr || atlas_sta == nullptr, VL3D_ENULL, "grad_sta is NULL");
+    VL3D_REQUIRE(items && counters && ticket, VL3D_ENULL, "fused_bwd_adam: schedule pointers are NULL");
+    VL3D_REQUIRE(T >= FUSED_TF && T % FUSED_TF == 0, VL3D_EINVAL, "fused_bwd_adam: T=%d must be a positive multiple of %d", T, FUSED_TF);
+    VL3D_REQUIRE(n_items >= 1 && n_counters >= 1 && n_rounds >= T / FUSED_TF && n_rounds <= T / FUSED_TF + 1, VL3D_EINVAL,
+                 "fused_bwd_adam: bad schedule (n_items=%d n_rounds=%d n_counters=%d)", n_items, n_rounds, n_counters);
+    VL3D_REQUIRE(step >= 1, VL3D_EINVAL, "fused_bwd_adam: step=%d", step);
+    VL3D_REQUIRE((((uintptr_t)grad_dyn | (uintptr_t)grad_sta | (uintptr_t)adam_m | (uintptr_t)adam_v | (uintptr_t)items) & 15) == 0,
+                 VL3D_EALIGN, "fused_bwd_adam: pointers must be 16-byte aligned");
+    FusedParams F{};
+    CompositeParams& p = F.R.p;
+    p.view = *view; p.quads = quads;
+    p.atlas_dyn = reinterpret_cast<const float4*>(atlas_dyn);
+    p.atlas_sta = reinterpret_cast<const float4*>(atlas_sta);
+    p.ts = nullptr; p.T = T; p.pad = 0; p.tb = 0;
+    p.grad_rgb = grad_rgb; p.rgb = rgb;
+    p.grad_dyn = reinterpret_cast<float4*>(grad_dyn); p.grad_sta = reinterpret_cast<float4*>(grad_sta);
+    p.w_smooth = w_smooth; p.smooth = smooth_sums;
+    VL3D_REQUIRE(w_smooth != nullptr || smooth_sums == nullptr, VL3D_EINVAL, "smooth_sums needs w_smooth");
+    F.items = reinterpret_cast<const int4*>(items);
+    F.n_items = n_items; F.n_rounds = n_rounds; F.n_chunks = T / FUSED_TF; F.n_counters = n_counters;
+    F.counters = counters; F.ticket = ticket;
+    F.m = reinterpret_cast<float4*>(adam_m); F.v = reinterpret_cast<float4*>(adam_v);
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    F.b1 = beta1; F.b2 = beta2; F.eps = eps;
+    F.step_size = (float)((double)lr / bc1);
+    F.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool smooth = w_smooth != nullptr;
+    if (smooth && (view->flags & VL3D_VIEW_RECT_PLANES) && make_atlas_tmap(&F.R.tmap, p.view, atlas_dyn, T))
+        return launch_fused<true, 3>(F, ctas_per_sm, st);
+    if (smooth) return launch_fused<true, 0>(F, ctas_per_sm, st);
+    return launch_fused<false, 0>(F, ctas_per_sm, st);
+}

@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(SCALE_THREADS) scale_partial_kernel(const floa
         float sr = 0.f, sx = 0.f;
         for (int f = 0; f < F; ++f) sr += __ldg(res + (size_t)f * chw + i);
         for (int t = 0; t < T; ++t) sx += __ldg(rgb + (size_t)t * chw + i);
-        acc += __logf((sr / (float)F + 0.01f) / (sx / (float)T + 0.01f));
+        acc += logf((sr / (float)F + 0.01f) / (sx / (float)T + 0.01f));       // torch.log (MPV.py:499-504), not the approximate intrinsic
     }
     __shared__ float s_part[SCALE_THREADS / 32];
     acc = warp_sum(acc);
@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(SCALE_THREADS) scale_partial_presum_kernel(con
     for (size_t i = (size_t)blockIdx.x * SCALE_THREADS + threadIdx.x; i < chw; i += (size_t)gridDim.x * SCALE_THREADS) {
         float sx = 0.f;
         for (int t = 0; t < T; ++t) sx += __ldg(rgb + (size_t)t * chw + i);
-        acc += __logf((__ldg(res_sum + i) / (float)F + 0.01f) / (sx / (float)T + 0.01f));
+        acc += logf((__ldg(res_sum + i) / (float)F + 0.01f) / (sx / (float)T + 0.01f));
     }
     __shared__ float s_part[SCALE_THREADS / 32];
     acc = warp_sum(acc);
@@ -863,6 +863,16 @@ static int validate_desc(const vl3d_loss_desc* L) {
     return 0;
 }
 
+// tuning knobs (scripts/tune_search.py), read from the environment ONCE per process
+struct Knobs { bool tile8, tma, vote_v1; int sl; };
+static const Knobs& knobs() {
+    static const Knobs k = [] {
+        auto geti = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
+        return Knobs{geti("VL3D_NN_TILE8", 1) != 0, geti("VL3D_NN_TMA", 1) != 0, geti("VL3D_VOTE_V1", 0) != 0, geti("VL3D_NN_SL", 0)};
+    }();
+    return k;
+}
+
 }  // namespace vl3d
 
 using namespace vl3d;
@@ -880,12 +890,12 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
     if (tx_used <= NN_CF && M <= 3 && desc->p <= 32) {
         // strip kernel: rows shared between vertically overlapping patches
         {   // 4 x 8 register tiles (patchnn_strip8.cuh) for the common shapes; VL3D_NN_TILE8=0: tuning aid
-            const char* t8 = getenv("VL3D_NN_TILE8");
+            const bool tile8 = knobs().tile8;
             const int P4 = (desc->p + 3) / 4 * 4;
             const bool vec = desc->s % 4 == 0 && (3 * desc->p + 3) / 4 == 3 * P4 / 4 &&
                              ((desc->x_sf | desc->x_sc | desc->x_sr | desc->y_sf | desc->y_sc | desc->y_sr) & 3) == 0 &&
                              (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
-            if (vec && M >= 1 && M <= 3 && !(t8 && atoi(t8) == 0)) {
+            if (vec && M >= 1 && M <= 3 && tile8) {
                 StripParams P{};
                 P.d = *desc; P.x = x; P.y = y; P.nn = nn_out; P.groups = 3 * (P4 / 4);
                 P.row0 = row_begin; P.row1 = row_end;
@@ -895,7 +905,7 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
                 // strip length: long strips share more rows between patches (measured at 720p: 8 / 16 / 24 / 32 patches
                 // per strip = 21.3 / 20.2 / 19.8 / 22.0 ms), balanced so that the last strip is not a stub
                 int SL = 24;
-                { const char* e = getenv("VL3D_NN_SL"); if (e && atoi(e) >= 2) SL = atoi(e); }   // tuning aid
+                if (knobs().sl >= 2) SL = knobs().sl;                   // tuning aid
                 while (SL > 2 && (long long)desc->wo * ((rows + SL - 1) / SL) < 148 * 6) SL >>= 1;
                 SL = (rows + (rows + SL - 1) / SL - 1) / ((rows + SL - 1) / SL);
                 if (SL > rows) SL = rows;
@@ -913,9 +923,8 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
                 const int nch = P4 / 4;
                 Strip8Params PP;
                 // TMA staging (VL3D_NN_TMA=0: tuning aid); the box carries nch | 1 chunks per channel
-                const char* tenv = getenv("VL3D_NN_TMA");
                 const bool fits = best_ntb && smem <= 110 * 1024 && desc->n1 <= S8_TI * P.nta;
-                const bool tma = fits && !(tenv && atoi(tenv) == 0) &&
+                const bool tma = fits && knobs().tma &&
                                  make_video_tmap(&PP.tx, x, desc->x_sf, desc->x_sc, desc->x_sr, tx_used, nch | 1, S8_TI * P.nta) &&
                                  make_video_tmap(&PP.ty, y, desc->y_sf, desc->y_sc, desc->y_sr,
                                                  (desc->n2 - 1) * desc->st + desc->pt, nch | 1, S8_TJ * P.ntb);
@@ -1026,8 +1035,8 @@ extern "C" int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const 
     cudaStream_t st = (cudaStream_t)stream;
     // covering patches per axis: at most ceil(p/s) (space) and ceil(pt/st) (time)
     const int ms = (desc->p + desc->s - 1) / desc->s, mt = (desc->pt + desc->st - 1) / desc->st;
-    const char* v1 = getenv("VL3D_VOTE_V1");                         // tuning aid: the one-gather-at-a-time kernel
-    const bool batched = !(v1 && atoi(v1) != 0);
+    const bool vote_v1 = knobs().vote_v1;                             // tuning aid: the one-gather-at-a-time kernel
+    const bool batched = !vote_v1;
     if (batched && ms <= 2 && mt <= 3) vote_loss_batched_kernel<2, 2, 3><<<grid, VOTE_THREADS, 0, st>>>(P);
     else if (batched && ms <= 3 && mt <= 3) vote_loss_batched_kernel<3, 3, 3><<<grid, VOTE_THREADS, 0, st>>>(P);
     else vote_loss_kernel<<<grid, VOTE_THREADS, 0, st>>>(P);

@@ -24,7 +24,7 @@ import torch.nn.functional as F
 from . import ops
 from ._lib import Vl3dError
 from .loop_loss import (Patch3DAvg, Patch3DGPNNDirectLoss, Patch3DGPNNLowMemDownSampleLoss, Patch3DGPNNLowMemLoss,
-                        Patch3DMSE)
+                        Patch3DMSE, _check_dist)
 from .optim import FusedAdam
 
 
@@ -91,6 +91,22 @@ class LazyVariables(dict):
         if k in self._LAZY:
             self._materialise()
         return dict.__getitem__(self, k)
+
+    # every other way of reading a value materialises too (a `None` placeholder must never leak out)
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+    def items(self):
+        self._materialise()
+        return dict.items(self)
+
+    def values(self):
+        self._materialise()
+        return dict.values(self)
+
+    def copy(self):
+        self._materialise()
+        return dict(dict.items(self))
 
 
 class MPMeshVid(nn.Module):
@@ -193,6 +209,15 @@ class MPMeshVid(nn.Module):
 
     def invalidate_geometry(self):
         self._pack = None
+        self._ref_inv = None
+
+    def ref_extrin_inv_host(self):
+        """inverse of `ref_extrin` as a float64 host array, cached until the geometry is invalidated (the per-step
+        `extrin = tar_extrin @ ref_extrin^-1` of MPV.py:478 then needs no device round trip)."""
+        key = (self.ref_extrin.data_ptr(), self.ref_extrin._version)
+        if getattr(self, "_ref_inv", None) is None or self._ref_inv[0] != key:
+            self._ref_inv = (key, np.linalg.inv(self.ref_extrin.detach().double().cpu().numpy()))
+        return self._ref_inv[1]
 
     def _texels(self):
         """Keep both atlases in the RGBA-interleaved layout (re-home them once if something replaced
@@ -262,7 +287,9 @@ class MPMeshVid(nn.Module):
     def forward(self, h, w, tar_extrins, tar_intrins, ts=None, res=None, losscfg=None):
         """Train: (None, {swd, rgb_smooth, a_smooth}) each (1,1); eval: (rgb (T,3,H,W), {})
         (reference: MPV.py:477-556)."""
-        extrins = tar_extrins @ self.ref_extrin[None, ...].inverse().to(tar_extrins)
+        # MPV.py:478, evaluated in float64 on the host (where the view descriptor is built)
+        tar = tar_extrins.detach().double().cpu().numpy() if torch.is_tensor(tar_extrins) else np.asarray(tar_extrins, np.float64)
+        extrins = tar.reshape(-1, 4, 4)[:1] @ self.ref_extrin_inv_host()
         if not self.training:
             rgb, _, _, _, _, _ = self._render_planar(h, w, extrins, tar_intrins, ts)
             return rgb, {}
@@ -273,6 +300,7 @@ class MPMeshVid(nn.Module):
             if getattr(args, f"{k}_loss_weight", 0) > 0:
                 raise NotImplementedError(f"{k}_loss_weight > 0 is used by no stage-2 config and is not supported")
         cfg = {k: (v[0].item() if torch.is_tensor(v) else v[0]) for k, v in losscfg.items()}   # MPV.py:494
+        _check_dist(cfg)
         loss_name = cfg.pop('loss_name')
         loss_gain = float(cfg.pop('loss_gain', 1.))
         loss = self.losses[loss_name]

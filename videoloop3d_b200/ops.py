@@ -52,6 +52,7 @@ class MeshPack:
     n_static: int
     n_dynamic: int
     rect_planes: bool = False    # dense layout: one atlas rectangle per plane (enables the TMA render)
+    table: np.ndarray = None     # host copy of the quad table (schedule.band_schedule reads the plane rectangles)
 
 
 def make_mesh_pack(model_tensors, D, hv, wv, device):
@@ -62,7 +63,7 @@ def make_mesh_pack(model_tensors, D, hv, wv, device):
     q = torch.from_numpy(table.view(np.uint8).copy()).to(device)
     return MeshPack(quads=q, grids=grids, D=D, qh=hv - 1, qw=wv - 1,
                     n_static=int((table["kind"] == 1).sum()), n_dynamic=int((table["kind"] == 2).sum()),
-                    rect_planes=tiles.planes_are_rectangles(table, D, hv - 1, wv - 1))
+                    rect_planes=tiles.planes_are_rectangles(table, D, hv - 1, wv - 1), table=table)
 
 
 def make_view(pack: MeshPack, H, W, tar_extrin, tar_intrin, ref_extrin, dyn_hw, sta_hw):
@@ -263,6 +264,23 @@ def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=6e-8):
             raise _lib.Vl3dError("adam_step: p, g, m, v must share shape and strides")
     _lib.call("vl3d_adam_step", _lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), int(p.numel()), int(step),
               float(lr), float(beta1), float(beta2), float(eps), _lib.stream_ptr())
+
+
+def fused_bwd_adam(view, pack, atlas_dyn, atlas_sta, T, grad_rgb, rgb, w_smooth, smooth_sums, grad_dyn, grad_sta, m, v,
+                   step, lr, beta1, beta2, eps, items, n_items, n_rounds, state, n_counters, ctas_per_sm=0):
+    """Backward + Adam of `atlas_dyn[:T]` in one persistent kernel (csrc/fused_bwd_adam.cu).  `items`: device int32
+    (n_items, 8) table from schedule.py; `state`: device int32 scratch, zeroed by the caller: [0] = queue head,
+    [16:] = n_rounds x n_counters counters."""
+    for t in (grad_dyn, m, v):
+        if tuple(t.stride()) != tuple(atlas_dyn.stride()) or t.shape != atlas_dyn.shape:
+            raise _lib.Vl3dError("fused_bwd_adam: atlas_dyn, grad_dyn, m, v must share shape and strides")
+    if items.dtype != torch.int32 or state.dtype != torch.int32 or state.numel() < 16 + n_rounds * n_counters:
+        raise _lib.Vl3dError("fused_bwd_adam: bad schedule buffers")
+    _lib.call("vl3d_fused_bwd_adam", C.byref(view), _lib.ptr(pack.quads), _lib.ptr(atlas_dyn), _lib.ptr(atlas_sta), int(T),
+              _lib.ptr(grad_rgb), _lib.ptr(rgb), _lib.ptr(w_smooth), _lib.ptr(smooth_sums), _lib.ptr(grad_dyn),
+              _lib.ptr(grad_sta), _lib.ptr(m), _lib.ptr(v), int(step), float(lr), float(beta1), float(beta2), float(eps),
+              _lib.ptr(items), int(n_items), int(n_rounds), C.c_void_p(state.data_ptr() + 64), int(n_counters),
+              _lib.ptr(state), int(ctas_per_sm), _lib.stream_ptr())
 
 
 # ------------------------------------------------------------------------------------------------

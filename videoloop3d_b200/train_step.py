@@ -18,9 +18,11 @@ from argparse import Namespace
 import numpy as np
 import torch
 
-from . import ops
+import os
+
+from . import ops, schedule
 from ._lib import Vl3dError
-from .loop_loss import Patch3DGPNNDirectLoss, Patch3DGPNNLowMemLoss
+from .loop_loss import Patch3DGPNNDirectLoss, Patch3DGPNNLowMemLoss, _check_dist
 from .mpv import MPMeshVid, pose2extrin_torch
 
 
@@ -153,7 +155,15 @@ class FusedLoopStep:
     """
 
     def __init__(self, model: MPMeshVid, group=None, betas=(0.9, 0.999), eps=6e-8, global_frames=None, timers=False,
-                 overlap_chunks=1):
+                 overlap_chunks=1, fused=None, fused_opts=None):
+        """`fused`: how backward + Adam of the dynamic atlas run —
+        "off": separate kernels (zero-fill, vl3d_composite_bwd, vl3d_adam_step);
+        "generic": one persistent kernel, tiles of chunk c interleaved with Adam of chunk c-1 (any layout);
+        "band" / "band-zero": the same kernel walking the screen in row bands so that a band's gradient rows stay
+        L2-resident between accumulation and Adam (dense layout only; "-zero": rows are zeroed just ahead of the
+        band and dropped after Adam instead of living in HBM as zeros);
+        None: VL3D_FUSED from the environment (read once, here), else "auto" = band-zero for the dense layout,
+        generic otherwise."""
         if not model.atlas_dyn.is_cuda:
             raise Vl3dError("FusedLoopStep needs the model on a CUDA device")
         self.model = model
@@ -181,6 +191,16 @@ class FusedLoopStep:
         # gains), so the default is 1 (off).
         self.overlap_chunks = max(1, int(overlap_chunks))
         self._side = torch.cuda.Stream(device=model.atlas_dyn.device)
+        self.fused = (fused or os.environ.get("VL3D_FUSED", "auto")).lower()
+        if self.fused not in ("off", "generic", "band", "band-zero", "auto"):
+            raise ValueError(f"fused={self.fused!r}")
+        self.fused_opts = dict(fused_opts or {})
+        for k, cast in (("ctas_per_sm", int), ("row_block", int), ("zero_ahead", int), ("adam_lag", int), ("seg_texels", int)):
+            e = os.environ.get("VL3D_FUSED_" + k.upper())
+            if e is not None and k not in self.fused_opts:
+                self.fused_opts[k] = cast(e)
+        self._sched_cache = {}
+        self.last_schedule = None
 
     def _timed(self, name):
         return _Timed(self.timers, name)
@@ -213,6 +233,27 @@ class FusedLoopStep:
             self._buf[key] = b
         return b
 
+    def _schedule_for(self, mode, view, pack, h, w, smooth, dyn_hw):
+        """Work-item table of the fused kernel for this view (cached: a table depends on the view only)."""
+        key = (mode, bytes(view), bool(smooth), tuple(dyn_hw))
+        sched = self._sched_cache.get(key)
+        if sched is None:
+            o = self.fused_opts
+            if mode == "generic":
+                sched = schedule.generic_schedule(h, w, dyn_hw[0], dyn_hw[1], smooth, seg_texels=o.get("seg_texels", 32768))
+            else:
+                homs = np.ctypeslib.as_array(view.hom).reshape(-1)[:pack.D * 9].astype(np.float64)
+                sched = schedule.band_schedule(homs, view.cx, view.cy, h, w, pack.table, pack.D, pack.qh, pack.qw, dyn_hw[0],
+                                               dyn_hw[1], smooth, row_block=o.get("row_block", 8),
+                                               zero_ahead=o.get("zero_ahead", 2), adam_lag=o.get("adam_lag", 2),
+                                               use_zero=(mode == "band-zero"))
+            sched.dev_items = torch.from_numpy(sched.items).to(self.model.atlas_dyn.device)
+            if len(self._sched_cache) >= 8:
+                self._sched_cache.pop(next(iter(self._sched_cache)))
+            self._sched_cache[key] = sched
+        self.last_schedule = sched
+        return sched
+
     def _adam(self, name, p, g, lr):
         st = self._state.get(name)
         if st is None:
@@ -238,6 +279,7 @@ class FusedLoopStep:
         lossobj = m.losses[loss_name]
         if not isinstance(lossobj, (Patch3DGPNNLowMemLoss, Patch3DGPNNDirectLoss)):
             raise NotImplementedError(f"FusedLoopStep supports the gpnn / gpnn_lm losses, not {loss_name!r}")
+        _check_dist(cfg)
         T, t0, t1 = self.T, self.t0, self.t1
         Tl = t1 - t0
         pad = m.swd_patcht_size - 1 if m.isloop else 0
@@ -247,8 +289,9 @@ class FusedLoopStep:
         res_u8 = res0 if res0.dtype == torch.uint8 else None       # bytes from the loader: converted after `res_ready`
         if res_u8 is None and not res0.is_contiguous():
             res0 = res0.contiguous()
-        ext = tar_extrin.reshape(4, 4).double().cpu().numpy() @ np.linalg.inv(m.ref_extrin.double().cpu().numpy())
-        view = m.make_view(h, w, ext, tar_intrin)
+        # pose / intrinsics are host data (the view descriptor is built on the host); a device tensor costs a sync here
+        ext = _host64(tar_extrin).reshape(4, 4) @ m.ref_extrin_inv_host()
+        view = m.make_view(h, w, ext, _host64(tar_intrin))
         pack = m._pack
         wr, wa = args.rgb_smooth_loss_weight, args.a_smooth_loss_weight
         smooth = wr > 0 or wa > 0
@@ -363,45 +406,60 @@ class FusedLoopStep:
         if not optimise:
             return assemble()
 
-        # ---- backward into persistent gradient buffers, then Adam on the owned frames
-        g_dyn = self._like("g_dyn", dyn_local)
+        # ---- backward + Adam on the owned frames
         g_sta = self._like("g_sta", atlas.data)
-        main = torch.cuda.current_stream()
-        with self._timed("grad_zero"):      # (overlapping this memset with the NN search on a side stream was
-            g_dyn.zero_()                   #  measured to give nothing: the search slows down by the same amount)
-            g_sta.zero_()
+        if pack.n_static > 0:
+            with self._timed("grad_sta_zero"):
+                g_sta.zero_()
         bwd_sums = sums[:4] if smooth else None
         # adjoint of the loop pad for the frames we own, so the backward can run per frame chunk with pad = 0
         if pad and t0 < pad:
             n = min(t1, pad) - t0
             grad_rgb[t0:t0 + n] += grad_rgb[T + t0:T + t0 + n]
-        self.t += 1
-        nch = min(self.overlap_chunks, Tl)
-        cb = partition(Tl, nch)
         st = self._state.get("atlas_dyn")
+        if st is not None and st[0].shape != dyn_local.shape:      # lod() changed the atlas: fresh optimiser state
+            self.reset()
+            st = None
         if st is None:
             st = (torch.zeros_like(dyn_local), torch.zeros_like(dyn_local))
             self._state["atlas_dyn"] = st
-        for c in range(nch):
-            a, b = cb[c], cb[c + 1]
+        self.t += 1
+        mode = self.fused
+        if mode == "auto":
+            mode = "band-zero" if pack.rect_planes else "generic"
+        if mode.startswith("band") and not pack.rect_planes:
+            mode = "generic"
+        Te = Tl // 2 * 2 if mode != "off" else 0                   # frames handled by the fused kernel (chunks of 2)
+        if Te > 0:
+            sched = self._schedule_for(mode, view, pack, h, w, smooth, dyn_local.shape[-2:])
+            n_rounds = Te // 2 + (1 if sched.extra_round else 0)
+            g_dyn = self._buf.get("g_dyn")
+            if g_dyn is None or g_dyn.shape != dyn_local.shape or tuple(g_dyn.stride()) != tuple(dyn_local.stride()):
+                g_dyn = torch.zeros_like(dyn_local)                # all-zero between steps (the kernel keeps it so)
+                self._buf["g_dyn"] = g_dyn
+            state = self._get("fused_state", (16 + n_rounds * sched.n_counters,), torch.int32)
+            state.zero_()
+            with self._timed("fused_bwd_adam"):
+                ops.fused_bwd_adam(view, pack, dyn_local[:Te], atlas.data, Te, grad_rgb[t0:t0 + Te], rgb_pad[t0:t0 + Te],
+                                   w_smooth, bwd_sums, g_dyn[:Te], g_sta, st[0][:Te], st[1][:Te], self.t, lr,
+                                   self.betas[0], self.betas[1], self.eps, sched.dev_items, sched.n_items, n_rounds,
+                                   state, sched.n_counters, ctas_per_sm=self.fused_opts.get("ctas_per_sm", 0))
+        if Te < Tl:
+            # separate kernels: everything when fused == "off", else the odd last frame
+            g_dyn = self._buf.get("g_dyn")
+            if g_dyn is None or g_dyn.shape != dyn_local.shape or tuple(g_dyn.stride()) != tuple(dyn_local.stride()):
+                g_dyn = torch.zeros_like(dyn_local)
+                self._buf["g_dyn"] = g_dyn
+            with self._timed("grad_zero"):
+                g_dyn[Te:].zero_()
             with self._timed("composite_bwd"):
-                ops.composite_bwd(view, pack, dyn_local[a:b], atlas.data, None, b - a, 0, grad_rgb[t0 + a:t0 + b],
-                                  rgb_pad[t0 + a:t0 + b], w_smooth, g_dyn[a:b], g_sta, smooth_sums=bwd_sums)
-            if nch > 1:
-                ev = torch.cuda.Event()
-                ev.record(main)
-                with torch.cuda.stream(self._side):
-                    self._side.wait_event(ev)
-                    ops.adam_step(dyn_local[a:b], g_dyn[a:b], st[0][a:b], st[1][a:b], self.t, lr, self.betas[0],
-                                  self.betas[1], self.eps)
-            else:
-                with self._timed("adam"):
-                    ops.adam_step(dyn_local[a:b], g_dyn[a:b], st[0][a:b], st[1][a:b], self.t, lr, self.betas[0],
-                                  self.betas[1], self.eps)
-        if nch > 1:
-            done = torch.cuda.Event()
-            done.record(self._side)
-            main.wait_event(done)
+                ops.composite_bwd(view, pack, dyn_local[Te:], atlas.data, None, Tl - Te, 0, grad_rgb[t0 + Te:t1],
+                                  rgb_pad[t0 + Te:t1], w_smooth, g_dyn[Te:], g_sta, smooth_sums=bwd_sums)
+            with self._timed("adam"):
+                ops.adam_step(dyn_local[Te:], g_dyn[Te:], st[0][Te:], st[1][Te:], self.t, lr, self.betas[0],
+                              self.betas[1], self.eps)
+            if Te > 0 and not mode.endswith("zero"):
+                g_dyn[Te:].zero_()                                  # keep the fused kernel's all-zero invariant
         if pack.n_static > 0:
             if self.world > 1:
                 with self._timed("allreduce_static_grad"):
@@ -409,6 +467,13 @@ class FusedLoopStep:
             with self._timed("adam_static"):
                 self._adam("atlas", atlas.data, g_sta, lr)
         return assemble()
+
+
+def _host64(a):
+    """float64 numpy copy of a pose / intrinsics argument (host tensors and arrays: no device sync)."""
+    if torch.is_tensor(a):
+        return a.detach().double().cpu().numpy()
+    return np.asarray(a, dtype=np.float64)
 
 
 class _Timed:
