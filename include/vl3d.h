@@ -178,11 +178,12 @@ int vl3d_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int3
 /* ---- fused backward + Adam (train_3dvid.py:242-244 `zero_grad / backward / step` for atlas_dyn) ----
  * One persistent kernel: the tiles of vl3d_composite_bwd (pad = 0, ts = NULL) and Adam (vl3d_adam_step's arithmetic)
  * on rectangles of atlas_dyn, pulled from ONE ordered work queue described by `items` (host-built, see
- * videoloop3d_b200/schedule.py; n_items x 8 int32 = {type | flags << 4, a, b, c, wait_first, wait_count, wait_target,
- * signal}: type 0 = tile (a, b) of chunk frames, 1 = Adam / 2 = zero-gradient on `c` rows x `b` texels starting at texel
- * `a` of each frame of the chunk, row stride dyn_w).  The table describes one round = one chunk of 2 frames and is
+ * videoloop3d_b200/schedule.py; n_items x 12 int32 = {type | flags << 4, a, b, c; wait_first, wait_count, wait_target,
+ * signal; wait2_first, wait2_count, wait2_target, 0}: type 0 = tile (a, b) of chunk frames, 1 = Adam / 2 = zero-gradient
+ * on `c` rows x `b` texels starting at texel `a` of each frame of the chunk, row stride dyn_w; an item starts when
+ * every counter of its two wait ranges has reached the range's target and bumps counter `signal` when done).  The table describes one round = one chunk of 2 frames and is
  * replayed for T/2 chunks (`n_rounds` = T/2, or T/2 + 1 when items are flagged "previous round").
- * T must be even.  counters: n_rounds' worth of n_counters int32 (zeroed by the caller), ticket: one int32 (zeroed).
+ * T must be even.  counters: n_rounds' worth of n_counters int32 (initialised by the caller), ticket: one int32 (zeroed).
  * grad_dyn: in schedules whose Adam items re-zero it, it must be all-zero on entry and is all-zero on exit; in
  * zero-ahead schedules its content on entry / exit is irrelevant.  grad_sta is accumulated into as in vl3d_composite_bwd
  * (the static atlas is optimised by the caller after its all-reduce).  atlas_dyn, adam_m, adam_v are updated in place.

@@ -257,17 +257,22 @@ __device__ __forceinline__ float sgn2(float c, float a, float b) {   // sign(c-a
 // scatter one sample gradient `gl` (w.r.t. the pre-sigmoid bilinear sample) to its four taps.  Lane i's
 // right-hand taps usually are lane i+1's left-hand taps: then the contribution travels by shuffle (gl_up
 // with the sender's weights wu10 / wu11, zero if nothing is received) and is folded into the receiver's RED.
+template <bool STICKY = false>
 __device__ __forceinline__ void scatter_taps(float4* gb, const Geo& tp, const float4& gl, const float4& gl_up, float wu10,
                                              float wu11, bool sent0, bool sent1) {
+    auto red = [](float4* a, float4 v) {
+        if (STICKY) red_add_v4_hint(a, v, 0x14F0000000000000ull);   // L2 evict_last: the line is consumed soon (fused pass)
+        else red_add_v4(a, v);
+    };
     float4 l0, l1;
     l0.x = fmaf(gl_up.x, wu10, gl.x * tp.w00); l0.y = fmaf(gl_up.y, wu10, gl.y * tp.w00);
     l0.z = fmaf(gl_up.z, wu10, gl.z * tp.w00); l0.w = fmaf(gl_up.w, wu10, gl.w * tp.w00);
     l1.x = fmaf(gl_up.x, wu11, gl.x * tp.w01); l1.y = fmaf(gl_up.y, wu11, gl.y * tp.w01);
     l1.z = fmaf(gl_up.z, wu11, gl.z * tp.w01); l1.w = fmaf(gl_up.w, wu11, gl.w * tp.w01);
-    red_add_v4(gb + tp.o00, l0);
-    red_add_v4(gb + tp.o01, l1);
-    if (!sent0) red_add_v4(gb + tp.o10, make_float4(gl.x * tp.w10, gl.y * tp.w10, gl.z * tp.w10, gl.w * tp.w10));
-    if (!sent1) red_add_v4(gb + tp.o11, make_float4(gl.x * tp.w11, gl.y * tp.w11, gl.z * tp.w11, gl.w * tp.w11));
+    red(gb + tp.o00, l0);
+    red(gb + tp.o01, l1);
+    if (!sent0) red(gb + tp.o10, make_float4(gl.x * tp.w10, gl.y * tp.w10, gl.z * tp.w10, gl.w * tp.w10));
+    if (!sent1) red(gb + tp.o11, make_float4(gl.x * tp.w11, gl.y * tp.w11, gl.z * tp.w11, gl.w * tp.w11));
 }
 
 __device__ __forceinline__ float4 shfl_up4(const float4& v) {
@@ -289,7 +294,8 @@ __device__ __forceinline__ float4 shfl_up4(const float4& v) {
 // CTA's first tile (initialises the mbarriers).  Callers separate two tiles by a __syncthreads().
 constexpr int BWD_TMA_STAGES = 3;
 
-template <int TF, bool SMOOTH, int MODE>
+// HINTS (fused pass): bit 0 = atlas boxes are streamed (TMA loads evict_first), bit 1 = texel-gradient REDs evict_last.
+template <int TF, bool SMOOTH, int MODE, int HINTS = 0>
 __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx, const int by, const int t0, unsigned& kbase,
                                          const bool first) {
     const CompositeParams& p = P.p;
@@ -388,8 +394,13 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
         const int4 bi = s_box[di];
         mbar_arrive_expect_tx(&s_full[s], TF * TMA_BOX_BYTES);
 #pragma unroll
-        for (int f = 0; f < TF; ++f)
-            tma_load_3d(tiles + (size_t)(s * TF + f) * (TMA_BOX_BYTES / 16), &P.tmap, &s_full[s], bi.x * 4, bi.y, t0 + f);
+        for (int f = 0; f < TF; ++f) {
+            if (HINTS & 1)
+                tma_load_3d_hint(tiles + (size_t)(s * TF + f) * (TMA_BOX_BYTES / 16), &P.tmap, &s_full[s], bi.x * 4, bi.y, t0 + f,
+                                 L2_EVICT_FIRST);
+            else
+                tma_load_3d(tiles + (size_t)(s * TF + f) * (TMA_BOX_BYTES / 16), &P.tmap, &s_full[s], bi.x * 4, bi.y, t0 + f);
+        }
         ++k_issue;
     };
     if (use_tma && tx == 0 && ty == 0) {
@@ -525,7 +536,7 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
             Tr[f] *= om;
             gsta.x += gl.x; gsta.y += gl.y; gsta.z += gl.z; gsta.w += gl.w;   // static tiles: sum over frames (MPV.py:445)
             const float4 gl_up = shfl_up4(gl);
-            if (wr && tp.kind == 2) scatter_taps(gb[f], tp, gl, gl_up, wu10, wu11, sent0, sent1);
+            if (wr && tp.kind == 2) scatter_taps<(HINTS & 2) != 0>(gb[f], tp, gl, gl_up, wu10, wu11, sent0, sent1);
         }
         if (__any_sync(0xffffffffu, tp.kind == 1)) {
             const float4 gl_up = shfl_up4(gsta);

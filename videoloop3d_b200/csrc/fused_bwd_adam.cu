@@ -16,8 +16,8 @@
 // so backward tiles (instruction issue) and Adam rectangles (DRAM) overlap on every SM, and — when the host orders the
 // items by screen band (dense layout) — a band's gradient rows are produced, consumed and dropped while L2-resident.
 //
-// The schedule is a host-built table (videoloop3d_b200/schedule.py): per item the work description, a range of
-// counters to wait for (each >= target) and a counter to bump when done.  An item only waits for items that precede
+// The schedule is a host-built table (videoloop3d_b200/schedule.py): per item the work description, up to two ranges
+// of counters to wait for (each >= a target) and a counter to bump when done.  An item only waits for items that precede
 // it in the queue, and items are claimed in queue order by running CTAs, so the waits cannot deadlock.  One table
 // describes one "round" (= one chunk of TF frames); the kernel replays it for every chunk, with per-chunk counters.
 #include "composite_common.cuh"
@@ -29,11 +29,11 @@ namespace vl3d {
 constexpr int FUSED_TF = 2;
 
 enum : int { ITEM_BWD = 0, ITEM_ADAM = 1, ITEM_ZERO = 2 };
-enum : int { FLAG_HAS_GRAD = 1, FLAG_REZERO = 2, FLAG_DISCARD = 4, FLAG_PREV_ROUND = 8, FLAG_ORDERED = 16 };
+enum : int { FLAG_HAS_GRAD = 1, FLAG_REZERO = 2, FLAG_DISCARD = 4, FLAG_PREV_ROUND = 8 };
 
 struct alignas(64) FusedParams {
     TmaRenderParams R;
-    const int4* items;     // [n_items][2]
+    const int4* items;     // [n_items][3]
     int n_items, n_rounds, n_chunks, n_counters;
     int* counters;         // [n_chunks][n_counters], initialised by the caller
     int* ticket;           // queue head, zeroed by the caller
@@ -42,6 +42,11 @@ struct alignas(64) FusedParams {
     float b1, b2, step_size, inv_sqrt_bc2, eps;
 };
 
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -133,7 +138,7 @@ __device__ __forceinline__ void zero_rect(const FusedParams& F, const int t0, co
         }
 }
 
-template <bool SMOOTH, int MODE>
+template <bool SMOOTH, int MODE, int HINTS>
 __global__ void __launch_bounds__(BX* BY, 3) fused_bwd_adam_kernel(const __grid_constant__ FusedParams F) {
     __shared__ int s_item;
     const int tid = threadIdx.y * BX + threadIdx.x;
@@ -147,27 +152,29 @@ __global__ void __launch_bounds__(BX* BY, 3) fused_bwd_adam_kernel(const __grid_
         __syncthreads();
         if (I >= total) break;
         const int round = I / F.n_items, j = I - round * F.n_items;
-        const int4 a = __ldg(&F.items[2 * j]), b = __ldg(&F.items[2 * j + 1]);
+        const int4 a = __ldg(&F.items[3 * j]), b = __ldg(&F.items[3 * j + 1]), c = __ldg(&F.items[3 * j + 2]);
         const int type = a.x & 15, flags = a.x >> 4;
         const int chunk = round - ((flags & FLAG_PREV_ROUND) ? 1 : 0);
         if (chunk < 0 || chunk >= F.n_chunks) continue;
         int* const cnt = F.counters + (size_t)chunk * F.n_counters;
-        if (b.y > 0) {                                              // wait: counters [b.x, b.x + b.y) >= b.z
+        if (b.y > 0 || c.y > 0) {                                   // wait: counters [b.x, b.x + b.y) >= b.z, [c.x, c.x + c.y) >= c.z
             if (tid < 32) {
                 unsigned ns = 32;
                 for (;;) {
                     bool ok = true;
-                    for (int i = tid; i < b.y; i += 32) ok = ok && (ld_acquire_gpu(cnt + b.x + i) >= b.z);
+                    for (int i = tid; i < b.y; i += 32) ok = ok && (ld_relaxed_gpu(cnt + b.x + i) >= b.z);
+                    for (int i = tid; i < c.y; i += 32) ok = ok && (ld_relaxed_gpu(cnt + c.x + i) >= c.z);
                     if (__all_sync(0xffffffffu, ok)) break;
                     __nanosleep(ns);
                     if (ns < 1024) ns *= 2;
                 }
+                __threadfence();                                    // acquire side of the producers' release increments
             }
             __syncthreads();
         }
         const int t0 = chunk * FUSED_TF;
         if (type == ITEM_BWD) {
-            bwd_tile<FUSED_TF, SMOOTH, MODE>(F.R, a.y, a.z, t0, kbase, first);
+            bwd_tile<FUSED_TF, SMOOTH, MODE, HINTS>(F.R, a.y, a.z, t0, kbase, first);
             first = false;
         } else if (type == ITEM_ADAM) {
             adam_rect(F, t0, a.y, a.z, a.w, flags);
@@ -178,19 +185,16 @@ __global__ void __launch_bounds__(BX* BY, 3) fused_bwd_adam_kernel(const __grid_
             __syncthreads();
             if (tid == 0) {
                 __threadfence();
-                if (flags & FLAG_ORDERED) {                         // in-order commit: item number b.z of this counter
-                    while (ld_acquire_gpu(cnt + b.w) != b.z) __nanosleep(32);
-                }
                 red_release_gpu_inc(cnt + b.w);
             }
         }
     }
 }
 
-template <bool SMOOTH, int MODE>
+template <bool SMOOTH, int MODE, int HINTS>
 static int launch_fused(const FusedParams& F, int ctas_per_sm, cudaStream_t st) {
     const size_t smem = MODE >= 2 ? (size_t)BWD_TMA_STAGES * FUSED_TF * TMA_BOX_BYTES : 0;
-    auto kern = fused_bwd_adam_kernel<SMOOTH, MODE>;
+    auto kern = fused_bwd_adam_kernel<SMOOTH, MODE, HINTS>;
     if (smem) {
         cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return set_err((int)ce, "fused_bwd_adam: cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
@@ -249,8 +253,16 @@ extern "C" int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads
     F.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     cudaStream_t st = (cudaStream_t)stream;
     const bool smooth = w_smooth != nullptr;
-    if (smooth && (view->flags & VL3D_VIEW_RECT_PLANES) && make_atlas_tmap(&F.R.tmap, p.view, atlas_dyn, T))
-        return launch_fused<true, 3>(F, ctas_per_sm, st);
-    if (smooth) return launch_fused<true, 0>(F, ctas_per_sm, st);
-    return launch_fused<false, 0>(F, ctas_per_sm, st);
+    const int hints = (ctas_per_sm >> 8) & 3;                       // tuning: L2 eviction hints (see bwd_tile)
+    ctas_per_sm &= 255;
+    if (smooth && (view->flags & VL3D_VIEW_RECT_PLANES) && make_atlas_tmap(&F.R.tmap, p.view, atlas_dyn, T)) {
+        switch (hints) {
+            case 1: return launch_fused<true, 3, 1>(F, ctas_per_sm, st);
+            case 2: return launch_fused<true, 3, 2>(F, ctas_per_sm, st);
+            case 3: return launch_fused<true, 3, 3>(F, ctas_per_sm, st);
+            default: return launch_fused<true, 3, 0>(F, ctas_per_sm, st);
+        }
+    }
+    if (smooth) return launch_fused<true, 0, 0>(F, ctas_per_sm, st);
+    return launch_fused<false, 0, 0>(F, ctas_per_sm, st);
 }

@@ -269,12 +269,13 @@ def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=6e-8):
 def fused_bwd_adam(view, pack, atlas_dyn, atlas_sta, T, grad_rgb, rgb, w_smooth, smooth_sums, grad_dyn, grad_sta, m, v,
                    step, lr, beta1, beta2, eps, items, n_items, n_rounds, state, n_counters, ctas_per_sm=0):
     """Backward + Adam of `atlas_dyn[:T]` in one persistent kernel (csrc/fused_bwd_adam.cu).  `items`: device int32
-    (n_items, 8) table from schedule.py; `state`: device int32 scratch, zeroed by the caller: [0] = queue head,
-    [16:] = n_rounds x n_counters counters."""
+    (n_items, 12) table from schedule.py; `state`: device int32 scratch prepared by the caller: [0] = queue head (0),
+    [16:] = n_rounds x n_counters counters (each round initialised to the schedule's `counter_init`)."""
     for t in (grad_dyn, m, v):
         if tuple(t.stride()) != tuple(atlas_dyn.stride()) or t.shape != atlas_dyn.shape:
             raise _lib.Vl3dError("fused_bwd_adam: atlas_dyn, grad_dyn, m, v must share shape and strides")
-    if items.dtype != torch.int32 or state.dtype != torch.int32 or state.numel() < 16 + n_rounds * n_counters:
+    if (items.dtype != torch.int32 or not items.is_contiguous() or items.numel() != 12 * n_items or state.dtype != torch.int32
+            or state.numel() < 16 + n_rounds * n_counters):
         raise _lib.Vl3dError("fused_bwd_adam: bad schedule buffers")
     _lib.call("vl3d_fused_bwd_adam", C.byref(view), _lib.ptr(pack.quads), _lib.ptr(atlas_dyn), _lib.ptr(atlas_sta), int(T),
               _lib.ptr(grad_rgb), _lib.ptr(rgb), _lib.ptr(w_smooth), _lib.ptr(smooth_sums), _lib.ptr(grad_dyn),

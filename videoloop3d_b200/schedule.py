@@ -24,14 +24,16 @@ from dataclasses import dataclass
 import numpy as np
 
 ITEM_BWD, ITEM_ADAM, ITEM_ZERO = 0, 1, 2
-FLAG_HAS_GRAD, FLAG_REZERO, FLAG_DISCARD, FLAG_PREV_ROUND, FLAG_ORDERED = 1, 2, 4, 8, 16
+FLAG_HAS_GRAD, FLAG_REZERO, FLAG_DISCARD, FLAG_PREV_ROUND = 1, 2, 4, 8
 BX, BY, TF = 32, 8, 2                  # tile shape / frames per chunk of the kernels (composite_common.cuh)
+# item columns (12 int32 = three int4 of the kernel)
+C_TYPE, C_A, C_B, C_C, C_W0, C_WN, C_WT, C_SIG, C_V0, C_VN, C_VT = range(11)
 
 
 @dataclass
 class Schedule:
-    items: np.ndarray        # (n_items, 8) int32: [type | flags << 4, a, b, c, wait_first, wait_count, wait_target, signal]
-    n_counters: int
+    items: np.ndarray        # (n_items, 12) int32, see include/vl3d.h
+    counter_init: np.ndarray  # (n_counters,) int32: initial counter values of every round
     extra_round: bool        # items of the last chunk run in one more round (generic schedule)
     kind: str
     stats: dict
@@ -40,14 +42,23 @@ class Schedule:
     def n_items(self):
         return int(self.items.shape[0])
 
+    @property
+    def n_counters(self):
+        return int(self.counter_init.shape[0])
+
 
 def tile_grid(H, W, smooth=True):
     sx, sy = (BX - 1, BY - 1) if smooth else (BX, BY)
     return (W + sx - 1) // sx, (H + sy - 1) // sy, sx, sy
 
 
-def _item(kind, flags, a=0, b=0, c=0, wait=(-1, 0, 0), signal=-1):
-    return (kind | (flags << 4), a, b, c, wait[0], wait[1], wait[2], signal)
+def _rows(n, kind, flags=0):
+    it = np.zeros((n, 12), dtype=np.int64)
+    it[:, C_TYPE] = kind | (flags << 4)
+    it[:, C_W0] = -1
+    it[:, C_SIG] = -1
+    it[:, C_V0] = -1
+    return it
 
 
 def generic_schedule(H, W, dyn_h, dyn_w, smooth=True, seg_texels=32768, lead_tiles=888):
@@ -55,16 +66,19 @@ def generic_schedule(H, W, dyn_h, dyn_w, smooth=True, seg_texels=32768, lead_til
     gx, gy, _, _ = tile_grid(H, W, smooth)
     n_tiles = gx * gy
     rows_per = max(1, seg_texels // max(dyn_w, 1))
-    segs = [(r0 * dyn_w, dyn_w, min(rows_per, dyn_h - r0)) for r0 in range(0, dyn_h, rows_per)]
-    adam = [_item(ITEM_ADAM, FLAG_HAS_GRAD | FLAG_REZERO | FLAG_PREV_ROUND, b, w, r, wait=(0, 1, n_tiles)) for b, w, r in segs]
-    tiles = [_item(ITEM_BWD, 0, bx, by, 0, signal=0) for by in range(gy) for bx in range(gx)]
+    r0 = np.arange(0, dyn_h, rows_per)
+    adam = _rows(len(r0), ITEM_ADAM, FLAG_HAS_GRAD | FLAG_REZERO | FLAG_PREV_ROUND)
+    adam[:, C_A], adam[:, C_B], adam[:, C_C] = r0 * dyn_w, dyn_w, np.minimum(rows_per, dyn_h - r0)
+    adam[:, C_W0], adam[:, C_WN], adam[:, C_WT] = 0, 1, n_tiles
+    tiles = _rows(n_tiles, ITEM_BWD)
+    tiles[:, C_A], tiles[:, C_B] = np.tile(np.arange(gx), gy), np.repeat(np.arange(gy), gx)
+    tiles[:, C_SIG] = 0
     lead = min(lead_tiles, n_tiles // 4)
     # merge: no Adam among the first `lead` tiles (the previous chunk's last tiles are still running), then evenly
     pos = lead + (np.arange(len(adam)) + 0.5) * (n_tiles - lead) / max(len(adam), 1)
     order = np.argsort(np.concatenate([np.arange(n_tiles, dtype=np.float64), pos]), kind="stable")
-    allitems = tiles + adam
-    items = np.asarray([allitems[i] for i in order], dtype=np.int32)
-    return Schedule(items=items, n_counters=1, extra_round=True, kind="generic",
+    items = np.concatenate([tiles, adam])[order].astype(np.int32)
+    return Schedule(items=items, counter_init=np.zeros(1, np.int32), extra_round=True, kind="generic",
                     stats=dict(tiles=n_tiles, adam=len(adam), zero=0))
 
 
@@ -79,8 +93,11 @@ def _plane_rects(table, D, qh, qw):
 
 
 def band_schedule(view_homs, cx, cy, H, W, table, D, qh, qw, dyn_h, dyn_w, smooth=True, row_block=8, col_blocks=None,
-                  zero_ahead=2, adam_lag=2, use_zero=True, margin=2):
-    """Dense layout.  Counters: [0, gy) finished tiles per tile row; gy = in-order count of finished ZERO items."""
+                  zero_ahead=2, adam_lag=2, use_zero=True, margin=2, long_span=12):
+    """Dense layout.  Counters of a round: [0, gy) finished tiles per tile row; [gy, 2 gy) finished ZERO items whose
+    first tile row is R, pre-biased so that every one of them is complete at `zmax`; 2 gy = finished ZERO items of the
+    few long-lived rectangles (atlas rows shared by two planes: touched by the first and the last tile rows), which are
+    zeroed at the start of the round."""
     gx, gy, sx_t, sy_t = tile_grid(H, W, smooth)
     homs = np.asarray(view_homs, dtype=np.float64).reshape(D, 3, 3)
     X0, Y0, qsx, qsy = _plane_rects(table, D, qh, qw)
@@ -159,74 +176,92 @@ def band_schedule(view_homs, cx, cy, H, W, table, D, qh, qw, dyn_h, dyn_w, smoot
     fb = np.pad(first, ((0, pad), (0, 0)), constant_values=BIG).reshape(n_rb, row_block, col_blocks).min(1)
     lb = np.pad(last, ((0, pad), (0, 0)), constant_values=-1).reshape(n_rb, row_block, col_blocks).max(1)
 
-    keys, items = [], []
-    zero_first = []
-    for by in range(gy):
-        for bx in range(gx):
-            keys.append(float(by))
-            items.append([ITEM_BWD, 0, bx, by, 0, -1, 0, 0, by])   # wait filled below
-    n_untouched = int((lb < 0).sum())
-    ui = 0
-    for rb in range(n_rb):
-        r0 = rb * row_block
-        nr = min(row_block, dyn_h - r0)
-        for cb in range(col_blocks):
-            base, width = r0 * dyn_w + cb_edges[cb], cb_edges[cb + 1] - cb_edges[cb]
-            if width <= 0:
-                continue
-            f, l = int(fb[rb, cb]), int(lb[rb, cb])
-            if l < 0:                                               # never touched: Adam with g = 0, any time
-                keys.append((ui + 0.5) * gy / max(n_untouched, 1))
-                ui += 1
-                items.append([ITEM_ADAM, 0, base, width, nr, -1, 0, 0, -1])
-                continue
-            aligned = (base % 8 == 0) and (width % 8 == 0) and (dyn_w % 8 == 0)
-            if use_zero:
-                keys.append(f - zero_ahead - 0.5)
-                items.append([ITEM_ZERO, FLAG_ORDERED, base, width, nr, -1, 0, 0, gy])
-                zero_first.append(f)
-                fl = FLAG_HAS_GRAD | (FLAG_DISCARD if aligned else 0)
-            else:
-                fl = FLAG_HAS_GRAD | FLAG_REZERO
-            keys.append(l + adam_lag + 0.25)
-            items.append([ITEM_ADAM, fl, base, width, nr, f, l - f + 1, gx, -1])
-    order = np.argsort(np.asarray(keys), kind="stable")
-    out = np.zeros((len(items), 8), dtype=np.int32)
-    zseq = 0
-    nz_before_row = np.zeros(gy, dtype=np.int64)
+    # ---- items (vectorised: this runs once per view)
+    rb_i, cb_i = np.meshgrid(np.arange(n_rb), np.arange(col_blocks), indexing="ij")
+    rb_i, cb_i = rb_i.reshape(-1), cb_i.reshape(-1)
+    edges = np.asarray(cb_edges)
+    r0 = rb_i * row_block
+    base = r0 * dyn_w + edges[cb_i]
+    width = edges[cb_i + 1] - edges[cb_i]
+    nr = np.minimum(row_block, dyn_h - r0)
+    f, l = fb.reshape(-1), lb.reshape(-1)
+    keep = width > 0
+    rb_i, cb_i, base, width, nr, f, l = (v[keep] for v in (rb_i, cb_i, base, width, nr, f, l))
+    touched = l >= 0
+    n_untouched = int((~touched).sum())
+    aligned = (base % 8 == 0) & (width % 8 == 0) & (dyn_w % 8 == 0)
+    long_lived = touched & ((l - f) > long_span)
+
+    tiles = _rows(gx * gy, ITEM_BWD)
+    tiles[:, C_A], tiles[:, C_B] = np.tile(np.arange(gx), gy), np.repeat(np.arange(gy), gx)
+    tiles[:, C_SIG] = tiles[:, C_B]
+    tile_keys = tiles[:, C_B].astype(np.float64)
+
+    adam = _rows(len(base), ITEM_ADAM)
+    adam[:, C_A], adam[:, C_B], adam[:, C_C] = base, width, nr
+    fl = np.where(touched, FLAG_HAS_GRAD | np.where(use_zero & aligned, FLAG_DISCARD, FLAG_REZERO), 0)
+    adam[:, C_TYPE] = ITEM_ADAM | (fl << 4)
+    adam[touched, C_W0] = f[touched]
+    adam[touched, C_WN] = (l - f + 1)[touched]
+    adam[touched, C_WT] = gx
+    adam_keys = np.where(touched, l + adam_lag + 0.25, 0.0)
+    adam_keys[~touched] = (np.arange(n_untouched) + 0.5) * gy / max(n_untouched, 1)     # g = 0: any time
+
+    n_counters = gy
+    init = np.zeros(gy, dtype=np.int64)
+    parts, keys = [tiles, adam], [tile_keys, adam_keys]
+    n_zero = 0
     if use_zero:
-        zf = np.sort(np.asarray(zero_first, dtype=np.int64))
-        nz_before_row = np.searchsorted(zf, np.arange(gy), side="right")       # ZERO items with first <= R
-    for k, i in enumerate(order):
-        kind, fl, a, b, c, w0, wn, wt, sig = items[i]
-        if kind == ITEM_BWD and use_zero:
-            w0, wn, wt = gy, 1, int(nz_before_row[b])
-            if wt == 0:
-                w0, wn = -1, 0
-        if kind == ITEM_ZERO:
-            wt = zseq                                               # in-order commit: bump counter gy when it equals zseq
-            zseq += 1
-        out[k] = _item(kind, fl, a, b, c, wait=(w0, wn, wt), signal=sig)
-    # the in-order ZERO sequence must match the order in which `nz_before_row` counts them: ZERO items are queued by
-    # ascending `first` (their keys), so the first nz_before_row[R] of them are exactly those with first <= R
-    return Schedule(items=out, n_counters=gy + 1, extra_round=False, kind="band-zero" if use_zero else "band",
-                    stats=dict(tiles=gx * gy, adam=int((out[:, 0] & 15 == ITEM_ADAM).sum()), zero=zseq,
-                               untouched=n_untouched, max_wait=int(out[:, 5].max())))
+        zsel = touched & aligned
+        zshort, zlong = zsel & ~long_lived, zsel & long_lived
+        zero = _rows(int(zsel.sum()), ITEM_ZERO)
+        zero[:, C_A], zero[:, C_B], zero[:, C_C] = base[zsel], width[zsel], nr[zsel]
+        is_long = zlong[zsel]
+        zero[:, C_SIG] = np.where(is_long, 2 * gy, gy + f[zsel])
+        zero_keys = np.where(is_long, -1e9, f[zsel] - zero_ahead - 0.5)
+        per_first = np.bincount(f[zshort], minlength=gy)[:gy]
+        zmax = int(per_first.max()) if per_first.size else 0
+        n_long = int(zlong.sum())
+        init = np.concatenate([init, zmax - per_first, [0]])        # pre-bias: every Z counter is complete at zmax
+        n_counters = 2 * gy + 1
+        # tile row R waits for the ZERO items of every rectangle it touches: first in [fmin(R), R]
+        fmin = np.arange(gy)
+        fs, ls = f[zshort], l[zshort]
+        if fs.size:
+            reach = np.full(gy + 1, gy, dtype=np.int64)             # reach[R] = min first among rectangles with last >= R
+            np.minimum.at(reach, ls, fs)
+            fmin = np.minimum(np.minimum.accumulate(reach[::-1])[::-1][:gy], np.arange(gy))
+        tR = tiles[:, C_B]
+        if zmax > 0:
+            tiles[:, C_W0], tiles[:, C_WN], tiles[:, C_WT] = gy + fmin[tR], tR - fmin[tR] + 1, zmax
+        if n_long > 0:
+            tiles[:, C_V0], tiles[:, C_VN], tiles[:, C_VT] = 2 * gy, 1, n_long
+        parts.append(zero)
+        keys.append(zero_keys)
+        n_zero = len(zero)
+    allitems = np.concatenate(parts)
+    order = np.argsort(np.concatenate(keys), kind="stable")
+    out = allitems[order].astype(np.int32)
+    return Schedule(items=out, counter_init=init.astype(np.int32), extra_round=False, kind="band-zero" if use_zero else "band",
+                    stats=dict(tiles=gx * gy, adam=len(adam), zero=n_zero, untouched=n_untouched,
+                               long_lived=int(long_lived.sum()), max_wait=int(out[:, C_WN].max())))
 
 
 def validate(s: Schedule):
-    """Host-side check of the queue invariant: an item only waits for counters that earlier items complete."""
+    """Host-side check of the queue invariant: an item only waits for counters that earlier items of the same round
+    complete (items flagged "previous round" wait for the whole previous round)."""
     it = s.items
-    done = np.zeros(s.n_counters, dtype=np.int64)
+    cnt = s.counter_init.astype(np.int64).copy()
     for k in range(len(it)):
-        kind, fl = it[k, 0] & 15, it[k, 0] >> 4
-        if fl & FLAG_PREV_ROUND:
-            continue                                                # waits for the previous round: checked separately
-        w0, wn, wt, sig = (int(x) for x in it[k, 4:8])
-        if kind == ITEM_ZERO and (fl & FLAG_ORDERED):
-            assert done[sig] == wt, f"item {k}: ZERO sequence {wt} but {done[sig]} committed"
-        elif wn > 0:
-            assert np.all(done[w0:w0 + wn] >= wt), f"item {k} waits for counters {w0}..{w0 + wn - 1} >= {wt}: {done[w0:w0 + wn]}"
-        if sig >= 0:
-            done[sig] += 1
+        fl = it[k, C_TYPE] >> 4
+        if not (fl & FLAG_PREV_ROUND):
+            for w0, wn, wt in ((it[k, C_W0], it[k, C_WN], it[k, C_WT]), (it[k, C_V0], it[k, C_VN], it[k, C_VT])):
+                if wn > 0:
+                    assert np.all(cnt[w0:w0 + wn] >= wt), f"item {k} waits for counters {w0}..{w0 + wn - 1} >= {wt}: {cnt[w0:w0 + wn]}"
+        if it[k, C_SIG] >= 0:
+            cnt[it[k, C_SIG]] += 1
+    final = cnt
+    for k in range(len(it)):                                        # previous-round waits: against the final counts
+        if (it[k, C_TYPE] >> 4) & FLAG_PREV_ROUND and it[k, C_WN] > 0:
+            assert np.all(final[it[k, C_W0]:it[k, C_W0] + it[k, C_WN]] >= it[k, C_WT]), f"item {k}"
     return True

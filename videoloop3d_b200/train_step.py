@@ -247,7 +247,9 @@ class FusedLoopStep:
                                                dyn_hw[1], smooth, row_block=o.get("row_block", 8),
                                                zero_ahead=o.get("zero_ahead", 2), adam_lag=o.get("adam_lag", 2),
                                                use_zero=(mode == "band-zero"))
-            sched.dev_items = torch.from_numpy(sched.items).to(self.model.atlas_dyn.device)
+            dev = self.model.atlas_dyn.device
+            sched.dev_items = torch.from_numpy(np.ascontiguousarray(sched.items)).to(dev)
+            sched.dev_init = torch.from_numpy(sched.counter_init).to(dev)
             if len(self._sched_cache) >= 8:
                 self._sched_cache.pop(next(iter(self._sched_cache)))
             self._sched_cache[key] = sched
@@ -438,7 +440,8 @@ class FusedLoopStep:
                 g_dyn = torch.zeros_like(dyn_local)                # all-zero between steps (the kernel keeps it so)
                 self._buf["g_dyn"] = g_dyn
             state = self._get("fused_state", (16 + n_rounds * sched.n_counters,), torch.int32)
-            state.zero_()
+            state[:16].zero_()                                      # [0] = queue head
+            state[16:].view(n_rounds, sched.n_counters).copy_(sched.dev_init)   # every round's counters
             with self._timed("fused_bwd_adam"):
                 ops.fused_bwd_adam(view, pack, dyn_local[:Te], atlas.data, Te, grad_rgb[t0:t0 + Te], rgb_pad[t0:t0 + Te],
                                    w_smooth, bwd_sums, g_dyn[:Te], g_sta, st[0][:Te], st[1][:Te], self.t, lr,
