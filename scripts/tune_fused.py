@@ -39,13 +39,16 @@ def main():
     lr = model.args.lrate * 0.01
     step = FusedLoopStep(model, timers=True, fused="off")
     H, W = wl["H"], wl["W"]
+    pr = torch.cuda.get_device_properties(0)
+    print(json.dumps({"L2": pr.L2_cache_size, "persisting_max": getattr(pr, "persisting_l2_cache_max_size", None),
+                      "access_policy_max_window": getattr(pr, "access_policy_max_window_size", None)}), flush=True)
     for spec in args.configs.split(","):
         f = spec.split(":")
         mode = f[0]
         ctas = int(f[1]) if len(f) > 1 else 3
         hints = int(f[2]) if len(f) > 2 else 0
         opts = dict(ctas_per_sm=ctas | (hints << 8))
-        for name, i in (("row_block", 3), ("zero_ahead", 4), ("adam_lag", 5)):
+        for name, i in (("row_block", 3), ("zero_ahead", 4), ("adam_lag", 5), ("discard", 6)):
             if len(f) > i and f[i] != "":
                 opts[name] = int(f[i])
         step.fused, step.fused_opts = mode, opts

@@ -40,6 +40,7 @@ struct alignas(64) FusedParams {
     float4* m;
     float4* v;
     float b1, b2, step_size, inv_sqrt_bc2, eps;
+    int tune;              // tuning bits: 4 = Adam streams with explicit L2::evict_first
 };
 
 __device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
@@ -57,6 +58,17 @@ __device__ __forceinline__ void red_release_gpu_inc(int* p) {
 }
 __device__ __forceinline__ void discard_l2_128(const void* p) {
     asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
+
+// streaming accesses with an explicit L2 eviction priority (the data is touched once per step)
+__device__ __forceinline__ float4 ld_evict_first(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::evict_first.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_evict_first(float4* p, const float4 v) {
+    asm volatile("st.global.L2::evict_first.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // same arithmetic, in the same order, as adam_kernel (optim.cu)
@@ -93,10 +105,17 @@ __device__ __forceinline__ void adam_rect(const FusedParams& F, const int t0, co
                 const size_t o = (size_t)f * frame + ro + c;
                 pp[f] = mm[f] = vv[f] = gg[f] = zero4;
                 if (in) {
-                    pp[f] = __ldcs(P0 + o);
-                    mm[f] = __ldcs(M0 + o);
-                    vv[f] = __ldcs(V0 + o);
-                    if (has_grad) gg[f] = __ldcg(G0 + o);
+                    if (F.tune & 4) {
+                        pp[f] = ld_evict_first(P0 + o);
+                        mm[f] = ld_evict_first(M0 + o);
+                        vv[f] = ld_evict_first(V0 + o);
+                        if (has_grad) gg[f] = ld_evict_first(G0 + o);
+                    } else {
+                        pp[f] = __ldcs(P0 + o);
+                        mm[f] = __ldcs(M0 + o);
+                        vv[f] = __ldcs(V0 + o);
+                        if (has_grad) gg[f] = __ldcg(G0 + o);
+                    }
                 }
             }
             if (has_grad && (flags & FLAG_DISCARD)) {
@@ -114,10 +133,17 @@ __device__ __forceinline__ void adam_rect(const FusedParams& F, const int t0, co
                 for (int f = 0; f < FUSED_TF; ++f) {
                     const size_t o = (size_t)f * frame + ro + c;
                     adam4(pp[f], gg[f], mm[f], vv[f], F);
-                    __stcs(P0 + o, pp[f]);
-                    __stcs(M0 + o, mm[f]);
-                    __stcs(V0 + o, vv[f]);
-                    if (has_grad && (flags & FLAG_REZERO)) G0[o] = zero4;
+                    if (F.tune & 4) {
+                        st_evict_first(P0 + o, pp[f]);
+                        st_evict_first(M0 + o, mm[f]);
+                        st_evict_first(V0 + o, vv[f]);
+                        if (has_grad && (flags & FLAG_REZERO)) st_evict_first(G0 + o, zero4);
+                    } else {
+                        __stcs(P0 + o, pp[f]);
+                        __stcs(M0 + o, mm[f]);
+                        __stcs(V0 + o, vv[f]);
+                        if (has_grad && (flags & FLAG_REZERO)) G0[o] = zero4;
+                    }
                 }
             }
         }
@@ -254,6 +280,15 @@ extern "C" int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads
     cudaStream_t st = (cudaStream_t)stream;
     const bool smooth = w_smooth != nullptr;
     const int hints = (ctas_per_sm >> 8) & 3;                       // tuning: L2 eviction hints (see bwd_tile)
+    F.tune = (ctas_per_sm >> 8) & 0xff;
+    if (F.tune & 8) {                                               // L2 set-aside for evict_last (persisting) lines
+        int dev = 0, maxp = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        size_t want = (size_t)maxp;
+        if (F.tune & 16) want /= 2;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    }
     ctas_per_sm &= 255;
     if (smooth && (view->flags & VL3D_VIEW_RECT_PLANES) && make_atlas_tmap(&F.R.tmap, p.view, atlas_dyn, T)) {
         switch (hints) {

@@ -93,7 +93,7 @@ def _plane_rects(table, D, qh, qw):
 
 
 def band_schedule(view_homs, cx, cy, H, W, table, D, qh, qw, dyn_h, dyn_w, smooth=True, row_block=8, col_blocks=None,
-                  zero_ahead=2, adam_lag=2, use_zero=True, margin=2, long_span=12):
+                  zero_ahead=2, adam_lag=2, use_zero=True, margin=2, long_span=12, discard=True):
     """Dense layout.  Counters of a round: [0, gy) finished tiles per tile row; [gy, 2 gy) finished ZERO items whose
     first tile row is R, pre-biased so that every one of them is complete at `zmax`; 2 gy = finished ZERO items of the
     few long-lived rectangles (atlas rows shared by two planes: touched by the first and the last tile rows), which are
@@ -199,7 +199,7 @@ def band_schedule(view_homs, cx, cy, H, W, table, D, qh, qw, dyn_h, dyn_w, smoot
 
     adam = _rows(len(base), ITEM_ADAM)
     adam[:, C_A], adam[:, C_B], adam[:, C_C] = base, width, nr
-    fl = np.where(touched, FLAG_HAS_GRAD | np.where(use_zero & aligned, FLAG_DISCARD, FLAG_REZERO), 0)
+    fl = np.where(touched, FLAG_HAS_GRAD | np.where(use_zero & aligned & discard, FLAG_DISCARD, np.where(use_zero & aligned, 0, FLAG_REZERO)), 0)
     adam[:, C_TYPE] = ITEM_ADAM | (fl << 4)
     adam[touched, C_W0] = f[touched]
     adam[touched, C_WN] = (l - f + 1)[touched]

@@ -195,7 +195,7 @@ class FusedLoopStep:
         if self.fused not in ("off", "generic", "band", "band-zero", "auto"):
             raise ValueError(f"fused={self.fused!r}")
         self.fused_opts = dict(fused_opts or {})
-        for k, cast in (("ctas_per_sm", int), ("row_block", int), ("zero_ahead", int), ("adam_lag", int), ("seg_texels", int)):
+        for k, cast in (("ctas_per_sm", int), ("row_block", int), ("zero_ahead", int), ("adam_lag", int), ("seg_texels", int), ("discard", int)):
             e = os.environ.get("VL3D_FUSED_" + k.upper())
             if e is not None and k not in self.fused_opts:
                 self.fused_opts[k] = cast(e)
@@ -246,7 +246,7 @@ class FusedLoopStep:
                 sched = schedule.band_schedule(homs, view.cx, view.cy, h, w, pack.table, pack.D, pack.qh, pack.qw, dyn_hw[0],
                                                dyn_hw[1], smooth, row_block=o.get("row_block", 8),
                                                zero_ahead=o.get("zero_ahead", 2), adam_lag=o.get("adam_lag", 2),
-                                               use_zero=(mode == "band-zero"))
+                                               use_zero=(mode == "band-zero"), discard=bool(o.get("discard", 1)))
             dev = self.model.atlas_dyn.device
             sched.dev_items = torch.from_numpy(np.ascontiguousarray(sched.items)).to(dev)
             sched.dev_init = torch.from_numpy(sched.counter_init).to(dev)
