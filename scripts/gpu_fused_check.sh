@@ -4,6 +4,7 @@
 tag=${1:-fused}
 out=gpurun_out
 mkdir -p $out
+python -c "from videoloop3d_b200 import build; import sys; sys.exit(1 if build.needs_build() else 0)" || { echo "libvl3d.so is stale: rebuild before gpurun"; exit 9; }
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > $out/${tag}_gpu.txt 2>&1
 timeout 300 python -m pytest tests/test_gpu_fused.py tests/test_gpu_tma.py -x -q > $out/${tag}_pytest_fused.log 2>&1
 echo "pytest fused rc=$?" > $out/${tag}_rc.log

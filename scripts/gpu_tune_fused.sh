@@ -4,6 +4,7 @@ tag=${1:-tune}
 cfgs=${2:-"off,generic:3:0,band:3:0,band:2:0,band:1:0,band:3:1,band:3:3,band:1:3,band-zero:3:0,band-zero:3:3,band-zero:1:3"}
 out=gpurun_out
 mkdir -p $out
+python -c "from videoloop3d_b200 import build; import sys; sys.exit(1 if build.needs_build() else 0)" || { echo "libvl3d.so is stale: rebuild before gpurun"; exit 9; }
 timeout 200 python -m pytest tests/test_gpu_fused.py -x -q > $out/${tag}_pytest_fused.log 2>&1
 echo "pytest fused rc=$?"; tail -3 $out/${tag}_pytest_fused.log
 timeout 500 python scripts/tune_fused.py --steps 3 --configs "$cfgs" > $out/${tag}_tune.jsonl 2> $out/${tag}_tune.err

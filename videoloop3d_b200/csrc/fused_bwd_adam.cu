@@ -63,12 +63,13 @@ __device__ __forceinline__ void discard_l2_128(const void* p) {
 // streaming accesses with an explicit L2 eviction priority (the data is touched once per step)
 __device__ __forceinline__ float4 ld_evict_first(const float4* p) {
     float4 v;
-    asm volatile("ld.global.L1::no_allocate.L2::evict_first.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(L2_EVICT_FIRST) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_evict_first(float4* p, const float4 v) {
-    asm volatile("st.global.L2::evict_first.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
+                 "l"(L2_EVICT_FIRST) : "memory");
 }
 
 // same arithmetic, in the same order, as adam_kernel (optim.cu)
