@@ -6,7 +6,7 @@ mkdir -p $out
 for cfg in "32 512 0" "32 128 0" "32 512 64" "64 1024 96"; do
   set -- $cfg
   name=${tag}_l2probe_g$1_s$2_p$3
-  timeout 120 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv \
+  timeout 120 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --cache-control none --csv \
       --log-file $out/$name.csv ./build_probe/l2_probe $1 $2 $3 > $out/$name.log 2>&1
   echo "== G=$1 MB, stream=$2 MB, persist=$3 MB"; head -3 $out/$name.log
   python - <<PY

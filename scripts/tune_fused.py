@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Sweep of the fused backward + Adam kernel's schedule knobs at the bench workload (one process, one model).
 
-    python scripts/tune_fused.py [--workload step720p] [--steps 3] [--configs "mode:ctas:hints:row_block:zero_ahead:adam_lag,..."]
+    python scripts/tune_fused.py [--workload step720p] [--steps 3] [--configs "mode:ctas:hints:row_block:zero_ahead:adam_lag:groups:group_lag,..."]
 
 Prints one line per configuration: CUDA-event ms of the fused kernel.  Run it under
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum -k regex:fused_bwd_adam
@@ -48,9 +48,9 @@ def main():
         ctas = int(f[1]) if len(f) > 1 else 3
         hints = int(f[2]) if len(f) > 2 else 0
         opts = dict(ctas_per_sm=ctas | (hints << 8))
-        for name, i in (("row_block", 3), ("zero_ahead", 4), ("adam_lag", 5), ("discard", 6)):
+        for name, i in (("row_block", 3), ("zero_ahead", 4), ("adam_lag", 5), ("groups", 6), ("group_lag", 7)):
             if len(f) > i and f[i] != "":
-                opts[name] = int(f[i])
+                opts[name] = float(f[i]) if name == "group_lag" else int(f[i])
         step.fused, step.fused_opts = mode, opts
         step._sched_cache.clear()
         step.timers.clear()

@@ -295,9 +295,18 @@ __device__ __forceinline__ float4 shfl_up4(const float4& v) {
 constexpr int BWD_TMA_STAGES = 3;
 
 // HINTS (fused pass): bit 0 = atlas boxes are streamed (TMA loads evict_first), bit 1 = texel-gradient REDs evict_last.
-template <int TF, bool SMOOTH, int MODE, int HINTS = 0>
+// SIG (fused pass, regulariser tiling): progress signals — after the exchange barrier of slot k every thread's REDs of
+// the slots before k have been issued, so once the lowest plane any pixel of the tile has reached lies beyond plane
+// group g, thread 0 publishes "group g of this tile is complete" (fence + release increment of sig[g * sig_stride]);
+// `next_g` returns how many groups were published (the caller publishes the rest after the tile).
+__device__ __forceinline__ void sig_release_inc(int* p) {
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
+}
+
+template <int TF, bool SMOOTH, int MODE, int HINTS = 0, bool SIG = false>
 __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx, const int by, const int t0, unsigned& kbase,
-                                         const bool first) {
+                                         const bool first, int* const sig = nullptr, int* const next_g_out = nullptr) {
     const CompositeParams& p = P.p;
     static_assert(MODE == 0 || SMOOTH, "the split launch is only built for the regulariser tiling");
     constexpr int SX = SMOOTH ? BX - 1 : BX, SY = SMOOTH ? BY - 1 : BY;
@@ -315,6 +324,12 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
     __shared__ int4 s_box[MODE >= 2 ? VL3D_MAX_PLANES : 1];
     __shared__ __align__(8) uint64_t s_full[MODE >= 2 ? NST : 1];
     extern __shared__ __align__(128) unsigned char bwd_dyn_smem[];  // MODE 2: [NST][TF][TMA_BH][TMA_BW] texels
+    __shared__ int s_prog[2];                                       // SIG, lazy tiles: lowest plane reached in slot k
+    int next_g = 0;
+    if (SIG) {
+        if (tx == 0 && ty == 0) s_prog[0] = s_prog[1] = VL3D_MAX_PLANES;
+        if (MODE == 0) __syncthreads();
+    }
     unsigned in_mask = 0u;
     bool use_tma = false;
     if (MODE != 0) {
@@ -412,6 +427,7 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
         tp.kind = 0; tp.o00 = tp.o10 = tp.o01 = tp.o11 = 0u;
         tp.w00 = tp.w10 = tp.w01 = tp.w11 = 0.f;
         float4 val[TF];
+        int slot_plane = VL3D_MAX_PLANES;                            // SIG: plane of this thread's slot k
 #pragma unroll
         for (int f = 0; f < TF; ++f) val[f] = make_float4(0.f, 0.f, 0.f, 0.f);   // zero canvas (MPV.py:441)
         if (MODE >= 2 && use_tma) {
@@ -419,6 +435,7 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
             if (k >= nplanes) break;
             const int dd = __ffs(rem_planes) - 1;
             rem_planes &= rem_planes - 1u;
+            slot_plane = dd;
             const unsigned use = kbase + (unsigned)k;
             const int s = (int)(use % NST);
             float gx, gy;
@@ -461,6 +478,7 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
                 const int4 qb = __ldg(reinterpret_cast<const int4*>(qp + 1));
                 if (qb.z == 0) continue;
                 tp = geo_from_quad(p, qp, qb, qx, qy, gx, gy);
+                slot_plane = dd;
                 break;
             }
             if (tp.kind == 2) {
@@ -470,6 +488,10 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
                 const float4 sv = sample_lean(sb, tp);
 #pragma unroll
                 for (int f = 0; f < TF; ++f) val[f] = sv;
+            }
+            if (SIG && SMOOTH) {
+                const int wmin = __reduce_min_sync(0xffffffffu, slot_plane);
+                if (tx == 0) atomicMin(&s_prog[k & 1], wmin);
             }
         }
         const bool has = tp.kind != 0;
@@ -487,6 +509,14 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
                 __syncthreads();                                    // also: everybody is done with the stage of slot k-1
                 if (tx == 0 && ty == 0 && k + 2 < nplanes) issue_plane();
             } else if (!__syncthreads_or(has)) break;              // (block-uniform)
+            if (SIG && tx == 0 && ty == 0) {
+                int reached = slot_plane;                           // lockstep tiles: the plane of slot k
+                if (!(MODE >= 2 && use_tma)) { reached = s_prog[k & 1]; s_prog[k & 1] = VL3D_MAX_PLANES; }
+                while (next_g < p.sig_groups && reached >= (next_g + 1) * p.sig_group_planes) {
+                    sig_release_inc(sig + next_g * p.sig_stride);
+                    ++next_g;
+                }
+            }
 #pragma unroll
             for (int f = 0; f < TF; ++f) {
                 const float4 c = val[f];
@@ -558,6 +588,7 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
         }
     }
     if (use_tma) kbase += (unsigned)nplanes;
+    if (SIG) *next_g_out = next_g;
 }
 
 template <int TF, bool SMOOTH, int MODE>

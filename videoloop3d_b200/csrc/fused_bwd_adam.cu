@@ -9,8 +9,8 @@
 // alternates with a DRAM-bound one (Adam: 6.3 TB/s).  Here resident CTAs pull work items from one ordered queue:
 //   BWD   one (screen tile, chunk of TF frames) of the backward — exactly composite_lean.cuh's bwd_tile;
 //   ADAM  Adam on a rectangle of texels (rows x width) of the chunk's frames: reads p, g, m, v; writes p, m, v; then
-//         either writes zeros back into g (the buffer is all-zero between steps: no separate fill) or, in the
-//         zero-ahead schedules, drops the gradient lines from L2 without write-back (discard.global.L2);
+//         writes zeros back into g unless the schedule zeroes ahead (then the buffer's content between steps does not
+//         matter).  (Dropping the consumed lines with discard.global.L2 was measured 3x slower on B200: not used.)
 //   ZERO  zero a rectangle of g shortly before the first tile that accumulates into it (full-line stores: the RED
 //         that follows hits L2 instead of fetching the line from DRAM).
 // so backward tiles (instruction issue) and Adam rectangles (DRAM) overlap on every SM, and — when the host orders the
@@ -29,7 +29,7 @@ namespace vl3d {
 constexpr int FUSED_TF = 2;
 
 enum : int { ITEM_BWD = 0, ITEM_ADAM = 1, ITEM_ZERO = 2 };
-enum : int { FLAG_HAS_GRAD = 1, FLAG_REZERO = 2, FLAG_DISCARD = 4, FLAG_PREV_ROUND = 8 };
+enum : int { FLAG_HAS_GRAD = 1, FLAG_REZERO = 2, FLAG_PREV_ROUND = 8 };
 
 struct alignas(64) FusedParams {
     TmaRenderParams R;
@@ -55,9 +55,6 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 }
 __device__ __forceinline__ void red_release_gpu_inc(int* p) {
     asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
-}
-__device__ __forceinline__ void discard_l2_128(const void* p) {
-    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
 }
 
 // streaming accesses with an explicit L2 eviction priority (the data is touched once per step)
@@ -97,7 +94,7 @@ __device__ __forceinline__ void adam_rect(const FusedParams& F, const int t0, co
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = 0; r < rows; ++r) {
         const size_t ro = (size_t)r * stride;
-        for (int c0 = 0; c0 < width; c0 += BX * BY) {              // (warp-uniform trip count: __syncwarp below)
+        for (int c0 = 0; c0 < width; c0 += BX * BY) {
             const int c = c0 + tid;
             const bool in = c < width;
             float4 pp[FUSED_TF], gg[FUSED_TF], mm[FUSED_TF], vv[FUSED_TF];
@@ -117,16 +114,6 @@ __device__ __forceinline__ void adam_rect(const FusedParams& F, const int t0, co
                         vv[f] = __ldcs(V0 + o);
                         if (has_grad) gg[f] = __ldcg(G0 + o);
                     }
-                }
-            }
-            if (has_grad && (flags & FLAG_DISCARD)) {
-                // every lane's gradient load has returned before the line is dropped (8 lanes share a 128-byte line)
-                float sink = gg[0].x + gg[FUSED_TF - 1].w;
-                asm volatile("" ::"f"(sink));
-                __syncwarp();
-                if (in && (c & 7) == 0) {
-#pragma unroll
-                    for (int f = 0; f < FUSED_TF; ++f) discard_l2_128(G0 + (size_t)f * frame + ro + c);
                 }
             }
             if (in) {
@@ -201,8 +188,17 @@ __global__ void __launch_bounds__(BX* BY, 3) fused_bwd_adam_kernel(const __grid_
         }
         const int t0 = chunk * FUSED_TF;
         if (type == ITEM_BWD) {
-            bwd_tile<FUSED_TF, SMOOTH, MODE, HINTS>(F.R, a.y, a.z, t0, kbase, first);
+            // progress counters of this tile row: [group][tile row] (band schedules; sig_groups == 0: none)
+            const int G = F.R.p.sig_groups;
+            int* const sig = cnt + a.z;
+            int next_g = 0;
+            bwd_tile<FUSED_TF, SMOOTH, MODE, HINTS, SMOOTH>(F.R, a.y, a.z, t0, kbase, first, sig, &next_g);
             first = false;
+            if (G > 0) {
+                __syncthreads();
+                if (tid == 0)
+                    for (int g = next_g; g < G; ++g) sig_release_inc(sig + g * F.R.p.sig_stride);
+            }
         } else if (type == ITEM_ADAM) {
             adam_rect(F, t0, a.y, a.z, a.w, flags);
         } else {
@@ -248,7 +244,8 @@ extern "C" int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads
                                    double* smooth_sums, float* grad_dyn, float* grad_sta, float* adam_m, float* adam_v,
                                    int32_t step, float lr, float beta1, float beta2, float eps, const int32_t* items,
                                    int32_t n_items, int32_t n_rounds, int32_t* counters, int32_t n_counters,
-                                   int32_t* ticket, int32_t ctas_per_sm, void* stream) {
+                                   int32_t* ticket, int32_t n_groups, int32_t group_planes, int32_t group_stride,
+                                   int32_t ctas_per_sm, void* stream) {
     if (int e = validate_view(view, quads, atlas_dyn, atlas_sta)) return e;
     VL3D_REQUIRE(grad_rgb && rgb && grad_dyn && adam_m && adam_v && atlas_dyn, VL3D_ENULL, "fused_bwd_adam: NULL pointer");
     VL3D_REQUIRE(grad_sta != nullptr || atlas_sta == nullptr, VL3D_ENULL, "grad_sta is NULL");
@@ -257,6 +254,9 @@ extern "C" int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads
     VL3D_REQUIRE(n_items >= 1 && n_counters >= 1 && n_rounds >= T / FUSED_TF && n_rounds <= T / FUSED_TF + 1, VL3D_EINVAL,
                  "fused_bwd_adam: bad schedule (n_items=%d n_rounds=%d n_counters=%d)", n_items, n_rounds, n_counters);
     VL3D_REQUIRE(step >= 1, VL3D_EINVAL, "fused_bwd_adam: step=%d", step);
+    VL3D_REQUIRE(n_groups >= 0 && n_groups <= VL3D_MAX_PLANES && (n_groups == 0 || (group_planes >= 1 && group_stride >= 1 &&
+                 (int64_t)n_groups * group_stride <= n_counters)), VL3D_EINVAL, "fused_bwd_adam: bad progress groups (%d x %d planes, stride %d)",
+                 n_groups, group_planes, group_stride);
     VL3D_REQUIRE((((uintptr_t)grad_dyn | (uintptr_t)grad_sta | (uintptr_t)adam_m | (uintptr_t)adam_v | (uintptr_t)items) & 15) == 0,
                  VL3D_EALIGN, "fused_bwd_adam: pointers must be 16-byte aligned");
     FusedParams F{};
@@ -268,6 +268,7 @@ extern "C" int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads
     p.grad_rgb = grad_rgb; p.rgb = rgb;
     p.grad_dyn = reinterpret_cast<float4*>(grad_dyn); p.grad_sta = reinterpret_cast<float4*>(grad_sta);
     p.w_smooth = w_smooth; p.smooth = smooth_sums;
+    p.sig_groups = n_groups; p.sig_group_planes = group_planes; p.sig_stride = group_stride;
     VL3D_REQUIRE(w_smooth != nullptr || smooth_sums == nullptr, VL3D_EINVAL, "smooth_sums needs w_smooth");
     F.items = reinterpret_cast<const int4*>(items);
     F.n_items = n_items; F.n_rounds = n_rounds; F.n_chunks = T / FUSED_TF; F.n_counters = n_counters;
