@@ -152,7 +152,7 @@ __device__ __forceinline__ void zero_rect(const FusedParams& F, const int t0, co
         }
 }
 
-template <bool SMOOTH, int MODE, int HINTS>
+template <bool SMOOTH, int MODE, int HINTS, bool SIG>
 __global__ void __launch_bounds__(BX* BY, 3) fused_bwd_adam_kernel(const __grid_constant__ FusedParams F) {
     __shared__ int s_item;
     const int tid = threadIdx.y * BX + threadIdx.x;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(BX* BY, 3) fused_bwd_adam_kernel(const __grid_
             const int G = F.R.p.sig_groups;
             int* const sig = cnt + a.z;
             int next_g = 0;
-            bwd_tile<FUSED_TF, SMOOTH, MODE, HINTS, SMOOTH>(F.R, a.y, a.z, t0, kbase, first, sig, &next_g);
+            bwd_tile<FUSED_TF, SMOOTH, MODE, HINTS, SIG>(F.R, a.y, a.z, t0, kbase, first, sig, &next_g);
             first = false;
             if (G > 0) {
                 __syncthreads();
@@ -214,10 +214,10 @@ __global__ void __launch_bounds__(BX* BY, 3) fused_bwd_adam_kernel(const __grid_
     }
 }
 
-template <bool SMOOTH, int MODE, int HINTS>
+template <bool SMOOTH, int MODE, int HINTS, bool SIG>
 static int launch_fused(const FusedParams& F, int ctas_per_sm, cudaStream_t st) {
     const size_t smem = MODE >= 2 ? (size_t)BWD_TMA_STAGES * FUSED_TF * TMA_BOX_BYTES : 0;
-    auto kern = fused_bwd_adam_kernel<SMOOTH, MODE, HINTS>;
+    auto kern = fused_bwd_adam_kernel<SMOOTH, MODE, HINTS, SIG>;
     if (smem) {
         cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return set_err((int)ce, "fused_bwd_adam: cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
@@ -293,13 +293,9 @@ extern "C" int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads
     }
     ctas_per_sm &= 255;
     if (smooth && (view->flags & VL3D_VIEW_RECT_PLANES) && make_atlas_tmap(&F.R.tmap, p.view, atlas_dyn, T)) {
-        switch (hints) {
-            case 1: return launch_fused<true, 3, 1>(F, ctas_per_sm, st);
-            case 2: return launch_fused<true, 3, 2>(F, ctas_per_sm, st);
-            case 3: return launch_fused<true, 3, 3>(F, ctas_per_sm, st);
-            default: return launch_fused<true, 3, 0>(F, ctas_per_sm, st);
-        }
+        if (n_groups > 0) return (hints & 2) ? launch_fused<true, 3, 2, true>(F, ctas_per_sm, st) : launch_fused<true, 3, 0, true>(F, ctas_per_sm, st);
+        return launch_fused<true, 3, 0, false>(F, ctas_per_sm, st);
     }
-    if (smooth) return launch_fused<true, 0, 0>(F, ctas_per_sm, st);
-    return launch_fused<false, 0, 0>(F, ctas_per_sm, st);
+    if (smooth) return launch_fused<true, 0, 0, false>(F, ctas_per_sm, st);
+    return launch_fused<false, 0, 0, false>(F, ctas_per_sm, st);
 }
