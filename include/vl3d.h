@@ -187,17 +187,13 @@ int vl3d_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int3
  * grad_dyn: in schedules whose Adam items re-zero it, it must be all-zero on entry and is all-zero on exit; in
  * zero-ahead schedules its content on entry / exit is irrelevant.  grad_sta is accumulated into as in vl3d_composite_bwd
  * (the static atlas is optimised by the caller after its all-reduce).  atlas_dyn, adam_m, adam_v are updated in place.
- * Progress groups (band schedules; n_groups = 0: none): the planes are split into n_groups groups of group_planes; a
- * tile of tile row R bumps counter [g * group_stride + R] as soon as its accumulation into the planes of group g is
- * complete (mid-tile), so that Adam on those planes' rows need not wait for the whole tile.
- * ctas_per_sm: 0 = as many as fit (bits 8.. carry tuning flags, see csrc/fused_bwd_adam.cu). */
+ * ctas_per_sm: 0 = as many as fit. */
 int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads, float* atlas_dyn, const float* atlas_sta,
                         int32_t T, const float* grad_rgb, const float* rgb, const float* w_smooth,
                         double* smooth_sums, float* grad_dyn, float* grad_sta, float* adam_m, float* adam_v,
                         int32_t step, float lr, float beta1, float beta2, float eps, const int32_t* items,
                         int32_t n_items, int32_t n_rounds, int32_t* counters, int32_t n_counters,
-                        int32_t* ticket, int32_t n_groups, int32_t group_planes, int32_t group_stride,
-                        int32_t ctas_per_sm, void* stream);
+                        int32_t* ticket, int32_t ctas_per_sm, void* stream);
 
 #ifdef __cplusplus
 }

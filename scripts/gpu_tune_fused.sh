@@ -1,7 +1,7 @@
 #!/bin/bash
 # gpurun --timeout 1200 -- 'bash scripts/gpu_tune_fused.sh r02b "<configs>"'
 tag=${1:-tune}
-cfgs=${2:-"off,generic:3:0,band:3:0,band:2:0,band:1:0,band:3:1,band:3:3,band:1:3,band-zero:3:0,band-zero:3:3,band-zero:1:3"}
+cfgs=${2:-"off,generic:3,generic:2,band:3,band-zero:3"}
 out=gpurun_out
 mkdir -p $out
 python -c "from videoloop3d_b200 import build; import sys; sys.exit(1 if build.needs_build() else 0)" || { echo "libvl3d.so is stale: rebuild before gpurun"; exit 9; }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Sweep of the fused backward + Adam kernel's schedule knobs at the bench workload (one process, one model).
 
-    python scripts/tune_fused.py [--workload step720p] [--steps 3] [--configs "mode:ctas:hints:row_block:zero_ahead:adam_lag:groups:group_lag,..."]
+    python scripts/tune_fused.py [--workload step720p] [--steps 3] [--configs "mode:ctas:row_block:zero_ahead:adam_lag,..."]
 
 Prints one line per configuration: CUDA-event ms of the fused kernel.  Run it under
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum -k regex:fused_bwd_adam
@@ -18,7 +18,7 @@ import torch  # noqa: E402
 
 import bench  # noqa: E402
 
-DEFAULT = ("off,generic:3:0,band:3:0,band:2:0,band:1:0,band:3:1,band:3:3,band:2:3,band:1:3,generic:3:1")
+DEFAULT = "off,generic:3,generic:2,band:3,band-zero:3"
 
 
 def main():
@@ -46,11 +46,10 @@ def main():
         f = spec.split(":")
         mode = f[0]
         ctas = int(f[1]) if len(f) > 1 else 3
-        hints = int(f[2]) if len(f) > 2 else 0
-        opts = dict(ctas_per_sm=ctas | (hints << 8))
-        for name, i in (("row_block", 3), ("zero_ahead", 4), ("adam_lag", 5), ("groups", 6), ("group_lag", 7)):
+        opts = dict(ctas_per_sm=ctas)
+        for name, i in (("row_block", 2), ("zero_ahead", 3), ("adam_lag", 4)):
             if len(f) > i and f[i] != "":
-                opts[name] = float(f[i]) if name == "group_lag" else int(f[i])
+                opts[name] = int(f[i])
         step.fused, step.fused_opts = mode, opts
         step._sched_cache.clear()
         step.timers.clear()

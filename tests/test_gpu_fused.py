@@ -76,7 +76,7 @@ def test_fused_gradient_equals_classic_backward(layout, vname, T):
     assert scale > 0
     modes = ["generic"] + (["band", "band-zero"] if layout == "dense" else [])
     for mode in modes:
-        for opts in ({}, dict(row_block=3, zero_ahead=1, adam_lag=1, ctas_per_sm=1, groups=3), dict(groups=1, group_lag=0.0)):
+        for opts in ({}, dict(row_block=3, zero_ahead=1, adam_lag=0, ctas_per_sm=1)):
             m1, s1, o1 = _run_steps(st, H, W, mode, vname, 1, 0.0, dev, opts)
             assert s1.last_schedule is not None and s1.last_schedule.kind == mode
             g = s1._state["atlas_dyn"][0] / 0.1

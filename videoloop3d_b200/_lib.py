@@ -55,7 +55,7 @@ _SIGNATURES = {
     "vl3d_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
     "vl3d_fused_bwd_adam": (C.c_int, [C.POINTER(View), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32,
                                       C.c_float, C.c_float, C.c_float, C.c_float, _P, C.c_int32, C.c_int32, _P, C.c_int32,
-                                      _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+                                      _P, C.c_int32, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

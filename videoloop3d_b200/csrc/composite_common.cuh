@@ -35,9 +35,6 @@ struct CompositeParams {
     float4* grad_dyn;
     float4* grad_sta;
     const float* w_smooth;
-    // fused pass: planes are grouped (group g = planes [g*sig_group_planes, (g+1)*sig_group_planes)); a tile bumps
-    // sig[g * sig_stride] as soon as its accumulation into group g's texels is complete (0 groups: no signalling)
-    int sig_groups, sig_group_planes, sig_stride;
 };
 
 // quad-grid coordinates of pixel (u, v) on plane with homography h; false if behind / outside.

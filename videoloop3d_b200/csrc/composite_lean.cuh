@@ -257,22 +257,17 @@ __device__ __forceinline__ float sgn2(float c, float a, float b) {   // sign(c-a
 // scatter one sample gradient `gl` (w.r.t. the pre-sigmoid bilinear sample) to its four taps.  Lane i's
 // right-hand taps usually are lane i+1's left-hand taps: then the contribution travels by shuffle (gl_up
 // with the sender's weights wu10 / wu11, zero if nothing is received) and is folded into the receiver's RED.
-template <bool STICKY = false>
 __device__ __forceinline__ void scatter_taps(float4* gb, const Geo& tp, const float4& gl, const float4& gl_up, float wu10,
                                              float wu11, bool sent0, bool sent1) {
-    auto red = [](float4* a, float4 v) {
-        if (STICKY) red_add_v4_hint(a, v, 0x14F0000000000000ull);   // L2 evict_last: the line is consumed soon (fused pass)
-        else red_add_v4(a, v);
-    };
     float4 l0, l1;
     l0.x = fmaf(gl_up.x, wu10, gl.x * tp.w00); l0.y = fmaf(gl_up.y, wu10, gl.y * tp.w00);
     l0.z = fmaf(gl_up.z, wu10, gl.z * tp.w00); l0.w = fmaf(gl_up.w, wu10, gl.w * tp.w00);
     l1.x = fmaf(gl_up.x, wu11, gl.x * tp.w01); l1.y = fmaf(gl_up.y, wu11, gl.y * tp.w01);
     l1.z = fmaf(gl_up.z, wu11, gl.z * tp.w01); l1.w = fmaf(gl_up.w, wu11, gl.w * tp.w01);
-    red(gb + tp.o00, l0);
-    red(gb + tp.o01, l1);
-    if (!sent0) red(gb + tp.o10, make_float4(gl.x * tp.w10, gl.y * tp.w10, gl.z * tp.w10, gl.w * tp.w10));
-    if (!sent1) red(gb + tp.o11, make_float4(gl.x * tp.w11, gl.y * tp.w11, gl.z * tp.w11, gl.w * tp.w11));
+    red_add_v4(gb + tp.o00, l0);
+    red_add_v4(gb + tp.o01, l1);
+    if (!sent0) red_add_v4(gb + tp.o10, make_float4(gl.x * tp.w10, gl.y * tp.w10, gl.z * tp.w10, gl.w * tp.w10));
+    if (!sent1) red_add_v4(gb + tp.o11, make_float4(gl.x * tp.w11, gl.y * tp.w11, gl.z * tp.w11, gl.w * tp.w11));
 }
 
 __device__ __forceinline__ float4 shfl_up4(const float4& v) {
@@ -294,19 +289,9 @@ __device__ __forceinline__ float4 shfl_up4(const float4& v) {
 // CTA's first tile (initialises the mbarriers).  Callers separate two tiles by a __syncthreads().
 constexpr int BWD_TMA_STAGES = 3;
 
-// HINTS (fused pass): bit 0 = atlas boxes are streamed (TMA loads evict_first), bit 1 = texel-gradient REDs evict_last.
-// SIG (fused pass, regulariser tiling): progress signals — after the exchange barrier of slot k every thread's REDs of
-// the slots before k have been issued, so once the lowest plane any pixel of the tile has reached lies beyond plane
-// group g, thread 0 publishes "group g of this tile is complete" (fence + release increment of sig[g * sig_stride]);
-// `next_g` returns how many groups were published (the caller publishes the rest after the tile).
-__device__ __forceinline__ void sig_release_inc(int* p) {
-    __threadfence();
-    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
-}
-
-template <int TF, bool SMOOTH, int MODE, int HINTS = 0, bool SIG = false>
+template <int TF, bool SMOOTH, int MODE>
 __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx, const int by, const int t0, unsigned& kbase,
-                                         const bool first, int* const sig = nullptr, int* const next_g_out = nullptr) {
+                                         const bool first) {
     const CompositeParams& p = P.p;
     static_assert(MODE == 0 || SMOOTH, "the split launch is only built for the regulariser tiling");
     constexpr int SX = SMOOTH ? BX - 1 : BX, SY = SMOOTH ? BY - 1 : BY;
@@ -324,12 +309,6 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
     __shared__ int4 s_box[MODE >= 2 ? VL3D_MAX_PLANES : 1];
     __shared__ __align__(8) uint64_t s_full[MODE >= 2 ? NST : 1];
     extern __shared__ __align__(128) unsigned char bwd_dyn_smem[];  // MODE 2: [NST][TF][TMA_BH][TMA_BW] texels
-    __shared__ int s_prog[2];                                       // SIG, lazy tiles: lowest plane reached in slot k
-    int next_g = 0;
-    if (SIG) {
-        if (tx == 0 && ty == 0) s_prog[0] = s_prog[1] = VL3D_MAX_PLANES;
-        if (MODE == 0) __syncthreads();
-    }
     unsigned in_mask = 0u;
     bool use_tma = false;
     if (MODE != 0) {
@@ -409,13 +388,8 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
         const int4 bi = s_box[di];
         mbar_arrive_expect_tx(&s_full[s], TF * TMA_BOX_BYTES);
 #pragma unroll
-        for (int f = 0; f < TF; ++f) {
-            if (HINTS & 1)
-                tma_load_3d_hint(tiles + (size_t)(s * TF + f) * (TMA_BOX_BYTES / 16), &P.tmap, &s_full[s], bi.x * 4, bi.y, t0 + f,
-                                 L2_EVICT_FIRST);
-            else
-                tma_load_3d(tiles + (size_t)(s * TF + f) * (TMA_BOX_BYTES / 16), &P.tmap, &s_full[s], bi.x * 4, bi.y, t0 + f);
-        }
+        for (int f = 0; f < TF; ++f)
+            tma_load_3d(tiles + (size_t)(s * TF + f) * (TMA_BOX_BYTES / 16), &P.tmap, &s_full[s], bi.x * 4, bi.y, t0 + f);
         ++k_issue;
     };
     if (use_tma && tx == 0 && ty == 0) {
@@ -427,7 +401,6 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
         tp.kind = 0; tp.o00 = tp.o10 = tp.o01 = tp.o11 = 0u;
         tp.w00 = tp.w10 = tp.w01 = tp.w11 = 0.f;
         float4 val[TF];
-        int slot_plane = VL3D_MAX_PLANES;                            // SIG: plane of this thread's slot k
 #pragma unroll
         for (int f = 0; f < TF; ++f) val[f] = make_float4(0.f, 0.f, 0.f, 0.f);   // zero canvas (MPV.py:441)
         if (MODE >= 2 && use_tma) {
@@ -435,7 +408,6 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
             if (k >= nplanes) break;
             const int dd = __ffs(rem_planes) - 1;
             rem_planes &= rem_planes - 1u;
-            slot_plane = dd;
             const unsigned use = kbase + (unsigned)k;
             const int s = (int)(use % NST);
             float gx, gy;
@@ -478,7 +450,6 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
                 const int4 qb = __ldg(reinterpret_cast<const int4*>(qp + 1));
                 if (qb.z == 0) continue;
                 tp = geo_from_quad(p, qp, qb, qx, qy, gx, gy);
-                slot_plane = dd;
                 break;
             }
             if (tp.kind == 2) {
@@ -488,10 +459,6 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
                 const float4 sv = sample_lean(sb, tp);
 #pragma unroll
                 for (int f = 0; f < TF; ++f) val[f] = sv;
-            }
-            if (SIG && SMOOTH) {
-                const int wmin = __reduce_min_sync(0xffffffffu, slot_plane);
-                if (tx == 0) atomicMin(&s_prog[k & 1], wmin);
             }
         }
         const bool has = tp.kind != 0;
@@ -509,14 +476,6 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
                 __syncthreads();                                    // also: everybody is done with the stage of slot k-1
                 if (tx == 0 && ty == 0 && k + 2 < nplanes) issue_plane();
             } else if (!__syncthreads_or(has)) break;              // (block-uniform)
-            if (SIG && tx == 0 && ty == 0) {
-                int reached = slot_plane;                           // lockstep tiles: the plane of slot k
-                if (!(MODE >= 2 && use_tma)) { reached = s_prog[k & 1]; s_prog[k & 1] = VL3D_MAX_PLANES; }
-                while (next_g < p.sig_groups && reached >= (next_g + 1) * p.sig_group_planes) {
-                    sig_release_inc(sig + next_g * p.sig_stride);
-                    ++next_g;
-                }
-            }
 #pragma unroll
             for (int f = 0; f < TF; ++f) {
                 const float4 c = val[f];
@@ -566,7 +525,7 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
             Tr[f] *= om;
             gsta.x += gl.x; gsta.y += gl.y; gsta.z += gl.z; gsta.w += gl.w;   // static tiles: sum over frames (MPV.py:445)
             const float4 gl_up = shfl_up4(gl);
-            if (wr && tp.kind == 2) scatter_taps<(HINTS & 2) != 0>(gb[f], tp, gl, gl_up, wu10, wu11, sent0, sent1);
+            if (wr && tp.kind == 2) scatter_taps(gb[f], tp, gl, gl_up, wu10, wu11, sent0, sent1);
         }
         if (__any_sync(0xffffffffu, tp.kind == 1)) {
             const float4 gl_up = shfl_up4(gsta);
@@ -588,7 +547,6 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
         }
     }
     if (use_tma) kbase += (unsigned)nplanes;
-    if (SIG) *next_g_out = next_g;
 }
 
 template <int TF, bool SMOOTH, int MODE>

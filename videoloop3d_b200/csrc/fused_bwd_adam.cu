@@ -40,7 +40,6 @@ struct alignas(64) FusedParams {
     float4* m;
     float4* v;
     float b1, b2, step_size, inv_sqrt_bc2, eps;
-    int tune;              // tuning bits: 4 = Adam streams with explicit L2::evict_first
 };
 
 __device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
@@ -55,18 +54,6 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 }
 __device__ __forceinline__ void red_release_gpu_inc(int* p) {
     asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
-}
-
-// streaming accesses with an explicit L2 eviction priority (the data is touched once per step)
-__device__ __forceinline__ float4 ld_evict_first(const float4* p) {
-    float4 v;
-    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(L2_EVICT_FIRST) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_evict_first(float4* p, const float4 v) {
-    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
-                 "l"(L2_EVICT_FIRST) : "memory");
 }
 
 // same arithmetic, in the same order, as adam_kernel (optim.cu)
@@ -102,18 +89,11 @@ __device__ __forceinline__ void adam_rect(const FusedParams& F, const int t0, co
             for (int f = 0; f < FUSED_TF; ++f) {
                 const size_t o = (size_t)f * frame + ro + c;
                 pp[f] = mm[f] = vv[f] = gg[f] = zero4;
-                if (in) {
-                    if (F.tune & 4) {
-                        pp[f] = ld_evict_first(P0 + o);
-                        mm[f] = ld_evict_first(M0 + o);
-                        vv[f] = ld_evict_first(V0 + o);
-                        if (has_grad) gg[f] = ld_evict_first(G0 + o);
-                    } else {
-                        pp[f] = __ldcs(P0 + o);
-                        mm[f] = __ldcs(M0 + o);
-                        vv[f] = __ldcs(V0 + o);
-                        if (has_grad) gg[f] = __ldcg(G0 + o);
-                    }
+                if (in) {                                           // streams: evict-first; the gradient: L2 only
+                    pp[f] = __ldcs(P0 + o);
+                    mm[f] = __ldcs(M0 + o);
+                    vv[f] = __ldcs(V0 + o);
+                    if (has_grad) gg[f] = __ldcg(G0 + o);
                 }
             }
             if (in) {
@@ -121,17 +101,10 @@ __device__ __forceinline__ void adam_rect(const FusedParams& F, const int t0, co
                 for (int f = 0; f < FUSED_TF; ++f) {
                     const size_t o = (size_t)f * frame + ro + c;
                     adam4(pp[f], gg[f], mm[f], vv[f], F);
-                    if (F.tune & 4) {
-                        st_evict_first(P0 + o, pp[f]);
-                        st_evict_first(M0 + o, mm[f]);
-                        st_evict_first(V0 + o, vv[f]);
-                        if (has_grad && (flags & FLAG_REZERO)) st_evict_first(G0 + o, zero4);
-                    } else {
-                        __stcs(P0 + o, pp[f]);
-                        __stcs(M0 + o, mm[f]);
-                        __stcs(V0 + o, vv[f]);
-                        if (has_grad && (flags & FLAG_REZERO)) G0[o] = zero4;
-                    }
+                    __stcs(P0 + o, pp[f]);
+                    __stcs(M0 + o, mm[f]);
+                    __stcs(V0 + o, vv[f]);
+                    if (has_grad && (flags & FLAG_REZERO)) G0[o] = zero4;
                 }
             }
         }
@@ -152,7 +125,7 @@ __device__ __forceinline__ void zero_rect(const FusedParams& F, const int t0, co
         }
 }
 
-template <bool SMOOTH, int MODE, int HINTS, bool SIG>
+template <bool SMOOTH, int MODE>
 __global__ void __launch_bounds__(BX* BY, 3) fused_bwd_adam_kernel(const __grid_constant__ FusedParams F) {
     __shared__ int s_item;
     const int tid = threadIdx.y * BX + threadIdx.x;
@@ -188,17 +161,8 @@ __global__ void __launch_bounds__(BX* BY, 3) fused_bwd_adam_kernel(const __grid_
         }
         const int t0 = chunk * FUSED_TF;
         if (type == ITEM_BWD) {
-            // progress counters of this tile row: [group][tile row] (band schedules; sig_groups == 0: none)
-            const int G = F.R.p.sig_groups;
-            int* const sig = cnt + a.z;
-            int next_g = 0;
-            bwd_tile<FUSED_TF, SMOOTH, MODE, HINTS, SIG>(F.R, a.y, a.z, t0, kbase, first, sig, &next_g);
+            bwd_tile<FUSED_TF, SMOOTH, MODE>(F.R, a.y, a.z, t0, kbase, first);
             first = false;
-            if (G > 0) {
-                __syncthreads();
-                if (tid == 0)
-                    for (int g = next_g; g < G; ++g) sig_release_inc(sig + g * F.R.p.sig_stride);
-            }
         } else if (type == ITEM_ADAM) {
             adam_rect(F, t0, a.y, a.z, a.w, flags);
         } else {
@@ -214,10 +178,10 @@ __global__ void __launch_bounds__(BX* BY, 3) fused_bwd_adam_kernel(const __grid_
     }
 }
 
-template <bool SMOOTH, int MODE, int HINTS, bool SIG>
+template <bool SMOOTH, int MODE>
 static int launch_fused(const FusedParams& F, int ctas_per_sm, cudaStream_t st) {
     const size_t smem = MODE >= 2 ? (size_t)BWD_TMA_STAGES * FUSED_TF * TMA_BOX_BYTES : 0;
-    auto kern = fused_bwd_adam_kernel<SMOOTH, MODE, HINTS, SIG>;
+    auto kern = fused_bwd_adam_kernel<SMOOTH, MODE>;
     if (smem) {
         cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return set_err((int)ce, "fused_bwd_adam: cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
@@ -244,8 +208,7 @@ extern "C" int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads
                                    double* smooth_sums, float* grad_dyn, float* grad_sta, float* adam_m, float* adam_v,
                                    int32_t step, float lr, float beta1, float beta2, float eps, const int32_t* items,
                                    int32_t n_items, int32_t n_rounds, int32_t* counters, int32_t n_counters,
-                                   int32_t* ticket, int32_t n_groups, int32_t group_planes, int32_t group_stride,
-                                   int32_t ctas_per_sm, void* stream) {
+                                   int32_t* ticket, int32_t ctas_per_sm, void* stream) {
     if (int e = validate_view(view, quads, atlas_dyn, atlas_sta)) return e;
     VL3D_REQUIRE(grad_rgb && rgb && grad_dyn && adam_m && adam_v && atlas_dyn, VL3D_ENULL, "fused_bwd_adam: NULL pointer");
     VL3D_REQUIRE(grad_sta != nullptr || atlas_sta == nullptr, VL3D_ENULL, "grad_sta is NULL");
@@ -254,9 +217,6 @@ extern "C" int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads
     VL3D_REQUIRE(n_items >= 1 && n_counters >= 1 && n_rounds >= T / FUSED_TF && n_rounds <= T / FUSED_TF + 1, VL3D_EINVAL,
                  "fused_bwd_adam: bad schedule (n_items=%d n_rounds=%d n_counters=%d)", n_items, n_rounds, n_counters);
     VL3D_REQUIRE(step >= 1, VL3D_EINVAL, "fused_bwd_adam: step=%d", step);
-    VL3D_REQUIRE(n_groups >= 0 && n_groups <= VL3D_MAX_PLANES && (n_groups == 0 || (group_planes >= 1 && group_stride >= 1 &&
-                 (int64_t)n_groups * group_stride <= n_counters)), VL3D_EINVAL, "fused_bwd_adam: bad progress groups (%d x %d planes, stride %d)",
-                 n_groups, group_planes, group_stride);
     VL3D_REQUIRE((((uintptr_t)grad_dyn | (uintptr_t)grad_sta | (uintptr_t)adam_m | (uintptr_t)adam_v | (uintptr_t)items) & 15) == 0,
                  VL3D_EALIGN, "fused_bwd_adam: pointers must be 16-byte aligned");
     FusedParams F{};
@@ -268,7 +228,6 @@ extern "C" int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads
     p.grad_rgb = grad_rgb; p.rgb = rgb;
     p.grad_dyn = reinterpret_cast<float4*>(grad_dyn); p.grad_sta = reinterpret_cast<float4*>(grad_sta);
     p.w_smooth = w_smooth; p.smooth = smooth_sums;
-    p.sig_groups = n_groups; p.sig_group_planes = group_planes; p.sig_stride = group_stride;
     VL3D_REQUIRE(w_smooth != nullptr || smooth_sums == nullptr, VL3D_EINVAL, "smooth_sums needs w_smooth");
     F.items = reinterpret_cast<const int4*>(items);
     F.n_items = n_items; F.n_rounds = n_rounds; F.n_chunks = T / FUSED_TF; F.n_counters = n_counters;
@@ -281,21 +240,8 @@ extern "C" int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads
     F.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     cudaStream_t st = (cudaStream_t)stream;
     const bool smooth = w_smooth != nullptr;
-    const int hints = (ctas_per_sm >> 8) & 3;                       // tuning: L2 eviction hints (see bwd_tile)
-    F.tune = (ctas_per_sm >> 8) & 0xff;
-    if (F.tune & 8) {                                               // L2 set-aside for evict_last (persisting) lines
-        int dev = 0, maxp = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
-        size_t want = (size_t)maxp;
-        if (F.tune & 16) want /= 2;
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-    }
-    ctas_per_sm &= 255;
-    if (smooth && (view->flags & VL3D_VIEW_RECT_PLANES) && make_atlas_tmap(&F.R.tmap, p.view, atlas_dyn, T)) {
-        if (n_groups > 0) return (hints & 2) ? launch_fused<true, 3, 2, true>(F, ctas_per_sm, st) : launch_fused<true, 3, 0, true>(F, ctas_per_sm, st);
-        return launch_fused<true, 3, 0, false>(F, ctas_per_sm, st);
-    }
-    if (smooth) return launch_fused<true, 0, 0, false>(F, ctas_per_sm, st);
-    return launch_fused<false, 0, 0, false>(F, ctas_per_sm, st);
+    if (smooth && (view->flags & VL3D_VIEW_RECT_PLANES) && make_atlas_tmap(&F.R.tmap, p.view, atlas_dyn, T))
+        return launch_fused<true, 3>(F, ctas_per_sm, st);
+    if (smooth) return launch_fused<true, 0>(F, ctas_per_sm, st);
+    return launch_fused<false, 0>(F, ctas_per_sm, st);
 }

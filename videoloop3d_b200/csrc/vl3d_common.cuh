@@ -29,13 +29,6 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float4 v) {
                  : "memory");
 }
 
-// the same with an L2 eviction-priority hint (tma_ptx.cuh: L2_EVICT_*)
-__device__ __forceinline__ void red_add_v4_hint(float4* addr, float4 v, uint64_t policy) {
-    asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(addr), "f"(v.x), "f"(v.y),
-                 "f"(v.z), "f"(v.w), "l"(policy)
-                 : "memory");
-}
-
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

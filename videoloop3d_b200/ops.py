@@ -267,7 +267,7 @@ def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=6e-8):
 
 
 def fused_bwd_adam(view, pack, atlas_dyn, atlas_sta, T, grad_rgb, rgb, w_smooth, smooth_sums, grad_dyn, grad_sta, m, v,
-                   step, lr, beta1, beta2, eps, items, n_items, n_rounds, state, n_counters, groups=(0, 1, 1), ctas_per_sm=0):
+                   step, lr, beta1, beta2, eps, items, n_items, n_rounds, state, n_counters, ctas_per_sm=0):
     """Backward + Adam of `atlas_dyn[:T]` in one persistent kernel (csrc/fused_bwd_adam.cu).  `items`: device int32
     (n_items, 12) table from schedule.py; `state`: device int32 scratch prepared by the caller: [0] = queue head (0),
     [16:] = n_rounds x n_counters counters (each round initialised to the schedule's `counter_init`)."""
@@ -281,7 +281,7 @@ def fused_bwd_adam(view, pack, atlas_dyn, atlas_sta, T, grad_rgb, rgb, w_smooth,
               _lib.ptr(grad_rgb), _lib.ptr(rgb), _lib.ptr(w_smooth), _lib.ptr(smooth_sums), _lib.ptr(grad_dyn),
               _lib.ptr(grad_sta), _lib.ptr(m), _lib.ptr(v), int(step), float(lr), float(beta1), float(beta2), float(eps),
               _lib.ptr(items), int(n_items), int(n_rounds), C.c_void_p(state.data_ptr() + 64), int(n_counters),
-              _lib.ptr(state), int(groups[0]), int(groups[1]), int(groups[2]), int(ctas_per_sm), _lib.stream_ptr())
+              _lib.ptr(state), int(ctas_per_sm), _lib.stream_ptr())
 
 
 # ------------------------------------------------------------------------------------------------

@@ -36,7 +36,6 @@ class Schedule:
     extra_round: bool        # items of the last chunk run in one more round (generic schedule)
     kind: str
     stats: dict
-    groups: tuple = (0, 1, 1)  # progress groups: (n_groups, planes per group, counter stride between groups)
 
     @property
     def n_items(self):
@@ -93,16 +92,13 @@ def _plane_rects(table, D, qh, qw):
 
 
 def band_schedule(view_homs, cx, cy, H, W, table, D, qh, qw, dyn_h, dyn_w, smooth=True, row_block=8, col_blocks=None,
-                  zero_ahead=2, adam_lag=0, use_zero=True, margin=2, long_span=12, n_groups=4, group_lag=None):
-    """Dense layout.  The planes are split into `n_groups` progress groups; a tile publishes "my accumulation into
-    group g is complete" mid-tile (csrc/composite_lean.cuh, SIG).  Counters of a round: [g * gy + R] = tiles of tile row R
-    that have completed group g; then (zero-ahead schedules) gy counters of finished ZERO items whose first tile row is
-    R, pre-biased so that every one of them is complete at `zmax`, and one counter for the ZERO items of the few
-    long-lived rectangles (atlas rows shared by two planes: touched by the first and the last tile rows), which are
-    zeroed at the start of the round.
-    Queue order: tile row R at key R; Adam of a rectangle at (last tile row touching it) + adam_lag + group_lag * (g + 1),
-    g = the highest group whose planes touch it, group_lag = tile rows the queue advances while a tile works through one
-    group (default: resident tiles / tiles per row / n_groups)."""
+                  zero_ahead=2, adam_lag=2, use_zero=True, margin=2, long_span=12):
+    """Dense layout.  Counters of a round: [0, gy) finished tiles per tile row; (zero-ahead schedules) [gy, 2 gy)
+    finished ZERO items whose first tile row is R, pre-biased so that every one of them is complete at `zmax`, and
+    2 gy = finished ZERO items of the few long-lived rectangles (atlas rows shared by two planes: touched by the first
+    and the last tile rows), which are zeroed at the start of the round.
+    Queue order: tile row R at key R; ZERO of a rectangle `zero_ahead` tile rows before the first tile row touching it;
+    Adam `adam_lag` tile rows after the last."""
     gx, gy, sx_t, sy_t = tile_grid(H, W, smooth)
     homs = np.asarray(view_homs, dtype=np.float64).reshape(D, 3, 3)
     X0, Y0, qsx, qsy = _plane_rects(table, D, qh, qw)
@@ -155,10 +151,6 @@ def band_schedule(view_homs, cx, cy, H, W, table, D, qh, qw, dyn_h, dyn_w, smoot
     BIG = 1 << 30
     first = np.full((dyn_h, col_blocks), BIG, dtype=np.int64)       # per atlas row and column block
     last = np.full((dyn_h, col_blocks), -1, dtype=np.int64)
-    n_groups = max(1, min(int(n_groups), D))
-    gp = (D + n_groups - 1) // n_groups                             # planes per group
-    n_groups = (D + gp - 1) // gp
-    grp = np.full((dyn_h, col_blocks), -1, dtype=np.int64)          # highest plane group touching
     ys = np.arange(dyn_h)
     for d in range(D):
         idx = np.nonzero(touches[d])[0]
@@ -180,14 +172,10 @@ def band_schedule(view_homs, cx, cy, H, W, table, D, qh, qw, dyn_h, dyn_w, smoot
                 continue
             first[hit, cb] = np.minimum(first[hit, cb], fR[hit])
             last[hit, cb] = np.maximum(last[hit, cb], lR[hit])
-            grp[hit, cb] = np.maximum(grp[hit, cb], d // gp)
     # row blocks
     pad = n_rb * row_block - dyn_h
     fb = np.pad(first, ((0, pad), (0, 0)), constant_values=BIG).reshape(n_rb, row_block, col_blocks).min(1)
     lb = np.pad(last, ((0, pad), (0, 0)), constant_values=-1).reshape(n_rb, row_block, col_blocks).max(1)
-    gb = np.pad(grp, ((0, pad), (0, 0)), constant_values=-1).reshape(n_rb, row_block, col_blocks).max(1)
-    if group_lag is None:
-        group_lag = 148 * 3 / max(gx, 1) / n_groups
 
     # ---- items (vectorised: this runs once per view)
     rb_i, cb_i = np.meshgrid(np.arange(n_rb), np.arange(col_blocks), indexing="ij")
@@ -197,9 +185,9 @@ def band_schedule(view_homs, cx, cy, H, W, table, D, qh, qw, dyn_h, dyn_w, smoot
     base = r0 * dyn_w + edges[cb_i]
     width = edges[cb_i + 1] - edges[cb_i]
     nr = np.minimum(row_block, dyn_h - r0)
-    f, l, sg = fb.reshape(-1), lb.reshape(-1), gb.reshape(-1)
+    f, l = fb.reshape(-1), lb.reshape(-1)
     keep = width > 0
-    rb_i, cb_i, base, width, nr, f, l, sg = (v[keep] for v in (rb_i, cb_i, base, width, nr, f, l, sg))
+    rb_i, cb_i, base, width, nr, f, l = (v[keep] for v in (rb_i, cb_i, base, width, nr, f, l))
     touched = l >= 0
     n_untouched = int((~touched).sum())
     aligned = (base % 8 == 0) & (width % 8 == 0) & (dyn_w % 8 == 0)
@@ -207,19 +195,20 @@ def band_schedule(view_homs, cx, cy, H, W, table, D, qh, qw, dyn_h, dyn_w, smoot
 
     tiles = _rows(gx * gy, ITEM_BWD)
     tiles[:, C_A], tiles[:, C_B] = np.tile(np.arange(gx), gy), np.repeat(np.arange(gy), gx)
-    tile_keys = tiles[:, C_B].astype(np.float64)                    # (tiles publish through the progress counters)
+    tiles[:, C_SIG] = tiles[:, C_B]
+    tile_keys = tiles[:, C_B].astype(np.float64)
 
     adam = _rows(len(base), ITEM_ADAM)
     adam[:, C_A], adam[:, C_B], adam[:, C_C] = base, width, nr
     fl = np.where(touched, FLAG_HAS_GRAD | np.where(use_zero & aligned, 0, FLAG_REZERO), 0)
     adam[:, C_TYPE] = ITEM_ADAM | (fl << 4)
-    adam[touched, C_W0] = (sg * gy + f)[touched]
+    adam[touched, C_W0] = f[touched]
     adam[touched, C_WN] = (l - f + 1)[touched]
     adam[touched, C_WT] = gx
-    adam_keys = np.where(touched, l + adam_lag + group_lag * (sg + 1) + 0.25, 0.0)
+    adam_keys = np.where(touched, l + adam_lag + 0.25, 0.0)
     adam_keys[~touched] = (np.arange(n_untouched) + 0.5) * gy / max(n_untouched, 1)     # g = 0: any time
 
-    zb = n_groups * gy                                              # first ZERO counter
+    zb = gy                                                         # first ZERO counter
     init = np.zeros(zb, dtype=np.int64)
     parts, keys = [tiles, adam], [tile_keys, adam_keys]
     n_zero = 0
@@ -255,8 +244,7 @@ def band_schedule(view_homs, cx, cy, H, W, table, D, qh, qw, dyn_h, dyn_w, smoot
     out = allitems[order].astype(np.int32)
     return Schedule(items=out, counter_init=init.astype(np.int32), extra_round=False, kind="band-zero" if use_zero else "band",
                     stats=dict(tiles=gx * gy, adam=len(adam), zero=n_zero, untouched=n_untouched,
-                               long_lived=int(long_lived.sum()), max_wait=int(out[:, C_WN].max()), groups=n_groups),
-                    groups=(n_groups, gp, gy))
+                               long_lived=int(long_lived.sum()), max_wait=int(out[:, C_WN].max())))
 
 
 def validate(s: Schedule):
@@ -272,9 +260,6 @@ def validate(s: Schedule):
                     assert np.all(cnt[w0:w0 + wn] >= wt), f"item {k} waits for counters {w0}..{w0 + wn - 1} >= {wt}: {cnt[w0:w0 + wn]}"
         if it[k, C_SIG] >= 0:
             cnt[it[k, C_SIG]] += 1
-        if (it[k, C_TYPE] & 15) == ITEM_BWD and s.groups[0] > 0:    # a tile publishes every progress group of its row
-            for g in range(s.groups[0]):
-                cnt[g * s.groups[2] + it[k, C_B]] += 1
     final = cnt
     for k in range(len(it)):                                        # previous-round waits: against the final counts
         if (it[k, C_TYPE] >> 4) & FLAG_PREV_ROUND and it[k, C_WN] > 0:

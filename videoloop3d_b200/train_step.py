@@ -162,8 +162,9 @@ class FusedLoopStep:
         "band" / "band-zero": the same kernel walking the screen in row bands so that a band's gradient rows stay
         L2-resident between accumulation and Adam (dense layout only; "-zero": rows are zeroed just ahead of the
         band and dropped after Adam instead of living in HBM as zeros);
-        None: VL3D_FUSED from the environment (read once, here), else "auto" = band-zero for the dense layout,
-        generic otherwise."""
+        None: VL3D_FUSED from the environment (read once, here), else "auto" = generic (on B200 the band schedules do
+        not keep the gradient on chip under the DRAM-saturating Adam traffic and are slower:
+        profiles/r02_fused_bwd_adam.md)."""
         if not model.atlas_dyn.is_cuda:
             raise Vl3dError("FusedLoopStep needs the model on a CUDA device")
         self.model = model
@@ -195,7 +196,7 @@ class FusedLoopStep:
         if self.fused not in ("off", "generic", "band", "band-zero", "auto"):
             raise ValueError(f"fused={self.fused!r}")
         self.fused_opts = dict(fused_opts or {})
-        for k, cast in (("ctas_per_sm", int), ("row_block", int), ("zero_ahead", int), ("adam_lag", int), ("seg_texels", int), ("groups", int), ("group_lag", float)):
+        for k, cast in (("ctas_per_sm", int), ("row_block", int), ("zero_ahead", int), ("adam_lag", int), ("seg_texels", int)):
             e = os.environ.get("VL3D_FUSED_" + k.upper())
             if e is not None and k not in self.fused_opts:
                 self.fused_opts[k] = cast(e)
@@ -246,8 +247,7 @@ class FusedLoopStep:
                 sched = schedule.band_schedule(homs, view.cx, view.cy, h, w, pack.table, pack.D, pack.qh, pack.qw, dyn_hw[0],
                                                dyn_hw[1], smooth, row_block=o.get("row_block", 8),
                                                zero_ahead=o.get("zero_ahead", 2), adam_lag=o.get("adam_lag", 2),
-                                               use_zero=(mode == "band-zero"), n_groups=o.get("groups", 4),
-                                               group_lag=o.get("group_lag", None))
+                                               use_zero=(mode == "band-zero"))
             dev = self.model.atlas_dyn.device
             sched.dev_items = torch.from_numpy(np.ascontiguousarray(sched.items)).to(dev)
             sched.dev_init = torch.from_numpy(sched.counter_init).to(dev)
@@ -429,7 +429,7 @@ class FusedLoopStep:
         self.t += 1
         mode = self.fused
         if mode == "auto":
-            mode = "band-zero" if pack.rect_planes else "generic"
+            mode = "generic"
         if mode.startswith("band") and not pack.rect_planes:
             mode = "generic"
         Te = Tl // 2 * 2 if mode != "off" else 0                   # frames handled by the fused kernel (chunks of 2)
@@ -447,7 +447,7 @@ class FusedLoopStep:
                 ops.fused_bwd_adam(view, pack, dyn_local[:Te], atlas.data, Te, grad_rgb[t0:t0 + Te], rgb_pad[t0:t0 + Te],
                                    w_smooth, bwd_sums, g_dyn[:Te], g_sta, st[0][:Te], st[1][:Te], self.t, lr,
                                    self.betas[0], self.betas[1], self.eps, sched.dev_items, sched.n_items, n_rounds,
-                                   state, sched.n_counters, groups=sched.groups, ctas_per_sm=self.fused_opts.get("ctas_per_sm", 0))
+                                   state, sched.n_counters, ctas_per_sm=self.fused_opts.get("ctas_per_sm", 0))
         if Te < Tl:
             # separate kernels: everything when fused == "off", else the odd last frame
             g_dyn = self._buf.get("g_dyn")
