@@ -53,7 +53,8 @@ def test_render_and_backward_match_oracle(mname, vname):
     from videoloop3d_b200.testing import model_from_tensors
     dev = torch.device("cuda:0")
     H, W = 37, 70
-    seed = (hash(mname + vname) % 997) + 1
+    # a literal, reproducible seed per case (Python's hash() of a str is randomised per process)
+    seed = 1 + 17 * sorted(MODELS).index(mname) + 5 * sorted(VIEWS).index(vname)
     st = _build(mname, H, W, seed)
     v = VIEWS[vname]
     ext = torch.eye(4)

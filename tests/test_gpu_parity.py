@@ -228,9 +228,9 @@ def test_fused_step_matches_oracle(case):
         assert float(err.max()) <= 4 * w_max + 2e-4 * float(ref.abs().max())
         n_off = int((err > 2e-4 * ref.abs().max()).sum())
         assert n_off <= max(64, 2e-4 * ref.numel()), f"{n_off} texel gradients off"
-    # fused path on a fresh copy of the model
+    # FusedLoopStep on a fresh copy of the model, separate kernels (the gradient buffer can be inspected)
     m2 = model_from_tensors(state_tensors(st), H, W, dev(), swd_patcht_size=case["pt"])
-    step = FusedLoopStep(m2)
+    step = FusedLoopStep(m2, fused="off")
     out = step.step(H, W, ext.to(dev()), intr.to(dev()), res.to(dev()), cfg, lr=0.01)
     assert abs(float(out["loss"]) - float(loss_c)) < 1e-5 * abs(float(loss_c))
     g_dyn = step._buf["g_dyn"]
@@ -241,6 +241,17 @@ def test_fused_step_matches_oracle(case):
     # a second step keeps running (Adam state, buffers re-used)
     out2 = step.step(H, W, ext.to(dev()), intr.to(dev()), res.to(dev()), cfg, lr=0.01)
     assert torch.isfinite(out2["loss"]) and step.t == 2
+    # the default path (backward + Adam in one persistent kernel): same losses, same first moment, same update
+    m3 = model_from_tensors(state_tensors(st), H, W, dev(), swd_patcht_size=case["pt"])
+    step3 = FusedLoopStep(m3)
+    out3 = step3.step(H, W, ext.to(dev()), intr.to(dev()), res.to(dev()), cfg, lr=0.01)
+    assert step3.last_schedule is not None
+    assert abs(float(out3["loss"]) - float(out["loss"])) < 1e-6 * abs(float(out["loss"]))
+    assert relerr(step3._state["atlas_dyn"][0].cpu(), 0.1 * g_dyn.cpu()) < 1e-5
+    d = (m3.atlas_dyn.detach().cpu() - p_ref).abs()                  # Adam's eps = 6e-8: a ~0 gradient may flip sign
+    assert float((d > 1e-5).float().mean()) < 2e-4 and float(d.median()) < 1e-7
+    out3b = step3.step(H, W, ext.to(dev()), intr.to(dev()), res.to(dev()), cfg, lr=0.01)
+    assert abs(float(out3b["loss"]) - float(out2["loss"])) < 2e-5 * abs(float(out2["loss"]))
 
 
 def test_render_edge_cases():
