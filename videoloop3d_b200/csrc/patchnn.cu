@@ -955,26 +955,31 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
         P.row0 = row_begin; P.row1 = row_end;
         P.nta = (tx_used + 3) / 4;
         if (P.nta < 2) P.nta = 2;
-        // candidate chunk width: 4*ntb frames per sweep; pick the ntb that wastes the fewest frame-sweeps
-        {
-            const int ty_used = (desc->n2 - 1) * desc->st + desc->pt;
-            int best_ntb = 0; long long best_cost = 0;
-            const int ntb_max = NN_THREADS / P.nta;
-            for (int ntb = (desc->pt + 3) / 4 + 1; ntb <= ntb_max; ++ntb) {
-                const int cands = (4 * ntb - desc->pt) / desc->st + 1;
-                const int chunks = (desc->n2 + cands - 1) / cands;
-                const long long cost = (long long)chunks * 4 * ntb * 64 + 2000LL * chunks;   // + per-chunk overhead
-                if (P.nta * ntb < 64 && 4 * ntb < ty_used) continue;   // keep at least two warps busy
-                if (best_ntb == 0 || cost < best_cost) { best_ntb = ntb; best_cost = cost; }
-            }
-            if (best_ntb == 0) best_ntb = ntb_max;
-            P.ntb = best_ntb;
-        }
         const int rows = row_end - row_begin;
         int SL = 16;                                                // longer strips share more rows, shorter ones fill the GPU
         while (SL > 2 && (long long)desc->wo * ((rows + SL - 1) / SL) < 148 * 6) SL >>= 1;
         if (SL > rows) SL = rows;
         P.SL = SL;
+        // candidate chunk width: 4*ntb frames per sweep; pick the ntb that wastes the fewest frame-sweeps among those
+        // whose staging buffers fit in shared memory (few query frames => many threads left for candidates: a wide
+        // chunk of a large patch would not fit)
+        {
+            const int ty_used = (desc->n2 - 1) * desc->st + desc->pt;
+            int best_ntb = 0, widest = 0; long long best_cost = 0;
+            const int ntb_max = NN_THREADS / P.nta;
+            const int ntb_min = (desc->pt + 3) / 4 + 1;
+            for (int ntb = ntb_min; ntb <= ntb_max; ++ntb) {
+                const int cands = (4 * ntb - desc->pt) / desc->st + 1;
+                const int chunks = (desc->n2 + cands - 1) / cands;
+                const long long cost = (long long)chunks * 4 * ntb * 64 + 2000LL * chunks;   // + per-chunk overhead
+                if (ntb > ntb_min && strip_smem_bytes(desc, P.nta, ntb, SL, NB) > 200 * 1024) break;
+                widest = ntb;
+                if (P.nta * ntb < 64 && 4 * ntb < ty_used) continue;   // keep at least two warps busy
+                if (best_ntb == 0 || cost < best_cost) { best_ntb = ntb; best_cost = cost; }
+            }
+            if (best_ntb == 0) best_ntb = widest;
+            P.ntb = best_ntb;
+        }
         const int P4 = (desc->p + 3) / 4 * 4;
         const bool vec = desc->s % 4 == 0 && (3 * desc->p + 3) / 4 == 3 * P4 / 4 &&
                          ((desc->x_sf | desc->x_sc | desc->x_sr | desc->y_sf | desc->y_sc | desc->y_sr) & 3) == 0 &&
