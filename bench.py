@@ -35,6 +35,8 @@ WORKLOADS = {
     "step720p": dict(H=720, W=1280, D=32, T=48, F=258, hv=36, wv=64),
     "step360p": dict(H=360, W=640, D=32, T=48, F=258, hv=36, wv=64),
     "patch180": dict(H=180, W=320, D=32, T=48, F=258, hv=36, wv=64),      # the reference's own step shape
+    # SURVEY §8(d) "sparse": Bernoulli(0.25) tile occupancy, half static / half dynamic, 32x32-texel tiles
+    "sparse720p": dict(H=720, W=1280, D=32, T=48, F=258, hv=36, wv=64, sparse=dict(tile=32, occupancy=0.25, dyn_frac=0.5)),
     "tiny": dict(H=45, W=80, D=8, T=6, F=12, hv=6, wv=9),
 }
 CPU_SAMPLE = dict(H=90, W=160, D=32, T=48, F=258, hv=36, wv=64)             # 1/64 of the 720p frame
@@ -83,6 +85,11 @@ def build_model(wl, device, frames, seed=2, first_frame=0):
     m.atlas.data = m.atlas.data[:, :, :1, :1].clone()             # dummy static atlas (MPV.py:266)
     m.atlas_dyn.data = m.atlas_dyn.data[:, :, :1, :1].clone()
     m = m.to(device)
+    if wl.get("sparse"):
+        from videoloop3d_b200.testing import cull_to_tiles
+        sp = wl["sparse"]
+        return cull_to_tiles(m, sp["tile"], sp["occupancy"], sp["dyn_frac"], frames, seed=seed, device=device,
+                             first_frame=first_frame)
     g = torch.Generator(device=device)
     tex = torch.empty((frames, hd, wd, 4), dtype=torch.float32, device=device)
     for t in range(frames):
@@ -154,10 +161,14 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
-# `ncu --set full` capture of this same command (profiles/r01c_ncu_full_step720p.md); None if not captured.
-NCU_TRAFFIC_BYTES = {("step720p", 1, "composite_bwd"): 42.817052e9 + 20.455665e9,
-                     ("step720p", 1, "composite_fwd"): 21.071395e9 + 0.553144e9}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu capture of this
+# same workload (source file named in the line); None where nothing was captured.  A bench run cannot read DRAM
+# counters itself, so this is the capture's value, not a measurement of the run that prints it.
+NCU_TRAFFIC_BYTES = {
+    ("step720p", 1, "fused_bwd_adam"): (139.9e9 + 112.9e9, "profiles/r02_fused_bwd_adam.md (run r02g, generic schedule)"),
+    ("step720p", 1, "composite_bwd"): (42.817052e9 + 20.455665e9, "profiles/r01c_ncu_full_step720p.md"),
+    ("step720p", 1, "composite_fwd"): (21.071395e9 + 0.553144e9, "profiles/r01c_ncu_full_step720p.md"),
+}
 
 
 def algorithmic_bytes(wl, frames):
@@ -323,6 +334,134 @@ def run_reference(args):
     emit_line(line)
 
 
+
+# --------------------------------------------------------------------------------------------------
+# extra measurements carried by the default line
+# --------------------------------------------------------------------------------------------------
+def time_steps(step, call, steps, warmup, barrier):
+    """ms per step (CUDA events on the launching stream, max over ranks) + per-kernel ms of `steps` calls."""
+    import torch.distributed as dist
+    for _ in range(warmup):
+        call()
+    barrier()
+    n0 = {k: len(v) for k, v in (step.timers or {}).items()}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = call()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    kms = {}
+    for k, evs in (step.timers or {}).items():
+        evs = evs[n0.get(k, 0):]
+        if evs:
+            kms[k] = round(sum(a.elapsed_time(b) for a, b in evs) / len(evs), 4)
+    return float(ms) / steps, kms, out
+
+
+def loss_sweep(dev, extents=((180, 320),), ps=(7, 11, 15), Ts=(24, 48, 96), n2s=(256, 1024, 4096), reps=2):
+    """BASELINE config 5: the looping-loss kernels (NN search + vote / robust loss / gradient) over patch size, video
+    length and candidate-set size; reference-view config otherwise (pt=3, s=4, st=1, alpha=0, rou=-2).  ms per call."""
+    from videoloop3d_b200 import ops
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(5)
+    for (h, w) in extents:
+        y_all = torch.rand((max(n2s) + 2, 3, h, w), device=dev, generator=g)
+        for T in Ts:
+            x = torch.rand((T + 2, 3, h, w), device=dev, generator=g)
+            xs = torch.ones(1, device=dev)
+            for n2 in n2s:
+                y = y_all[:n2 + 2]
+                for p in ps:
+                    desc = ops.make_loss_desc(x.shape, (x.stride(0), x.stride(1), x.stride(2)), y.shape,
+                                              (y.stride(0), y.stride(1), y.stride(2)), p, 3, 4, 1, 0.0)
+                    nn = torch.empty((desc.ho, desc.wo, desc.n1), dtype=torch.int32, device=dev)
+                    grad = torch.empty_like(x)
+                    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                    for r in range(1 + reps):
+                        if r == 1:
+                            ev[0].record()
+                        ops.patchnn_search(desc, x, None, y, nn_out=nn)
+                    ev[1].record()
+                    for r in range(reps):
+                        ops.vote_loss(desc, x, xs, y, nn, "-2", 0.1, 1.0, (T + 2, h, w), grad_out=grad)
+                    ev[2].record()
+                    torch.cuda.synchronize()
+                    out[f"{h}x{w}_p{p}_T{T}_n{n2}"] = {"search_ms": round(ev[0].elapsed_time(ev[1]) / reps, 3),
+                                                       "vote_ms": round(ev[1].elapsed_time(ev[2]) / reps, 3)}
+        del y_all
+    return out
+
+
+def config0_static_render(dev):
+    """BASELINE configs[0]: single-view MPI render, D=8 planes, 256x256, static frame — the reference's CPU path
+    (oracle port, all host threads) next to the same render through libvl3d on the GPU."""
+    from oracle import mpv_oracle as MO
+    from videoloop3d_b200.testing import model_from_tensors
+    H = W = 256
+    st = MO.sparse_state(H, W, 8, 9, 9, 1, 1.0, 10.0, tile=32, occupancy=1.0, dyn_frac=0.0, h_scale=1.0, w_scale=1.0, seed=2)
+    wl = dict(H=H, W=W)
+    ext, intr = view_for(wl)
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    n = 3
+    for _ in range(n):
+        rgb_o, _ = MO.render(st, H, W, ext, intr, [0], dtype=torch.float32)
+    cpu_ms = (time.perf_counter() - t0) / n * 1e3
+    tens = dict(verts=st.verts, planedepth=st.planedepth, faces=st.faces, faces_dyn=st.faces_dyn, uvs=st.uvs,
+                uvs_dyn=st.uvs_dyn, uvfaces=st.uvfaces, uvfaces_dyn=st.uvfaces_dyn, atlas=st.atlas, atlas_dyn=st.atlas_dyn,
+                ref_extrin=st.ref_extrin, ref_intrin=st.ref_intrin, mpi_d=8, hv=9, wv=9)
+    m = model_from_tensors(tens, H, W, dev)
+    m.eval()
+    with torch.no_grad():
+        for _ in range(3):
+            rgb, _ = m(H, W, ext, intr, ts=[0])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            rgb, _ = m(H, W, ext, intr, ts=[0])
+        e1.record()
+        torch.cuda.synchronize()
+    err = float((rgb[0].permute(1, 2, 0).cpu() - rgb_o[0]).abs().max())
+    return {"workload": "D=8, 256x256, static atlas, one frame (BASELINE configs[0])", "cpu_ms": round(cpu_ms, 3),
+            "cpu_kind": "port", "cores": os.cpu_count() or 1, "gpu_ms_per_call": round(e0.elapsed_time(e1) / 20, 4),
+            "max_abs_diff": err}
+
+
+def sharded_check(dev, group, world, rank):
+    """Before timing at N > 1: two optimisation steps of a small dense model (the reference's step shape, 180x320,
+    D=32, T=16) — sharded over the ranks vs. every rank computing the whole thing alone — must give the same frames,
+    the same NN map and the same parameters on the frames a rank owns."""
+    import torch.distributed as dist
+    from videoloop3d_b200 import FusedLoopStep
+    from videoloop3d_b200.train_step import loss_config
+    wl = dict(H=180, W=320, D=32, T=16, F=34, hv=9, wv=16)
+    T = wl["T"]
+    t0, t1 = (T * rank) // world, (T * (rank + 1)) // world
+    full = build_model(wl, dev, T, seed=5)
+    shard = build_model(wl, dev, t1 - t0, seed=5, first_frame=t0)
+    assert torch.equal(full.atlas_dyn.data[t0:t1], shard.atlas_dyn.data)
+    cfg = loss_config(full.args, ref_view=True)
+    ext, intr = view_for(wl)
+    res = make_target(wl, dev)
+    a = FusedLoopStep(full)
+    b = FusedLoopStep(shard, group=group, global_frames=T)
+    for _ in range(2):
+        oa = a.step(wl["H"], wl["W"], ext, intr, res, cfg, 0.005)
+        ob = b.step(wl["H"], wl["W"], ext, intr, res, cfg, 0.005)
+    torch.cuda.synchronize()
+    d = (full.atlas_dyn.data[t0:t1] - shard.atlas_dyn.data).abs()
+    stats = torch.tensor([float(d.max()), float((d > 1e-5).float().mean()),
+                          abs(float(oa["loss"]) - float(ob["loss"])) / abs(float(oa["loss"])),
+                          float((a._buf["nn"] != b._buf["nn"]).sum())], device=dev, dtype=torch.float64)
+    dist.all_reduce(stats, op=dist.ReduceOp.MAX, group=group)
+    return {"workload": "dense 180x320, D=32, T=16, F=34, 2 steps", "max_abs_dparam": float(stats[0]),
+            "frac_dparam_gt_1e-5": float(stats[1]), "loss_rel_diff": float(stats[2]), "nn_mismatches": int(stats[3])}
+
+
 # --------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
@@ -340,6 +479,47 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    extras = not args.quick and args.workload == "step720p"
+    check = sharded_check(dev, group, world, rank) if (world > 1 and not args.quick) else None
+    torch.cuda.empty_cache()
+    line = measure_main(args, world, rank, local, dev, group, barrier, extras)
+    torch.cuda.empty_cache()
+    if extras:
+        more = measure_extras(args, world, rank, dev, group, barrier)
+        if rank == 0:
+            line.update(more)
+    if rank == 0:
+        if check is not None:
+            line["sharded_check"] = check
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_entry(args)
+        emit_line(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_entry(args):
+    wl = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    sample = dict(CPU_SAMPLE) if args.workload in ("step720p", "sparse720p") else dict(wl)
+    ratio = (wl["H"] * wl["W"]) / (sample["H"] * sample["W"])
+    sec = cpu_reference_step(sample, threads, 1, warmup=0)
+    return {"value": 1.0 / (sec * ratio), "unit": "steps/s", "cores": threads, "kind": "port",
+            "sample": f"oracle port of the reference's PyTorch CPU path on one {sample['H']}x{sample['W']} "
+                      f"patch (1/{ratio:.0f} of the frame), D={sample['D']}, T={sample['T']}, F={sample['F']}: "
+                      f"{sec:.2f} s, scaled x{ratio:.0f}"}
+
+
+def measure_main(args, world, rank, local, dev, group, barrier, extras):
+    """The headline workload: resident-input arm (`value`), end-to-end arm (`e2e`), per-kernel times, roofline."""
+    import torch.distributed as dist
+    from videoloop3d_b200 import FusedLoopStep, _lib
+    from videoloop3d_b200.train_step import loss_config
     wl = WORKLOADS[args.workload]
     T = wl["T"]
     t0, t1 = (T * rank) // world, (T * (rank + 1)) // world
@@ -353,11 +533,6 @@ def run_ours(args):
     res_dev = make_target(wl, dev)
     lr = margs.lrate * 0.01
     step = FusedLoopStep(model, group=group, global_frames=T, timers=True, fused=args.fused)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     # ---------------- resident-input arm (value) ----------------
     for _ in range(args.warmup):
@@ -496,24 +671,96 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, world, dom)), "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes),
+                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, world, dom), (None, None))[0],
+                         "traffic_source": NCU_TRAFFIC_BYTES.get((args.workload, world, dom), (None, None))[1], "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes),
                          "ms_per_launch": kernel_ms[dom]},
             "kernels_ms": {k: round(v, 4) for k, v in kernel_ms.items()},
             "composite": comp,
             "final_loss": final_loss,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            sample = dict(CPU_SAMPLE) if args.workload == "step720p" else dict(wl)
-            ratio = (H * W) / (sample["H"] * sample["W"])
-            sec = cpu_reference_step(sample, threads, 1, warmup=0)
-            line["cpu_baseline"] = {"value": 1.0 / (sec * ratio), "unit": "steps/s", "cores": threads, "kind": "port",
-                                    "sample": f"oracle port of the reference's PyTorch CPU path on one {sample['H']}x{sample['W']} "
-                                              f"patch (1/{ratio:.0f} of the frame), D={sample['D']}, T={sample['T']}, F={sample['F']}: "
-                                              f"{sec:.2f} s, scaled x{ratio:.0f}"}
-        emit_line(line)
+    else:
+        line = None
+    if extras:
+        # the configuration the other ~8 of 9 training views use (configs/mpv_base.txt:60-68): p=3, pt=3, s=2, alpha=None
+        cfg_o = loss_config(margs, ref_view=False)
+        ms_o, kms_o, out_o = time_steps(step, lambda: step.step(H, W, ext, intr, res_dev, cfg_o, lr), 3, 1, barrier)
+        if rank == 0:
+            line["other_view"] = {"loss": "gpnn_lm p=3 pt=3 s=2 alpha=None rou=-2 + rgb/a smooth 0.2 + scale-invariant",
+                                  "ms_per_step": ms_o, "steps_per_s": 1000.0 / ms_o, "kernels_ms": kms_o,
+                                  "final_loss": float(out_o["loss"])}
+    return line
+
+
+def measure_extras(args, world, rank, dev, group, barrier):
+    """Further workloads of the same path (all ranks take part in the sharded ones; the rest is N = 1 only)."""
+    from videoloop3d_b200 import FusedLoopStep
+    from videoloop3d_b200.train_step import loss_config
+    more = {}
+    # ---- tile-culled model with static + dynamic tiles: per-thread loads, static-gradient all-reduce
+    wl = WORKLOADS["sparse720p"]
+    T = wl["T"]
+    t0, t1 = (T * rank) // world, (T * (rank + 1)) // world
+    model = build_model(wl, dev, t1 - t0, seed=2, first_frame=t0)
+    cfg = loss_config(model.args, ref_view=True)
+    ext, intr = view_for(wl)
+    res = make_target(wl, dev)
+    lr = model.args.lrate * 0.01
+    step = FusedLoopStep(model, group=group, global_frames=T, timers=True, fused=args.fused)
+    H, W = wl["H"], wl["W"]
+    ms_s, kms_s, out_s = time_steps(step, lambda: step.step(H, W, ext, intr, res, cfg, lr), 5, 2, barrier)
+    pack = model.mesh_pack()
+    more["sparse"] = {"workload": "sparse720p: Bernoulli(0.25) tile occupancy, half static / half dynamic, 32x32-texel tiles, "
+                                  "D=32, T=48, 720x1280, F=258, ref-view loss", "static_tiles": pack.n_static,
+                      "dynamic_tiles": pack.n_dynamic, "atlas_dyn": list(model.atlas_dyn.shape), "atlas": list(model.atlas.shape),
+                      "ms_per_step": ms_s, "steps_per_s": 1000.0 / ms_s, "kernels_ms": kms_s, "final_loss": float(out_s["loss"])}
+    del step, model, res
+    torch.cuda.empty_cache()
     if world > 1:
-        dist.destroy_process_group()
+        return more
+    # ---- the reference's own step shape (configs/mpv_base.txt:21-24): host overhead shows here
+    wl = WORKLOADS["patch180"]
+    model = build_model(wl, dev, wl["T"], seed=2)
+    cfg = loss_config(model.args, ref_view=True)
+    ext, intr = view_for(wl)
+    res = make_target(wl, dev)
+    step = FusedLoopStep(model, timers=False, fused=args.fused)
+    H, W = wl["H"], wl["W"]
+    ms_p, _, out_p = time_steps(step, lambda: step.step(H, W, ext, intr, res, cfg, lr), 30, 5, barrier)
+    t_host = time.perf_counter()
+    for _ in range(30):
+        step.step(H, W, ext, intr, res, cfg, lr)
+    host_ms = (time.perf_counter() - t_host) / 30 * 1e3               # launch-side time of a step (no sync inside)
+    torch.cuda.synchronize()
+    more["patch180"] = {"workload": "dense 180x320 (the reference's step shape), D=32, T=48, F=258, ref-view loss",
+                        "ms_per_step": ms_p, "steps_per_s": 1000.0 / ms_p, "host_ms_per_step": host_ms,
+                        "final_loss": float(out_p["loss"])}
+    del step, model, res
+    torch.cuda.empty_cache()
+    # ---- BASELINE config 5 sweep and config 0
+    more["loss_sweep_ms"] = loss_sweep(dev)
+    more["loss_sweep_ms"].update(loss_sweep(dev, extents=((720, 1280),), Ts=(48,), n2s=(256,)))
+    torch.cuda.empty_cache()
+    more["config0"] = config0_static_render(dev)
+    # ---- the reference's torch operator sequence on this same GPU (the north_star's ">= 10x" denominator)
+    if not args.no_gpu_reference:
+        torch.cuda.empty_cache()
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        sampler = ClockSampler(0)
+        sampler.start()
+        try:
+            ms_pt, ms_ad, n, (ph, pw) = gpu_torch_reference_step(WORKLOADS["step720p"], dev, 3)
+            more["gpu_reference"] = {"ms_per_step": ms_pt + ms_ad, "steps_per_s": 1000.0 / (ms_pt + ms_ad), "repetitions": 3,
+                                     "parts_ms": {"patches_fwd_bwd": ms_pt, "adam": ms_ad}, "clocks": sampler.stop(),
+                                     "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9,
+                                     "what": f"the reference's torch operator sequence (oracle/torch_ref_ops.py: grid_sample / "
+                                             f"masked_scatter / cumprod / unfold / bmm / index_add, allow_tf32=False) on this GPU: "
+                                             f"{n} patches of {ph}x{pw} covering 720x1280, gradients accumulated, one "
+                                             f"torch.optim.Adam step; host rasteriser stand-in not timed"}
+        except torch.cuda.OutOfMemoryError as ex:
+            sampler.stop()
+            more["gpu_reference"] = {"unavailable": f"out of memory: {str(ex)[:100]}"}
+    return more
 
 
 class _OnlyJsonOnStdout:
@@ -558,6 +805,8 @@ def main():
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference: host CPU (the reference arm) or the reference's torch operators on cuda:0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-operators-on-GPU leg")
+    ap.add_argument("--quick", action="store_true", help="headline workload only (no sparse / patch180 / sweep / config0 legs)")
     ap.add_argument("--no-smooth", action="store_true", help="tuning aid: drop the smoothness regularisers")
     ap.add_argument("--fused", default=None, choices=["off", "generic", "band", "band-zero", "auto"],
                     help="backward + Adam: separate kernels or one persistent kernel (default: VL3D_FUSED, else auto)")

@@ -233,7 +233,7 @@ def test_fused_step_matches_oracle(case):
     step = FusedLoopStep(m2, fused="off")
     out = step.step(H, W, ext.to(dev()), intr.to(dev()), res.to(dev()), cfg, lr=0.01)
     assert abs(float(out["loss"]) - float(loss_c)) < 1e-5 * abs(float(loss_c))
-    g_dyn = step._buf["g_dyn"]
+    g_dyn = step._buf["g_dyn"].clone()                                  # (the buffer is reused by the next step)
     assert relerr(g_dyn.cpu(), m.atlas_dyn.grad.cpu()) < 1e-5           # same kernels, same inputs
     p_ref, _, _ = MO.adam_step(st.atlas_dyn, g_dyn.cpu(), torch.zeros_like(st.atlas_dyn), torch.zeros_like(st.atlas_dyn),
                                1, 0.01)

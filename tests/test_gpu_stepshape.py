@@ -65,20 +65,26 @@ def test_reference_step_shape_matches_oracle(layout, cfg):
     assert pack.rect_planes == (layout == "dense")
     assert step.last_schedule is not None and step.last_schedule.kind == "generic"
 
-    a = st.atlas.float().requires_grad_(True)
-    ad = st.atlas_dyn.float().requires_grad_(True)
-    extra, aux = MO.forward_train(st, H, W, ext, intr, res, cfg, dtype=torch.float32, atlas=a, atlas_dyn=ad)
+    # NN search on IDENTICAL inputs: the oracle's float64 search over the video the CUDA path searched (its own render
+    # times its own gain) must select the same indices, except where two candidates tie to 1e-5 in float64
+    x_cuda = step._buf["x_scaled"].cpu().double().permute(1, 0, 2, 3)[None]
+    y64 = res.permute(0, 2, 1, 3, 4).double()
+    lcfg = {k: cfg[k] for k in ("patch_size", "patcht_size", "stride", "stridet", "alpha", "rou", "scaling")}
+    _, aux_nn = LL.gpnn_lowmem(x_cuda, y64, macro_block=65, **lcfg)
     nn_c = step._buf["nn"].cpu().long()
-    assert nn_c.shape == aux["nn"].shape
-    mism = int((nn_c != aux["nn"]).sum())
+    assert nn_c.shape == aux_nn["nn"].shape
+    mism = int((nn_c != aux_nn["nn"]).sum())
     if mism:
-        ycrop = res.permute(0, 2, 1, 3, 4).double()[..., :aux["x"].shape[-2], :aux["x"].shape[-1]]
-        mism, bad = LL.tie_margin_ok(aux["x"].detach().double(), ycrop, aux["nn"], nn_c, cfg["patch_size"], cfg["patcht_size"],
+        ycrop = y64[..., :aux_nn["x"].shape[-2], :aux_nn["x"].shape[-1]]
+        mism, bad = LL.tie_margin_ok(aux_nn["x"].detach(), ycrop, aux_nn["nn"], nn_c, cfg["patch_size"], cfg["patcht_size"],
                                      cfg["stride"], cfg["stridet"], cfg["alpha"])
         assert bad == 0, f"{bad} NN mismatches that are not fp64 near-ties"
         assert mism <= 1e-5 * nn_c.numel() + 2, f"{mism} near-tie NN mismatches out of {nn_c.numel()}"
-        extra, aux = MO.forward_train(st, H, W, ext, intr, res, dict(cfg, nn_override=nn_c), dtype=torch.float32, atlas=a,
-                                      atlas_dyn=ad)
+    # the whole step on the oracle (float32 render), continuing with the CUDA path's (equally valid) matches
+    a = st.atlas.float().requires_grad_(True)
+    ad = st.atlas_dyn.float().requires_grad_(True)
+    extra, aux = MO.forward_train(st, H, W, ext, intr, res, dict(cfg, nn_override=nn_c), dtype=torch.float32, atlas=a,
+                                  atlas_dyn=ad)
     rgb = step._buf["rgb_pad"][:T].cpu()
     assert float((rgb - aux["rgb"].detach()).abs().max()) < 1e-4 * float(aux["rgb"].abs().max())
     for k in ("swd", "rgb_smooth", "a_smooth"):
@@ -92,7 +98,8 @@ def test_reference_step_shape_matches_oracle(layout, cfg):
         scale = float(ref.abs().max())
         assert scale > 0
         err = (got - ref).abs()
-        assert float(err.max()) <= 4 * w_max + 5e-4 * scale, float(err.max()) / scale
+        # (a texel collects the taps of several pixels: allow a few sign flips per texel)
+        assert float(err.max()) <= 8 * w_max + 5e-4 * scale, float(err.max()) / scale
         n_off = int((err > 5e-4 * scale).sum())
         assert n_off <= max(64, 2e-4 * ref.numel()), f"{n_off} texel gradients off"
     assert torch.equal(m.atlas_dyn.data.cpu(), st.atlas_dyn.float())         # lr = 0
