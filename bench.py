@@ -533,10 +533,12 @@ def measure_main(args, world, rank, local, dev, group, barrier, extras):
     res_dev = make_target(wl, dev)
     lr = margs.lrate * 0.01
     step = FusedLoopStep(model, group=group, global_frames=T, timers=True, fused=args.fused)
+    ya, yb = step.band_rows(H, cfg)                                    # this rank's rows of the target (N > 1: its loss band)
+    res_main = res_dev if (ya, yb) == (0, H) else res_dev[:, :, :, ya:yb].contiguous()
 
     # ---------------- resident-input arm (value) ----------------
     for _ in range(args.warmup):
-        step.step(H, W, ext, intr, res_dev, cfg, lr)
+        step.step(H, W, ext, intr, res_main, cfg, lr)
     barrier()
     n_warm_events = len(step.timers.get("composite_fwd", []))
     sampler = ClockSampler(local)
@@ -547,7 +549,7 @@ def measure_main(args, world, rank, local, dev, group, barrier, extras):
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        out = step.step(H, W, ext, intr, res_dev, cfg, lr)
+        out = step.step(H, W, ext, intr, res_main, cfg, lr)
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -563,41 +565,26 @@ def measure_main(args, world, rank, local, dev, group, barrier, extras):
     # The public call (FusedLoopStep.step, the run_iter equivalent) is fed from pinned host memory the way
     # train_3dvid.run_iter feeds it (`datainfo_.to(device)`, train_3dvid.py:215); the next item's copy is
     # issued on a side stream while the current step computes (double buffer), the loss is read back.
-    # With N ranks every rank needs the whole target video: each rank copies only ITS block of target frames
-    # from its pinned host buffer (1/N of the bytes over its own PCIe link) and the blocks are all-gathered
-    # over NVLink on the copy stream (a second NCCL communicator, so it cannot interleave with the step's own
-    # collectives).  h2d_bytes_per_step is the total over all ranks.
-    fb = [(wl["F"] * r) // world for r in range(world + 1)]
-    f0, f1 = fb[rank], fb[rank + 1]
-    # the host holds the video the way a decoder delivers it and MVVidPatchDataset(storage="uint8") keeps it: bytes.
-    # `/ 255` happens on the device inside the step (vl3d_u8_to_unit: the same bits as the host conversion), so a
-    # quarter of the fp32 bytes cross PCIe (and NVLink, with N ranks).
+    # The host holds the video the way a decoder delivers it and MVVidPatchDataset(storage="uint8") keeps it: bytes;
+    # `/ 255` happens on the device inside the step (vl3d_u8_to_unit: the same bits as the host conversion).
+    # With N ranks the loss is sharded by pixel-row bands, so every rank's loader holds — and copies over its own PCIe
+    # link — only the rows of the target video its band needs (FusedLoopStep.band_rows); h2d_bytes_per_step is the
+    # total over all ranks.
     res_full_host = make_target(wl, None, seed=3, as_bytes=True)
-    res_host = res_full_host[:, f0:f1].contiguous().pin_memory()        # this rank's share of the item
+    res_host = res_full_host[:, :, :, ya:yb].contiguous().pin_memory()    # this rank's share of the item
     del res_full_host
-    loader_group = dist.new_group(backend="nccl") if world > 1 else None
-    bufs_u8 = [torch.empty((1, wl["F"], 3, H, W), dtype=torch.uint8, device=dev) for _ in range(2)]
-    bufs = [torch.empty_like(res_dev), res_dev]                         # the step's float input, double-buffered
+    bufs_u8 = [torch.empty(tuple(res_host.shape), dtype=torch.uint8, device=dev) for _ in range(2)]
     copy_stream = torch.cuda.Stream()
     ext_h, intr_h = ext.pin_memory(), intr.pin_memory()
-    h2d = wl["F"] * 3 * H * W + 1216 * world          # target video as bytes (all ranks together) + the view descriptors
+    rows_all = torch.tensor([yb - ya], device=dev)
+    if world > 1:
+        dist.all_reduce(rows_all)
+    h2d = wl["F"] * 3 * int(rows_all) * W + 1216 * world   # target bytes (all ranks together) + the view descriptors
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
-    from videoloop3d_b200 import ops as vl_ops
-    # where `/ 255` runs: inside the step right before the loss (default), or on the copy stream behind the H2D
-    # (VL3D_BENCH_CONVERT=copy; measured slower: 81.4 vs 77.5 ms e2e — the conversion's 3.6 GB of traffic then
-    # lands under the HBM-bound backward / Adam of the previous step instead of next to the latency-bound loss)
-    convert_on_copy_stream = os.environ.get("VL3D_BENCH_CONVERT", "step") == "copy"
-
     def load(i):
-        """H2D of this rank's frames as bytes (+ NVLink all-gather of the other ranks' frames) on the copy stream."""
-        buf = bufs_u8[i]
-        buf[:, f0:f1].copy_(res_host, non_blocking=True)
-        if world > 1:
-            parts = [buf[0, a:b] for a, b in zip(fb[:-1], fb[1:])]
-            dist.all_gather(parts, buf[0, f0:f1], group=loader_group)
-        if convert_on_copy_stream:
-            vl_ops.u8_to_unit(buf[0], out=bufs[i][0])
+        """H2D of this rank's rows of the target video, as bytes, on the copy stream."""
+        bufs_u8[i].copy_(res_host, non_blocking=True)
 
     def e2e_loop(n):
         ready = [torch.cuda.Event(), torch.cuda.Event()]
@@ -615,8 +602,7 @@ def measure_main(args, world, rank, local, dev, group, barrier, extras):
                     ready[nxt].record()
             # pose / intrinsics stay on the host: the view descriptor (plane homographies) is built there;
             # the step waits for the copy only where it first reads the target video (after the render)
-            o = step.step(H, W, ext_h, intr_h, bufs[cur] if convert_on_copy_stream else bufs_u8[cur], cfg, lr,
-                          res_ready=ready[cur])
+            o = step.step(H, W, ext_h, intr_h, bufs_u8[cur], cfg, lr, res_ready=ready[cur])
             done[cur].record()
             loss_host.copy_(o["loss"].reshape(1), non_blocking=True)
         torch.cuda.synchronize()
@@ -661,13 +647,14 @@ def measure_main(args, world, rank, local, dev, group, barrier, extras):
             "config": {"workload": args.workload, "H": H, "W": W, "planes": wl["D"], "frames": T,
                        "target_frames": wl["F"], "mesh": [wl["hv"], wl["wv"]], "atlas": "dense 1 texel:1 pixel",
                        "loss": "gpnn_lm p=11 pt=3 s=4 alpha=0 rou=-2 gain=3.5 + rgb/a smooth 0.2 + scale-invariant",
-                       "optimizer": "Adam eps=6e-8 over all texels", "parallelism": f"T-shard x{world}",
+                       "optimizer": "Adam eps=6e-8 over all texels",
+                       "parallelism": f"T-shard x{world} (render / backward / Adam by frames, looping loss by pixel-row bands)",
                        "l2": "inputs (>= 22 GB of texels per step) far exceed the 126 MB L2; no explicit flush"},
             "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms / args.steps,
                     "api": "FusedLoopStep.step fed from pinned host memory holding the uint8 target video (double-buffered "
-                           "H2D on a copy stream, /255 (vl3d_u8_to_unit) inside the step; with N ranks each copies 1/N of the frames and they are all-gathered "
-                           "over NVLink), loss read back"},
+                           "H2D on a copy stream, /255 (vl3d_u8_to_unit) inside the step; with N ranks each rank copies only the "
+                           "pixel rows of its loss band), loss read back"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

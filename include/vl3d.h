@@ -129,6 +129,13 @@ int vl3d_scale_invariant(const float* rgb, int32_t T, const float* res, int32_t 
 int vl3d_frame_sum(const float* v, int32_t n_frames, int64_t chw, float* out, void* stream);
 int vl3d_scale_invariant_presum(const float* rgb, int32_t T, const float* res_sum, int32_t F, int32_t H, int32_t W,
                                 double* partials, float* out, void* stream);
+/* Band-sharded form (the loss split over ranks by pixel-row bands): vl3d_scale_log_sum writes
+ *   sum_out[0] = sum over channels, rows [row_begin,row_end) and columns of log((mean_F res + .01)/(mean_T rgb + .01))
+ * for a band buffer rgb (>=T,3,H,W) / res (F,3,H,W); after an all-reduce(SUM) of the ranks' sums,
+ * vl3d_scale_finish gives out[0] = (exp(log_sum[0] / count) + 3) / 4 with count = 3 * (pixels of the whole image). */
+int vl3d_scale_log_sum(const float* rgb, int32_t T, const float* res, int32_t F, int32_t H, int32_t W,
+                       int32_t row_begin, int32_t row_end, double* partials, double* sum_out, void* stream);
+int vl3d_scale_finish(const double* log_sum, int64_t count, float* out, void* stream);
 /* out[i] = x[i] * xscale[0] for n contiguous floats (rgb_pad * scale, MPV.py:504). */
 int vl3d_scale_video(const float* x, const float* xscale, float* out, int64_t n, void* stream);
 
@@ -142,16 +149,18 @@ int vl3d_scale_video(const float* x, const float* xscale, float* out, int64_t n,
  *   (utils_vid.py:217-229, 344-348, 10-26).  rou_kind: 0 general float rou, 1 'mse', 2 'abs'.
  *   y2x_out (3,t,h,w)/weight_out (t,h,w) optional (last_y2x / last_weight caches).
  *   grad_out: (Tx_full, 3, Hfull, Wfull) = gcoef * xscale * rho'(x*xscale - y2x) / N inside the
- *   fitted crop, 0 outside (optional).  Only frames [frame_begin, frame_end) of x are processed (ranks
- *   split the frames); loss_out[0] = (sum of rho over those frames) / N_total, so partial results add up
- *   to the mean. partials: workspace of
- *   >= vl3d_vote_partials(Tx_full, Hfull, Wfull) doubles. */
+ *   fitted crop, 0 outside (optional).  Only frames [frame_begin, frame_end) and pixel rows [row_begin, row_end) of x
+ *   contribute (ranks split the frames, or the rows: then x / y / nn describe the rank's row band and rows outside
+ *   the range are the overlap owned by a neighbour; their gradient is written as 0); loss_out[0] = (sum of rho over
+ *   those frames and rows) / N_total, N_total = n_total if > 0 else 3*t*h*w of `desc`, so partial results add up to the
+ *   mean.  partials: workspace of >= vl3d_vote_partials(Tx_full, Hfull, Wfull) doubles. */
 int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, const float* y,
                         int32_t row_begin, int32_t row_end, int32_t* nn_out, void* stream);
 int vl3d_vote_partials(int32_t Tx_full, int32_t Hfull, int32_t Wfull);
 int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const float* xscale, const float* y,
                    const int32_t* nn, int32_t rou_kind, float rou, float scaling, float gcoef,
                    int32_t Tx_full, int32_t Hfull, int32_t Wfull, int32_t frame_begin, int32_t frame_end,
+                   int32_t row_begin, int32_t row_end, int64_t n_total,
                    float* y2x_out, float* weight_out, float* grad_out, double* partials, float* loss_out,
                    void* stream);
 

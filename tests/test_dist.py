@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from videoloop3d_b200.train_step import exchange_row_bands, gather_frames, owned_frame_ranges, partition, rows_equal
+from videoloop3d_b200.train_step import (band_layout, bands_to_frames, exchange_row_bands, frames_to_bands, gather_frames,
+                                         owned_frame_ranges, partition, rows_equal)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -26,6 +27,70 @@ def test_partitions_cover_everything_once():
             for lo, hi in owned_frame_ranges(b, r, T, pad):
                 seen += list(range(lo, hi))
         assert sorted(seen) == list(range(T + pad))
+
+
+def test_band_layout_covers_rows_and_votes():
+    """Row bands of the loss: the owned pixel rows partition [0, h); a band buffer holds every row its patch rows and
+    its owned rows touch; every patch row that covers an owned pixel row is inside the band's NN slice."""
+    for h, p, s, world in [(720, 11, 4, 8), (720, 3, 2, 8), (180, 11, 4, 4), (46, 5, 2, 3), (43, 7, 3, 2), (64, 3, 4, 4), (37, 15, 4, 2)]:
+        hf = (h - p) // s * s + p
+        ho = (hf - p) // s + 1
+        if ho < world:
+            continue
+        bands = band_layout(h, p, s, ho, world)
+        assert bands[0]["own0"] == 0 and bands[-1]["own1"] == h and bands[0]["pr0"] == 0 and bands[-1]["pr1"] == ho
+        for a, b in zip(bands[:-1], bands[1:]):
+            assert a["own1"] == b["own0"] and a["pr1"] == b["pr0"]
+        for b in bands:
+            assert b["ya"] <= b["own0"] <= b["own1"] <= b["yb"] <= h and b["ya"] == (b["pr0"] - b["halo"]) * s
+            assert b["yb"] >= min((b["pr1"] - 1) * s + p, h)
+            for y in range(b["own0"], b["own1"]):
+                if y >= hf:
+                    continue
+                i0, i1 = max(0, -(-(y - p + 1) // s)), min(y // s, ho - 1)     # patch rows covering pixel row y
+                assert b["pr0"] - b["halo"] <= i0 and i1 < b["pr1"], (h, p, s, world, y)
+
+
+def _band_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ok = True
+        for T, h, w, p, s in ((6, 46, 5, 5, 2), (7, 43, 4, 7, 3)):
+            hf = (h - p) // s * s + p
+            ho = (hf - p) // s + 1
+            bounds = partition(T, world)
+            bands = band_layout(h, p, s, ho, world)
+            me = bands[rank]
+            truth = torch.arange(T * 3 * h * w, dtype=torch.float32).reshape(T, 3, h, w)
+            mine = truth[bounds[rank]:bounds[rank + 1]].clone()
+            hb = me["yb"] - me["ya"]
+            band = torch.full((T + 2, 3, hb, w), -1.0)
+            frames_to_bands(mine, band, bounds, bands, rank, None)
+            ok &= torch.equal(band[:T], truth[:, :, me["ya"]:me["yb"]])
+            # adjoint: every rank contributes its owned rows of every frame
+            gband = torch.zeros(T + 2, 3, hb, w)
+            gband[:T] = 2 * truth[:, :, me["ya"]:me["yb"]] + 1
+            out = torch.full((bounds[rank + 1] - bounds[rank], 3, h, w), -7.0)
+            bands_to_frames(gband, out, bounds, bands, rank, None)
+            ok &= torch.equal(out, 2 * mine + 1)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_band_exchanges_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_band_worker, args=(r, world, 29535 + world, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = dict(q.get(timeout=10) for _ in range(world))
+    assert got == {r: True for r in range(world)}
 
 
 def _worker(rank, world, port, q):

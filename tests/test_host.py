@@ -350,8 +350,13 @@ def test_argument_validation_of_the_data_entry_points():
     d = ops.make_loss_desc((50, 3, 180, 320), (1, 1, 1), (258, 3, 180, 320), (1, 1, 1), 11, 3, 4, 1, 0.0)
     with pytest.raises(_lib.Vl3dError, match="NULL"):
         _lib.call("vl3d_vote_loss", ctypes.byref(d), None, None, None, None, 0, -2.0, 0.1, 1.0, 50, 180, 320, 0, 50,
-                  None, None, None, None, None, None)
+                  0, 180, 0, None, None, None, None, None, None)
     with pytest.raises(_lib.Vl3dError, match="frame range"):
         _lib.call("vl3d_vote_loss", ctypes.byref(d), p16, None, p16, p16, 0, -2.0, 0.1, 1.0, 50, 180, 320, 7, 3,
-                  None, None, None, p16, p16, None)
+                  0, 180, 0, None, None, None, p16, p16, None)
+    with pytest.raises(_lib.Vl3dError, match="row range"):
+        _lib.call("vl3d_vote_loss", ctypes.byref(d), p16, None, p16, p16, 0, -2.0, 0.1, 1.0, 50, 180, 320, 0, 50,
+                  90, 181, 0, None, None, None, p16, p16, None)
+    with pytest.raises(_lib.Vl3dError, match="row range"):
+        _lib.call("vl3d_scale_log_sum", p16, 4, p16, 4, 8, 8, 5, 3, p16, p16, None)
     assert lib.vl3d_vote_partials(50, 180, 320) == 50 * 10 * 23 and lib.vl3d_vote_partials(0, 1, 1) == 0

@@ -514,6 +514,8 @@ struct VoteParams {
     int rou_kind; float rou, scaling, gcoef;
     int Tx_full, Hfull, Wfull;
     int f0;                     // first frame handled by this launch
+    int row0, row1;             // pixel rows whose loss / gradient this call owns (a rank's band; [0, Hfull) normally)
+    float n_inv;                // 1 / (elements of the whole fitted crop): partial results add up to the mean
     float* y2x; float* weight; float* grad; double* partials; float* loss;
 };
 
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) vote_loss_kernel(const __grid_co
     const int py = blockIdx.z * 8 + (threadIdx.x >> 5);
     float lsum = 0.f;
     if (px < P.Wfull && py < P.Hfull) {
-        const bool inside = px < L.w && py < L.h && tf < L.t;
+        const bool inside = px < L.w && py < L.h && tf < L.t && py >= P.row0 && py < P.row1;
         float g[3] = {0.f, 0.f, 0.f};
         if (inside) {
             const int p = L.p, s = L.s, pt = L.pt, st = L.st;
@@ -565,7 +567,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) vote_loss_kernel(const __grid_co
             const float wgt = fmaxf((float)cnt, 1e-10f);                       // clamp_min(1e-10) (utils_vid.py:228)
             const float m[3] = {v0 / wgt, v1 / wgt, v2 / wgt};
             const float xsc = P.xscale ? __ldg(P.xscale) : 1.f;
-            const float n_inv = 1.f / ((float)L.t * (float)L.h * (float)L.w * 3.f);
+            const float n_inv = P.n_inv;
             const size_t fit_plane = (size_t)L.h * L.w;
             const size_t fit_pix = (size_t)py * L.w + px;
 #pragma unroll
@@ -611,7 +613,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) vote_loss_batched_kernel(const _
     const int py = blockIdx.z * 8 + (threadIdx.x >> 5);
     float lsum = 0.f;
     if (px < P.Wfull && py < P.Hfull) {
-        const bool inside = px < L.w && py < L.h && tf < L.t;
+        const bool inside = px < L.w && py < L.h && tf < L.t && py >= P.row0 && py < P.row1;
         float g[3] = {0.f, 0.f, 0.f};
         if (inside) {
             const int p = L.p, s = L.s, pt = L.pt, st = L.st;
@@ -656,7 +658,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) vote_loss_batched_kernel(const _
             const float wgt = fmaxf((float)cnt, 1e-10f);                       // clamp_min(1e-10) (utils_vid.py:228)
             const float m[3] = {v0 / wgt, v1 / wgt, v2 / wgt};
             const float xsc = P.xscale ? __ldg(P.xscale) : 1.f;
-            const float n_inv = 1.f / ((float)L.t * (float)L.h * (float)L.w * 3.f);
+            const float n_inv = P.n_inv;
             const size_t fit_plane = (size_t)L.h * L.w;
             const size_t fit_pix = (size_t)py * L.w + px;
 #pragma unroll
@@ -759,6 +761,48 @@ __global__ void __launch_bounds__(SCALE_THREADS) scale_partial_presum_kernel(con
 #pragma unroll
         for (int i = 0; i < SCALE_THREADS / 32; ++i) a += (double)s_part[i];
         partials[blockIdx.x] = a;
+    }
+}
+
+// band-sharded variant: sum of log((mean_F res + .01) / (mean_T rgb + .01)) over the pixel rows [row0, row1) of a
+// (.,3,H,W) band buffer (all channels, all columns); the ranks' sums are all-reduced and vl3d_scale_finish turns the
+// total into the gain
+__global__ void __launch_bounds__(SCALE_THREADS) scale_partial_rows_kernel(const float* __restrict__ rgb, int T,
+                                                                            const float* __restrict__ res, int F, int H, int W,
+                                                                            int row0, int row1, double* partials) {
+    float acc = 0.f;
+    const size_t chw = (size_t)3 * H * W, rw = (size_t)(row1 - row0) * W, n = 3 * rw;
+    for (size_t j = (size_t)blockIdx.x * SCALE_THREADS + threadIdx.x; j < n; j += (size_t)gridDim.x * SCALE_THREADS) {
+        const size_t c = j / rw, r = j - c * rw;
+        const size_t i = c * H * W + (size_t)row0 * W + r;
+        float sr = 0.f, sx = 0.f;
+        for (int f = 0; f < F; ++f) sr += __ldg(res + (size_t)f * chw + i);
+        for (int t = 0; t < T; ++t) sx += __ldg(rgb + (size_t)t * chw + i);
+        acc += logf((sr / (float)F + 0.01f) / (sx / (float)T + 0.01f));
+    }
+    __shared__ float s_part[SCALE_THREADS / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < SCALE_THREADS / 32; ++i) a += (double)s_part[i];
+        partials[blockIdx.x] = a;
+    }
+}
+
+__global__ void __launch_bounds__(1024) sum_partials_kernel(const double* partials, int n, double* out) {
+    __shared__ double s[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.0;
+        acc = warp_sum(acc);
+        if (threadIdx.x == 0) out[0] = acc;
     }
 }
 
@@ -1022,6 +1066,7 @@ extern "C" int vl3d_vote_partials(int32_t Tx_full, int32_t Hfull, int32_t Wfull)
 extern "C" int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const float* xscale, const float* y,
                               const int32_t* nn, int32_t rou_kind, float rou, float scaling, float gcoef,
                               int32_t Tx_full, int32_t Hfull, int32_t Wfull, int32_t frame_begin, int32_t frame_end,
+                              int32_t row_begin, int32_t row_end, int64_t n_total,
                               float* y2x_out, float* weight_out, float* grad_out, double* partials, float* loss_out,
                               void* stream) {
     if (int e = validate_desc(desc)) return e;
@@ -1030,12 +1075,16 @@ extern "C" int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const 
     VL3D_REQUIRE(rou_kind >= 0 && rou_kind <= 2, VL3D_EINVAL, "rou_kind %d", rou_kind);
     VL3D_REQUIRE(frame_begin >= 0 && frame_begin < frame_end && frame_end <= Tx_full, VL3D_EINVAL,
                  "bad frame range [%d,%d)", frame_begin, frame_end);
+    VL3D_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= Hfull && n_total >= 0, VL3D_EINVAL,
+                 "bad row range [%d,%d) / n_total", row_begin, row_end);
+    const double denom = n_total > 0 ? (double)n_total : (double)desc->t * desc->h * desc->w * 3.0;
     dim3 grid = vote_grid(desc, frame_end - frame_begin, Hfull, Wfull);
     const int nblocks = grid.x * grid.y * grid.z;
     VoteParams P{};
     P.d = *desc; P.x = x; P.xscale = xscale; P.y = y; P.nn = nn;
     P.rou_kind = rou_kind; P.rou = rou; P.scaling = scaling; P.gcoef = gcoef;
     P.Tx_full = Tx_full; P.Hfull = Hfull; P.Wfull = Wfull; P.f0 = frame_begin;
+    P.row0 = row_begin; P.row1 = row_end; P.n_inv = (float)(1.0 / denom);
     P.y2x = y2x_out; P.weight = weight_out; P.grad = grad_out; P.partials = partials; P.loss = loss_out;
     cudaStream_t st = (cudaStream_t)stream;
     // covering patches per axis: at most ceil(p/s) (space) and ceil(pt/st) (time)
@@ -1046,7 +1095,6 @@ extern "C" int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const 
     else if (batched && ms <= 3 && mt <= 3) vote_loss_batched_kernel<3, 3, 3><<<grid, VOTE_THREADS, 0, st>>>(P);
     else vote_loss_kernel<<<grid, VOTE_THREADS, 0, st>>>(P);
     if (int e = check_launch("vote_loss")) return e;
-    const double denom = (double)desc->t * desc->h * desc->w * 3.0;
     finalize_mean_kernel<<<1, 1024, 0, st>>>(partials, nblocks, denom, loss_out);
     return check_launch("vote_finalize");
 }
@@ -1117,6 +1165,29 @@ extern "C" int vl3d_scale_invariant_presum(const float* rgb, int32_t T, const fl
     if (int e = check_launch("scale_partial_presum")) return e;
     scale_finalize_kernel<<<1, 1024, 0, st>>>(partials, blocks, (double)chw, out);
     return check_launch("scale_finalize");
+}
+
+extern "C" int vl3d_scale_log_sum(const float* rgb, int32_t T, const float* res, int32_t F, int32_t H, int32_t W,
+                                  int32_t row_begin, int32_t row_end, double* partials, double* sum_out, void* stream) {
+    VL3D_REQUIRE(rgb && res && partials && sum_out, VL3D_ENULL, "required pointer is NULL");
+    VL3D_REQUIRE(T >= 1 && F >= 1 && H >= 1 && W >= 1 && row_begin >= 0 && row_begin <= row_end && row_end <= H, VL3D_EINVAL,
+                 "bad sizes / row range");
+    const size_t n = (size_t)3 * (row_end - row_begin) * W;
+    int blocks = (int)((n + SCALE_THREADS - 1) / SCALE_THREADS);
+    if (blocks > SCALE_BLOCKS) blocks = SCALE_BLOCKS;
+    if (blocks < 1) blocks = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    scale_partial_rows_kernel<<<blocks, SCALE_THREADS, 0, st>>>(rgb, T, res, F, H, W, row_begin, row_end, partials);
+    if (int e = check_launch("scale_partial_rows")) return e;
+    sum_partials_kernel<<<1, 1024, 0, st>>>(partials, blocks, sum_out);
+    return check_launch("sum_partials");
+}
+
+extern "C" int vl3d_scale_finish(const double* log_sum, int64_t count, float* out, void* stream) {
+    VL3D_REQUIRE(log_sum && out, VL3D_ENULL, "required pointer is NULL");
+    VL3D_REQUIRE(count >= 1, VL3D_EINVAL, "scale_finish: count < 1");
+    scale_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(log_sum, 1, (double)count, out);
+    return check_launch("scale_finish");
 }
 
 extern "C" int vl3d_scale_invariant(const float* rgb, int32_t T, const float* res, int32_t F, int32_t H, int32_t W,

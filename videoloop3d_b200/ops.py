@@ -149,6 +149,23 @@ def scale_invariant_presum(rgb, T, res_sum, F_, out=None, partials=None):
     return out
 
 
+def scale_log_sum(rgb, T, res, rows, partials, out):
+    """Band-sharded scale-invariant gain, step 1 (MPV.py:499-504): out[0] (float64) = sum over channels, `rows` and columns
+    of log((mean_F res + .01)/(mean_T rgb + .01)); rgb (>=T,3,H,W) and res (F,3,H,W) contiguous band buffers."""
+    _require_cuda(rgb, "rgb"); _require_cuda(res, "res")
+    F_, _, H, W = res.shape
+    assert rgb.is_contiguous() and res.is_contiguous() and tuple(rgb.shape[1:]) == (3, H, W)
+    _lib.call("vl3d_scale_log_sum", _lib.ptr(rgb), int(T), _lib.ptr(res), int(F_), int(H), int(W), int(rows[0]), int(rows[1]),
+              _lib.ptr(partials), _lib.ptr(out), _lib.stream_ptr())
+    return out
+
+
+def scale_finish(log_sum, count, out):
+    """Step 2: out[0] = (exp(log_sum[0] / count) + 3) / 4."""
+    _lib.call("vl3d_scale_finish", _lib.ptr(log_sum), int(count), _lib.ptr(out), _lib.stream_ptr())
+    return out
+
+
 def _fit(size, p, st, name):
     """fit_patch of utils_vid.py:307-313."""
     if size < p:
@@ -237,7 +254,9 @@ def parse_rou(rou):
 
 
 def vote_loss(desc, x, xscale, y, nn, rou, scaling, gcoef, full_shape, want_cache=False, grad_out=None,
-              want_grad=True, partials=None, loss_out=None, frames=None):
+              want_grad=True, partials=None, loss_out=None, frames=None, rows=None, n_total=0):
+    """`frames` / `rows`: the frame range / pixel-row range this call owns (default: everything); `n_total`: element
+    count of the whole problem when `desc` describes a rank's row band (0: 3*t*h*w of `desc`)."""
     Tx, Hf, Wf = full_shape
     dev = x.device
     kind, rouf = parse_rou(rou)
@@ -252,7 +271,9 @@ def vote_loss(desc, x, xscale, y, nn, rou, scaling, gcoef, full_shape, want_cach
         loss_out = torch.empty(1, dtype=torch.float32, device=dev)
     _lib.call("vl3d_vote_loss", C.byref(desc), _lib.ptr(x), _lib.ptr(xscale), _lib.ptr(y), _lib.ptr(nn),
               int(kind), float(rouf), float(scaling), float(gcoef), int(Tx), int(Hf), int(Wf),
-              int(0 if frames is None else frames[0]), int(Tx if frames is None else frames[1]), _lib.ptr(y2x), _lib.ptr(wgt), _lib.ptr(grad_out if want_grad else None), _lib.ptr(partials),
+              int(0 if frames is None else frames[0]), int(Tx if frames is None else frames[1]),
+              int(0 if rows is None else rows[0]), int(Hf if rows is None else rows[1]), int(n_total),
+              _lib.ptr(y2x), _lib.ptr(wgt), _lib.ptr(grad_out if want_grad else None), _lib.ptr(partials),
               _lib.ptr(loss_out), _lib.stream_ptr())
     return loss_out, grad_out, y2x, wgt
 

@@ -138,6 +138,77 @@ def rows_equal(rows):
     return len({b - a for a, b in zip(rows[:-1], rows[1:])}) == 1
 
 
+def band_layout(h, p, s, ho, world):
+    """Row bands of the looping loss for `world` ranks (patch positions are independent, utils_vid.py:211-215).
+
+    Rank r searches the patch rows [pr0, pr1) and owns the loss / gradient of the pixel rows [own0, own1) (a partition
+    of [0, h)).  A pixel row is covered by up to ceil(p/s) patch rows, so the vote of the first owned rows also needs
+    the matches of the `halo` patch rows above pr0: the rank's band buffer holds the pixel rows [ya, yb) = everything
+    its patch rows [pr0 - halo, pr1) and its owned rows touch.  Returns a list of dicts (one per rank)."""
+    rows = partition(ho, world)
+    M = (p - 1) // s
+    out = []
+    for r in range(world):
+        pr0, pr1 = rows[r], rows[r + 1]
+        halo = min(M, pr0)
+        own0 = pr0 * s if r > 0 else 0
+        own1 = rows[r + 1] * s if r < world - 1 else h
+        ya = (pr0 - halo) * s
+        yb = max((pr1 - 1) * s + p if pr1 > pr0 else ya, own1)
+        out.append(dict(pr0=pr0, pr1=pr1, halo=halo, own0=own0, own1=own1, ya=ya, yb=min(yb, h)))
+    return out
+
+
+def frames_to_bands(frames_local, band_out, bounds, bands, rank, group, send_ws=None):
+    """All-to-all #1: every rank holds ALL rows of ITS frames (`frames_local`: (Tl,C,h,w)); afterwards it holds ITS
+    row band of ALL frames (`band_out[:T]`: (>=T,C,hb,w), frame-major, so the block received from rank q lands
+    contiguously at frames [bounds[q], bounds[q+1])).  Returns the packed send buffer (reusable workspace)."""
+    import torch.distributed as dist
+    world = len(bands)
+    Tl, C_, _, w = frames_local.shape
+    T = bounds[-1]
+    hb = bands[rank]["yb"] - bands[rank]["ya"]
+    in_splits = [Tl * C_ * (b["yb"] - b["ya"]) * w for b in bands]
+    out_splits = [(bounds[q + 1] - bounds[q]) * C_ * hb * w for q in range(world)]
+    n_send = sum(in_splits)
+    if send_ws is None or send_ws.numel() < n_send or send_ws.dtype != frames_local.dtype or send_ws.device != frames_local.device:
+        send_ws = torch.empty(n_send, dtype=frames_local.dtype, device=frames_local.device)
+    off = 0
+    for q, b in enumerate(bands):                                   # pack: rank q's rows of my frames, contiguous
+        n = in_splits[q]
+        send_ws[off:off + n].view(Tl, C_, b["yb"] - b["ya"], w).copy_(frames_local[:, :, b["ya"]:b["yb"]])
+        off += n
+    dist.all_to_all_single(band_out[:T].reshape(-1), send_ws[:n_send], out_splits, in_splits, group=group)
+    return send_ws
+
+
+def bands_to_frames(band_grad, frames_grad_out, bounds, bands, rank, group, send_ws=None, recv_ws=None):
+    """All-to-all #2 (the adjoint of #1 restricted to owned rows): `band_grad` (>=T,C,hb,w) holds dL/dx for my band of
+    all frames; every rank receives, for ITS frames, the rows each rank owns -> `frames_grad_out` (Tl,C,h,w)."""
+    import torch.distributed as dist
+    world = len(bands)
+    me = bands[rank]
+    Tl, C_, h, w = frames_grad_out.shape
+    lo, hi = me["own0"] - me["ya"], me["own1"] - me["ya"]
+    in_splits = [(bounds[q + 1] - bounds[q]) * C_ * (hi - lo) * w for q in range(world)]
+    out_splits = [Tl * C_ * (b["own1"] - b["own0"]) * w for b in bands]
+    n_send, n_recv = sum(in_splits), sum(out_splits)
+    kw = dict(dtype=band_grad.dtype, device=band_grad.device)
+    if send_ws is None or send_ws.numel() < n_send:
+        send_ws = torch.empty(n_send, **kw)
+    if recv_ws is None or recv_ws.numel() < n_recv:
+        recv_ws = torch.empty(n_recv, **kw)
+    T = bounds[-1]
+    send_ws[:n_send].view(T, C_, hi - lo, w).copy_(band_grad[:T, :, lo:hi])     # frames are already in rank order
+    dist.all_to_all_single(recv_ws[:n_recv], send_ws[:n_send], out_splits, in_splits, group=group)
+    off = 0
+    for q, b in enumerate(bands):
+        n = out_splits[q]
+        frames_grad_out[:, :, b["own0"]:b["own1"]].copy_(recv_ws[off:off + n].view(Tl, C_, b["own1"] - b["own0"], w))
+        off += n
+    return send_ws, recv_ws
+
+
 class FusedLoopStep:
     """render + looping loss + backward + Adam for one (view, patch) item, fused and sync-free.
 
@@ -155,7 +226,7 @@ class FusedLoopStep:
     """
 
     def __init__(self, model: MPMeshVid, group=None, betas=(0.9, 0.999), eps=6e-8, global_frames=None, timers=False,
-                 overlap_chunks=1, fused=None, fused_opts=None):
+                 overlap_chunks=1, fused=None, fused_opts=None, loss_shard="rows"):
         """`fused`: how backward + Adam of the dynamic atlas run —
         "off": separate kernels (zero-fill, vl3d_composite_bwd, vl3d_adam_step);
         "generic": one persistent kernel, tiles of chunk c interleaved with Adam of chunk c-1 (any layout);
@@ -192,6 +263,12 @@ class FusedLoopStep:
         # gains), so the default is 1 (off).
         self.overlap_chunks = max(1, int(overlap_chunks))
         self._side = torch.cuda.Stream(device=model.atlas_dyn.device)
+        # with several ranks: "rows" = the looping loss is sharded by pixel-row bands (two all-to-alls: rendered frames ->
+        # row bands, loss gradient -> frames; every rank needs only its band of the target video); "frames" = the first
+        # design (all-gather of the rendered frames, every rank holds the whole target video)
+        self.loss_shard = os.environ.get("VL3D_LOSS_SHARD", loss_shard)
+        if self.loss_shard not in ("rows", "frames"):
+            raise ValueError(f"loss_shard={self.loss_shard!r}")
         self.fused = (fused or os.environ.get("VL3D_FUSED", "auto")).lower()
         if self.fused not in ("off", "generic", "band", "band-zero", "auto"):
             raise ValueError(f"fused={self.fused!r}")
@@ -257,6 +334,90 @@ class FusedLoopStep:
         self.last_schedule = sched
         return sched
 
+    def band_rows(self, h, cfg, fit=True, pt_frames=None):
+        """(ya, yb): the pixel rows of the target video this rank needs when the loss is sharded by row bands
+        (`loss_shard="rows"`): a loader may hand `step()` exactly `res[..., ya:yb, :]`."""
+        p, s = int(cfg["patch_size"]), int(cfg["stride"])
+        hf = ops._fit(h, p, s, "patch_height") if fit else h
+        ho = (hf - p) // s + 1
+        if self.world == 1 or self.loss_shard != "rows" or ho < self.world:
+            return 0, h
+        b = band_layout(h, p, s, ho, self.world)[self.rank]
+        return b["ya"], b["yb"]
+
+    def _loss_band_sharded(self, h, w, T, pad, rgb_pad, res0, res_u8, res_ready, cfg, lossobj, gain, sums, grad_rgb, dg):
+        """The looping loss sharded by pixel-row bands (SURVEY §8(e) "alternative"): all-to-all of the rendered frames
+        into row bands, gain / NN search / vote on the band, all-to-all of dL/drgb back to the frame owners.  Fills
+        grad_rgb[t0:t1] (pad adjoint included) and sums[4]."""
+        import torch.distributed as dist
+        t0, t1 = self.t0, self.t1
+        p, s = dg.p, dg.s
+        bands = band_layout(h, p, s, dg.ho, self.world)
+        me = bands[self.rank]
+        ya, yb, hb = me["ya"], me["yb"], me["yb"] - me["ya"]
+        F_ = res0.shape[0]
+        # ---- target band: bytes -> float on the band only; a full-height target is cropped here
+        if res_ready is not None:
+            torch.cuda.current_stream().wait_event(res_ready)
+        src = res_u8 if res_u8 is not None else res0
+        if src.shape[-2] == h and hb != h:
+            src = src[:, :, ya:yb]
+        elif src.shape[-2] != hb:
+            raise Vl3dError(f"target video has {src.shape[-2]} rows; expected the full {h} or this rank's band of {hb}")
+        if res_u8 is not None:
+            with self._timed("target_u8_to_float"):
+                y_band = ops.u8_to_unit(src, out=self._get("y_band", (F_, 3, hb, w), torch.float32))
+        else:
+            y_band = src if src.is_contiguous() else self._get("y_band", (F_, 3, hb, w), torch.float32).copy_(src)
+        # ---- rendered frames -> row bands
+        x_band = self._get("x_band", (T + pad, 3, hb, w), torch.float32)
+        with self._timed("frames_to_bands"):
+            self._buf["a2a_send"] = frames_to_bands(rgb_pad[t0:t1], x_band, self.bounds, bands, self.rank, self.group,
+                                                    self._buf.get("a2a_send"))
+            if pad:
+                x_band[T:T + pad].copy_(x_band[:pad])                # loop pad (MPV.py:490-492)
+        # ---- scale-invariant gain: partial log-sum over the owned rows, one all-reduce of a double
+        xscale = None
+        own = (me["own0"] - ya, me["own1"] - ya)
+        if self.model.args.scale_invariant:
+            with self._timed("scale_invariant"):
+                part = self._get("scale_part", (ops._lib.load().vl3d_scale_partials(),), torch.float64)
+                lsum = ops.scale_log_sum(x_band, T, y_band, own, part, self._get("scale_lsum", (1,), torch.float64))
+                dist.all_reduce(lsum, group=self.group)
+                xscale = ops.scale_finish(lsum, 3 * h * w, self._get("xscale", (1,), torch.float32))
+        # ---- NN search on the band; the index map of the whole image is assembled in place
+        desc = ops.make_loss_desc(x_band.shape, (x_band.stride(0), x_band.stride(1), x_band.stride(2)), y_band.shape,
+                                  (y_band.stride(0), y_band.stride(1), y_band.stride(2)), p, dg.pt, s, dg.st,
+                                  dg.alpha if dg.use_alpha else 1e10, fit=lossobj.fit)
+        if desc.ho != me["pr1"] - (me["pr0"] - me["halo"]) or desc.wo != dg.wo or desc.n1 != dg.n1:
+            raise Vl3dError("band layout does not match the loss descriptor")
+        nn = self._get("nn", (dg.ho, dg.wo, dg.n1), torch.int32)
+        rows = [b["pr0"] for b in bands] + [dg.ho]
+        if not rows_equal(rows):
+            nn.zero_()
+        nn_band = nn[me["pr0"] - me["halo"]:me["pr1"]]
+        x_scaled = self._get("xb_scaled", tuple(x_band.shape), torch.float32)
+        with self._timed("patchnn_search"):
+            ops.patchnn_search(desc, x_band, xscale, y_band, nn_out=nn_band, rows=(me["halo"], desc.ho), scaled_ws=x_scaled)
+        with self._timed("exchange_nn"):
+            exchange_row_bands(nn, rows, self.rank, self.group)
+        # ---- votes, robust loss and its gradient for the owned rows of every frame
+        g_band = self._get("g_band", (T + pad, 3, hb, w), torch.float32)
+        vote_part = self._get("vote_part_band", (ops._lib.load().vl3d_vote_partials(T + pad, hb, w),), torch.float64)
+        lo = self._get("loss_out0", (1,), torch.float32)
+        with self._timed("vote_loss"):
+            ops.vote_loss(desc, x_band, xscale, y_band, nn_band, cfg.get("rou", 0), cfg.get("scaling", 0.2), gain,
+                          (T + pad, hb, w), grad_out=g_band, partials=vote_part, loss_out=lo, rows=own,
+                          n_total=3 * dg.t * dg.h * dg.w)
+            sums[4] += lo[0]
+        # ---- dL/drgb back to the frame owners (adjoint of the loop pad first)
+        with self._timed("bands_to_frames"):
+            if pad:
+                g_band[:pad] += g_band[T:T + pad]
+            self._buf["a2a_send2"], self._buf["a2a_recv2"] = bands_to_frames(
+                g_band, grad_rgb[t0:t1], self.bounds, bands, self.rank, self.group, self._buf.get("a2a_send2"),
+                self._buf.get("a2a_recv2"))
+
     def _adam(self, name, p, g, lr):
         st = self._state.get(name)
         if st is None:
@@ -312,8 +473,18 @@ class FusedLoopStep:
             else:
                 ops.composite_fwd(view, pack, dyn_local, atlas.data, None, Tl, 0, rgb_out=rgb_pad[t0:t1],
                                   smooth_sums=fwd_sums)
+        band_mode = False
+        if self.world > 1 and self.loss_shard == "rows":
+            dg = ops.make_loss_desc(rgb_pad.shape, (3 * h * w, h * w, w), (res0.shape[0], 3, h, w), (3 * h * w, h * w, w),
+                                    cfg["patch_size"], cfg["patcht_size"], cfg["stride"], cfg["stridet"],
+                                    cfg.get("alpha", 1e10), fit=lossobj.fit)
+            band_mode = dg.ho >= self.world                         # (fewer patch rows than ranks: frame sharding)
+        if band_mode:
+            grad_rgb = self._get("grad_rgb", (T + pad, 3, h, w), torch.float32)
+            self._loss_band_sharded(h, w, T, pad, rgb_pad, res0, res_u8, res_ready, cfg, lossobj, gain, sums, grad_rgb, dg)
+            desc = dg
         gather = None
-        if self.world > 1:
+        if self.world > 1 and not band_mode:
             # asynchronous: the target-frame sums of the scale-invariant gain (which do not need the rendered video)
             # run on the compute stream while NVLink moves the frames; waited for right before the gain is evaluated
             with self._timed("allgather_rgb_issue"):
@@ -327,58 +498,59 @@ class FusedLoopStep:
                 if pad:
                     rgb_pad[T:T + pad].copy_(rgb_pad[:pad])          # loop pad (MPV.py:490-492)
 
-        # ---- looping loss
-        if res_ready is not None:
-            torch.cuda.current_stream().wait_event(res_ready)
-        if res_u8 is not None:                                      # `vid / 255` of the dataset (train_3dvid.py:54), on device
-            with self._timed("target_u8_to_float"):
-                res0 = ops.u8_to_unit(res_u8, out=self._get("res_f32", tuple(res_u8.shape), torch.float32))
-        xscale = None
-        if args.scale_invariant:
-            with self._timed("scale_invariant"):
-                out = self._get("xscale", (1,), torch.float32)
-                part = self._get("scale_part", (ops._lib.load().vl3d_scale_partials(),), torch.float64)
-                if self.world == 1:
-                    xscale = ops.scale_invariant(rgb_pad, T, res0, out=out, partials=part)
-                else:
-                    # the mean over the F target frames is the expensive part (the whole target video is read):
-                    # every rank sums its block of frames, one all-reduce of the (3,h,w) sums
-                    fb = partition(res0.shape[0], self.world)
-                    rsum = ops.frame_sum(res0[fb[self.rank]:fb[self.rank + 1]], out=self._get("res_sum", (3, h, w), torch.float32))
-                    dist.all_reduce(rsum, group=self.group)
-                    finish_gather()
-                    xscale = ops.scale_invariant_presum(rgb_pad, T, rsum, res0.shape[0], out=out, partials=part)
-        finish_gather()
-        desc = ops.make_loss_desc(rgb_pad.shape, (rgb_pad.stride(0), rgb_pad.stride(1), rgb_pad.stride(2)), res0.shape,
-                                  (res0.stride(0), res0.stride(1), res0.stride(2)), cfg["patch_size"],
-                                  cfg["patcht_size"], cfg["stride"], cfg["stridet"], cfg.get("alpha", 1e10),
-                                  fit=lossobj.fit)
-        nn = self._get("nn", (desc.ho, desc.wo, desc.n1), torch.int32)
-        x_scaled = self._get("x_scaled", tuple(rgb_pad.shape), torch.float32)
-        if self.world == 1:
-            with self._timed("patchnn_search"):
-                ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn, scaled_ws=x_scaled)
-        else:
-            # patch positions are independent (utils_vid.py:211-215): each rank searches a band of patch rows,
-            # then the int32 index map is summed across ranks (disjoint rows, zeros elsewhere)
-            rows = partition(desc.ho, self.world)
-            if not rows_equal(rows):
-                nn.zero_()
-            with self._timed("patchnn_search"):
-                ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn, rows=(rows[self.rank], rows[self.rank + 1]),
-                                   scaled_ws=x_scaled)
-            with self._timed("exchange_nn"):
-                exchange_row_bands(nn, rows, self.rank, self.group)
-        grad_rgb = self._get("grad_rgb", (T + pad, 3, h, w), torch.float32)
-        n_part = ops._lib.load().vl3d_vote_partials(T + pad, h, w)
-        vote_part = self._get("vote_part", (n_part,), torch.float64)
-        with self._timed("vote_loss"):
-            ranges = [(0, T + pad)] if self.world == 1 else owned_frame_ranges(self.bounds, self.rank, T, pad)
-            for i, fr in enumerate(ranges):
-                lo = self._get(f"loss_out{i}", (1,), torch.float32)
-                ops.vote_loss(desc, rgb_pad, xscale, res0, nn, cfg.get("rou", 0), cfg.get("scaling", 0.2), gain,
-                              (T + pad, h, w), grad_out=grad_rgb, partials=vote_part, loss_out=lo, frames=fr)
-                sums[4] += lo[0]
+        # ---- looping loss (single GPU, or frame-sharded: every rank holds the whole rendered and target video)
+        if not band_mode:
+            if res_ready is not None:
+                torch.cuda.current_stream().wait_event(res_ready)
+            if res_u8 is not None:                                      # `vid / 255` of the dataset (train_3dvid.py:54), on device
+                with self._timed("target_u8_to_float"):
+                    res0 = ops.u8_to_unit(res_u8, out=self._get("res_f32", tuple(res_u8.shape), torch.float32))
+            xscale = None
+            if args.scale_invariant:
+                with self._timed("scale_invariant"):
+                    out = self._get("xscale", (1,), torch.float32)
+                    part = self._get("scale_part", (ops._lib.load().vl3d_scale_partials(),), torch.float64)
+                    if self.world == 1:
+                        xscale = ops.scale_invariant(rgb_pad, T, res0, out=out, partials=part)
+                    else:
+                        # the mean over the F target frames is the expensive part (the whole target video is read):
+                        # every rank sums its block of frames, one all-reduce of the (3,h,w) sums
+                        fb = partition(res0.shape[0], self.world)
+                        rsum = ops.frame_sum(res0[fb[self.rank]:fb[self.rank + 1]], out=self._get("res_sum", (3, h, w), torch.float32))
+                        dist.all_reduce(rsum, group=self.group)
+                        finish_gather()
+                        xscale = ops.scale_invariant_presum(rgb_pad, T, rsum, res0.shape[0], out=out, partials=part)
+            finish_gather()
+            desc = ops.make_loss_desc(rgb_pad.shape, (rgb_pad.stride(0), rgb_pad.stride(1), rgb_pad.stride(2)), res0.shape,
+                                      (res0.stride(0), res0.stride(1), res0.stride(2)), cfg["patch_size"],
+                                      cfg["patcht_size"], cfg["stride"], cfg["stridet"], cfg.get("alpha", 1e10),
+                                      fit=lossobj.fit)
+            nn = self._get("nn", (desc.ho, desc.wo, desc.n1), torch.int32)
+            x_scaled = self._get("x_scaled", tuple(rgb_pad.shape), torch.float32)
+            if self.world == 1:
+                with self._timed("patchnn_search"):
+                    ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn, scaled_ws=x_scaled)
+            else:
+                # patch positions are independent (utils_vid.py:211-215): each rank searches a band of patch rows,
+                # then the int32 index map is summed across ranks (disjoint rows, zeros elsewhere)
+                rows = partition(desc.ho, self.world)
+                if not rows_equal(rows):
+                    nn.zero_()
+                with self._timed("patchnn_search"):
+                    ops.patchnn_search(desc, rgb_pad, xscale, res0, nn_out=nn, rows=(rows[self.rank], rows[self.rank + 1]),
+                                       scaled_ws=x_scaled)
+                with self._timed("exchange_nn"):
+                    exchange_row_bands(nn, rows, self.rank, self.group)
+            grad_rgb = self._get("grad_rgb", (T + pad, 3, h, w), torch.float32)
+            n_part = ops._lib.load().vl3d_vote_partials(T + pad, h, w)
+            vote_part = self._get("vote_part", (n_part,), torch.float64)
+            with self._timed("vote_loss"):
+                ranges = [(0, T + pad)] if self.world == 1 else owned_frame_ranges(self.bounds, self.rank, T, pad)
+                for i, fr in enumerate(ranges):
+                    lo = self._get(f"loss_out{i}", (1,), torch.float32)
+                    ops.vote_loss(desc, rgb_pad, xscale, res0, nn, cfg.get("rou", 0), cfg.get("scaling", 0.2), gain,
+                                  (T + pad, h, w), grad_out=grad_rgb, partials=vote_part, loss_out=lo, frames=fr)
+                    sums[4] += lo[0]
 
         # d total / d smooth_sums (host constants): MPV.py:517-531 with K cancelled, train_3dvid.py:230-240
         nx = max(T * h * (w - 1), 1) * m.mpi_d
@@ -416,7 +588,7 @@ class FusedLoopStep:
                 g_sta.zero_()
         bwd_sums = sums[:4] if smooth else None
         # adjoint of the loop pad for the frames we own, so the backward can run per frame chunk with pad = 0
-        if pad and t0 < pad:
+        if pad and t0 < pad and not band_mode:                      # (band mode: folded before the exchange)
             n = min(t1, pad) - t0
             grad_rgb[t0:t0 + n] += grad_rgb[T + t0:T + t0 + n]
         st = self._state.get("atlas_dyn")
