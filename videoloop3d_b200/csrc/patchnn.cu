@@ -950,7 +950,21 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
                 // per strip = 21.3 / 20.2 / 19.8 / 22.0 ms), balanced so that the last strip is not a stub
                 int SL = 24;
                 if (knobs().sl >= 2) SL = knobs().sl;                   // tuning aid
-                while (SL > 2 && (long long)desc->wo * ((rows + SL - 1) / SL) < 148 * 6) SL >>= 1;
+                if ((long long)desc->wo * ((rows + SL - 1) / SL) < 148 * 6) {
+                    // few patch rows (a rank's band of a sharded search): the grid is only a few waves of the 2 x 148
+                    // resident CTAs, so pick the strip count that minimises (waves) x (pixel rows a strip sweeps +
+                    // its fixed per-strip work, ~8 rows' worth)
+                    long long best = 0; int best_sl = 0;
+                    for (int strips = 1; strips <= rows; ++strips) {
+                        const int sl = (rows + strips - 1) / strips;
+                        if (sl < 2 && rows >= 2) break;
+                        if (sl > 32) continue;                          // (strip state is sized for <= 32 rows)
+                        const long long waves = ((long long)desc->wo * ((rows + sl - 1) / sl) + 295) / 296;
+                        const long long cost = waves * (sl * desc->s + desc->p - desc->s + 8);
+                        if (best_sl == 0 || cost < best) { best = cost; best_sl = sl; }
+                    }
+                    SL = best_sl > 0 ? best_sl : rows;
+                }
                 SL = (rows + (rows + SL - 1) / SL - 1) / ((rows + SL - 1) / SL);
                 if (SL > rows) SL = rows;
                 // candidate chunk width 8*ntb: fewest sweeps that still leave two CTAs per SM
