@@ -938,12 +938,11 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
             // config 5); VL3D_NN_TILE8=0: tuning aid
             const bool tile8 = knobs().tile8;
             const int P4 = (desc->p + 3) / 4 * 4;
-            // 16-byte chunk layout of a pixel row; with a stride that is not a multiple of 4 pixels the window starts are
-            // not 16-byte aligned: fine for TMA staging (box coordinates are element offsets), not for LDGSTS
-            const bool vec = (3 * desc->p + 3) / 4 == 3 * P4 / 4 &&
+            // (a stride that is not a multiple of 4 pixels puts window starts off the 16-byte grid: LDGSTS cannot copy them
+            // and the TMA unit raises an illegal-instruction fault for a box that starts at such an element — measured)
+            const bool vec = desc->s % 4 == 0 && (3 * desc->p + 3) / 4 == 3 * P4 / 4 &&
                              ((desc->x_sf | desc->x_sc | desc->x_sr | desc->y_sf | desc->y_sc | desc->y_sr) & 3) == 0 &&
                              (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
-            const bool aligned_x0 = desc->s % 4 == 0;
             if (vec && M >= 1 && M <= 3 && tile8) {
                 StripParams P{};
                 P.d = *desc; P.x = x; P.y = y; P.nn = nn_out; P.groups = 3 * (P4 / 4);
@@ -996,7 +995,7 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
                 // the wide chunk only pays when <= 2 sweeps cover the candidates (20.2 vs 22.0; n2=1024: 88 vs 79).
                 const int cands8 = best_ntb ? (S8_TJ * best_ntb - desc->pt) / desc->st + 1 : 1;
                 const bool few_sweeps = (desc->n2 + cands8 - 1) / cands8 <= 2 && tx_used >= 40;
-                if (fits && (tma || (few_sweeps && aligned_x0))) {
+                if (fits && (tma || few_sweeps)) {
                     const int tail = desc->p - (P4 - 4);
                     PP.P = P;
                     void (*kern)(Strip8Params) = nullptr;
