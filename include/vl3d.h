@@ -164,6 +164,15 @@ int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const float* xsca
                    float* y2x_out, float* weight_out, float* grad_out, double* partials, float* loss_out,
                    void* stream);
 
+/* The two trivial entries of MPMeshVid.losses (MPV.py:135-136), value and dL/dx in one pass over channel-major videos
+ * x (3,tx,h,w), y (3,ty,h,w), both contiguous:
+ *   kind 0 = Patch3DMSE (utils_vid.py:437-440): mean over the first min(tx,ty) frames of (x - y)^2;
+ *   kind 1 = Patch3DAvg (utils_vid.py:443-445): mean over (c,h,w) of (mean_t x - mean_t y)^2.
+ * grad_out (3,tx,h,w) or NULL; partials: >= vl3d_video_loss_partials() doubles. */
+int vl3d_video_loss_partials(void);
+int vl3d_video_loss(int32_t kind, const float* x, const float* y, int32_t tx, int32_t ty, int32_t h, int32_t w,
+                    float* grad_out, double* partials, float* loss_out, void* stream);
+
 /* ---- "next" rows ------------------------------------------------------------
  * vl3d_patch_l1 (N3, evaluations/NNMSE.py:45-53): err_out[ho,wo,n1] = mean |y_patch[nn] - x_patch| over the
  *   3*pt*p*p elements of each (patch position, query) pair, given the NN map from vl3d_patchnn_search.

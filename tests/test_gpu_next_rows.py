@@ -211,3 +211,26 @@ def _same_crop(dev_vid, host_vid, host_crop):
     """The view of `dev_vid` that corresponds to `host_crop`, a basic-slicing view of `host_vid`."""
     off = host_crop.storage_offset() - host_vid.storage_offset()
     return dev_vid.as_strided(host_crop.shape, host_crop.stride(), dev_vid.storage_offset() + off)
+
+
+def test_trivial_video_losses_match_their_formulas():
+    """`MPMeshVid.losses['mse' | 'avg']` (utils_vid.py:437-445) through `vl3d_video_loss`: value and gradient against the
+    reference's two-line torch expressions, equal and unequal frame counts."""
+    import videoloop3d_b200 as V
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    for tx, ty in ((5, 5), (7, 4), (3, 6)):
+        x = torch.rand(1, 3, tx, 13, 17, generator=g).to(dev).requires_grad_(True)
+        y = torch.rand(1, 3, ty, 13, 17, generator=g).to(dev)
+        frm = min(tx, ty)
+        for fn, ref in ((V.Patch3DMSE, lambda a: ((a[:, :, :frm] - y[:, :, :frm]) ** 2).mean()),
+                        (V.Patch3DAvg, lambda a: ((a.mean(dim=2) - y.mean(dim=2)) ** 2).mean())):
+            x.grad = None
+            out = fn(x, y, patch_size=3)
+            (out * 2.5).backward()
+            got_g = x.grad.clone()
+            x.grad = None
+            want = ref(x)
+            (want * 2.5).backward()
+            assert abs(float(out) - float(want)) < 1e-6 * abs(float(want))
+            assert float((got_g - x.grad).abs().max()) < 1e-6 * float(x.grad.abs().max())

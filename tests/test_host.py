@@ -360,3 +360,29 @@ def test_argument_validation_of_the_data_entry_points():
     with pytest.raises(_lib.Vl3dError, match="row range"):
         _lib.call("vl3d_scale_log_sum", p16, 4, p16, 4, 8, 8, 5, 3, p16, p16, None)
     assert lib.vl3d_vote_partials(50, 180, 320) == 50 * 10 * 23 and lib.vl3d_vote_partials(0, 1, 1) == 0
+
+
+def test_constructor_state_equals_reference_state():
+    """The dense model `MPMeshVid.__init__` builds (from the quad grid: tiles.quad_grid_faces / dense_atlas_uvs) carries
+    exactly the tensors the unmodified reference's constructor produced for the same arguments (MPV.py:26-104; stored in
+    tests/golden/render_dense.npz by oracle/make_golden.py::golden_render) — checkpoints are interchangeable."""
+    from util import load_golden
+    from videoloop3d_b200 import MPMeshVid, default_args
+    g = load_golden("render_dense")
+    H, W, D, hv, wv = int(g["H"]), int(g["W"]), int(g["mpi_d"]), int(g["hv"]), int(g["wv"])
+    args = default_args(mpi_d=D, mpi_h_verts=hv, mpi_w_verts=wv, atlas_grid_h=2, mpv_frm_num=int(g["T"]), mpi_h_scale=1.2,
+                        mpi_w_scale=1.2)
+    f = 0.8 * W
+    m = MPMeshVid(args, H, W, np.eye(4, dtype=np.float32), np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32),
+                  1.0, 10.0)
+    assert torch.equal(m.faces_dyn, torch.as_tensor(g["faces_dyn"]).long()) and torch.equal(m.uvfaces_dyn, m.faces_dyn)
+    assert len(m.faces) == 0 and len(m.uvfaces) == 0 and len(m.uvs) == 0
+    assert torch.equal(m.uvs_dyn.data, torch.as_tensor(g["uvs_dyn"]))            # bit for bit
+    assert torch.allclose(m._verts.data, torch.as_tensor(g["verts"]), rtol=0, atol=0)
+    assert torch.equal(m.planedepth, torch.as_tensor(g["planedepth"]))
+    assert tuple(m.atlas_dyn.shape) == tuple(g["atlas_dyn"].shape)
+    assert set(m.losses) == {"swd", "gpnn", "gpnn_lm", "mse", "avg"}
+    sd = m.state_dict()
+    for k in ("self.is_sparse", "self.atlas_full_w", "self.atlas_full_h", "self.atlas_grid_h", "self.atlas_grid_w", "self.has_dyn",
+              "self.atlas_full_dyn_w", "self.atlas_full_dyn_h", "self.atlas_grid_dyn_h", "self.atlas_grid_dyn_w"):
+        assert k in sd

@@ -8,7 +8,7 @@ Public surface mirrors the reference's Python operators:
 The numerical work is done by hand-written CUDA kernels in libvl3d.so (C ABI: include/vl3d.h).
 """
 from ._lib import Vl3dError, load as load_library  # noqa: F401
-from .loop_loss import (Patch3DAvg, Patch3DGPNNDirectLoss, Patch3DGPNNLowMemDownSampleLoss,  # noqa: F401
+from .loop_loss import (Patch3DAvg, Patch3DGPNNDirectLoss,   # noqa: F401
                         Patch3DGPNNLowMemLoss, Patch3DMSE)
 from .mpv import MPMeshVid, get_new_intrin, make_depths, gen_mpi_vertices, pose2extrin_torch  # noqa: F401
 from .optim import FusedAdam  # noqa: F401

@@ -52,6 +52,8 @@ _SIGNATURES = {
     "vl3d_vote_loss": (C.c_int, [C.POINTER(LossDesc), _P, _P, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_float,
                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                  _P, _P, _P, _P, _P, _P]),
+    "vl3d_video_loss_partials": (C.c_int, []),
+    "vl3d_video_loss": (C.c_int, [C.c_int32, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "vl3d_patch_l1": (C.c_int, [C.POINTER(LossDesc), _P, _P, _P, _P, _P]),
     "vl3d_to8b": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "vl3d_u8_to_unit": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P]),
@@ -65,7 +67,7 @@ EXPORTS = tuple(_SIGNATURES)
 _lib = None
 LAUNCHES = 0          # kernels launched through this binding (bench.py's gpu_launches)
 _LAUNCHES_PER_CALL = {"vl3d_composite_fwd": 1, "vl3d_composite_bwd": 1, "vl3d_scale_invariant": 2, "vl3d_frame_sum": 1, "vl3d_scale_invariant_presum": 2, "vl3d_scale_log_sum": 2, "vl3d_scale_finish": 1,
-                      "vl3d_patchnn_search": 1, "vl3d_scale_video": 1, "vl3d_patch_l1": 1, "vl3d_to8b": 1, "vl3d_u8_to_unit": 1, "vl3d_vote_loss": 2, "vl3d_adam_step": 1, "vl3d_fused_bwd_adam": 1}
+                      "vl3d_patchnn_search": 1, "vl3d_scale_video": 1, "vl3d_patch_l1": 1, "vl3d_to8b": 1, "vl3d_u8_to_unit": 1, "vl3d_vote_loss": 2, "vl3d_video_loss": 2, "vl3d_adam_step": 1, "vl3d_fused_bwd_adam": 1}
 
 
 class Vl3dError(RuntimeError):

@@ -907,6 +907,68 @@ static int validate_desc(const vl3d_loss_desc* L) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// the two trivial entries of MPMeshVid.losses (MPV.py:135-136): Patch3DMSE / Patch3DAvg (utils_vid.py:437-445)
+// on channel-major videos x (3,tx,h,w) and y (3,ty,h,w); value (block partials in double) and dL/dx in one pass.
+// ------------------------------------------------------------------------------------------------
+constexpr int VMSE_BLOCKS = 1184, VMSE_THREADS = 256;
+
+__global__ void __launch_bounds__(VMSE_THREADS) video_mse_kernel(const float* __restrict__ x, const float* __restrict__ y, int tx,
+                                                                 int ty, int frm, size_t hw, float* __restrict__ grad,
+                                                                 double* partials) {
+    const size_t n = (size_t)3 * frm * hw, per_c = (size_t)frm * hw;
+    const float gscale = 2.f / (float)n;
+    float acc = 0.f;
+    for (size_t i = (size_t)blockIdx.x * VMSE_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * VMSE_THREADS) {
+        const size_t c = i / per_c, r = i - c * per_c;             // r = f*hw + pixel
+        const size_t xi = c * (size_t)tx * hw + r;
+        const float d = __ldg(x + xi) - __ldg(y + c * (size_t)ty * hw + r);
+        acc = fmaf(d, d, acc);
+        if (grad) grad[xi] = gscale * d;
+    }
+    __shared__ float s_part[VMSE_THREADS / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < VMSE_THREADS / 32; ++i) a += (double)s_part[i];
+        partials[blockIdx.x] = a;
+    }
+}
+
+__global__ void __launch_bounds__(VMSE_THREADS) video_avg_kernel(const float* __restrict__ x, const float* __restrict__ y, int tx,
+                                                                 int ty, size_t hw, float* __restrict__ grad, double* partials) {
+    const size_t n = (size_t)3 * hw;
+    const float gscale = 2.f / ((float)n * (float)tx);
+    float acc = 0.f;
+    for (size_t i = (size_t)blockIdx.x * VMSE_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * VMSE_THREADS) {
+        const size_t c = i / hw, r = i - c * hw;
+        const float* xp = x + c * (size_t)tx * hw + r;
+        const float* yp = y + c * (size_t)ty * hw + r;
+        float sx = 0.f, sy = 0.f;
+        for (int f = 0; f < tx; ++f) sx += __ldg(xp + (size_t)f * hw);
+        for (int f = 0; f < ty; ++f) sy += __ldg(yp + (size_t)f * hw);
+        const float d = sx / (float)tx - sy / (float)ty;
+        acc = fmaf(d, d, acc);
+        if (grad) {
+            float* gp = grad + c * (size_t)tx * hw + r;
+            for (int f = 0; f < tx; ++f) gp[(size_t)f * hw] = gscale * d;
+        }
+    }
+    __shared__ float s_part[VMSE_THREADS / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < VMSE_THREADS / 32; ++i) a += (double)s_part[i];
+        partials[blockIdx.x] = a;
+    }
+}
+
 // tuning knobs (scripts/tune_search.py), read from the environment ONCE per process
 struct Knobs { bool tile8, tma, vote_v1; int sl; };
 static const Knobs& knobs() {
@@ -1117,6 +1179,37 @@ extern "C" int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const 
     if (int e = check_launch("vote_loss")) return e;
     finalize_mean_kernel<<<1, 1024, 0, st>>>(partials, nblocks, denom, loss_out);
     return check_launch("vote_finalize");
+}
+
+extern "C" int vl3d_video_loss_partials(void) { return VMSE_BLOCKS; }
+
+extern "C" int vl3d_video_loss(int32_t kind, const float* x, const float* y, int32_t tx, int32_t ty, int32_t h, int32_t w,
+                               float* grad_out, double* partials, float* loss_out, void* stream) {
+    VL3D_REQUIRE(x && y && partials && loss_out, VL3D_ENULL, "video_loss: NULL pointer");
+    VL3D_REQUIRE((kind == 0 || kind == 1) && tx >= 1 && ty >= 1 && h >= 1 && w >= 1, VL3D_EINVAL, "video_loss: bad kind / sizes");
+    const size_t hw = (size_t)h * w;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kind == 0) {
+        const int frm = tx < ty ? tx : ty;
+        const size_t n = (size_t)3 * frm * hw;
+        int blocks = (int)((n + VMSE_THREADS - 1) / VMSE_THREADS);
+        if (blocks > VMSE_BLOCKS) blocks = VMSE_BLOCKS;
+        if (grad_out && frm < tx) {                                 // frames beyond the common length take no part
+            cudaError_t ce = cudaMemsetAsync(grad_out, 0, (size_t)3 * tx * hw * sizeof(float), st);
+            if (ce != cudaSuccess) return set_err((int)ce, "video_loss: %s", cudaGetErrorString(ce));
+        }
+        video_mse_kernel<<<blocks, VMSE_THREADS, 0, st>>>(x, y, tx, ty, frm, hw, grad_out, partials);
+        if (int e = check_launch("video_mse")) return e;
+        finalize_mean_kernel<<<1, 1024, 0, st>>>(partials, blocks, (double)n, loss_out);
+    } else {
+        const size_t n = (size_t)3 * hw;
+        int blocks = (int)((n + VMSE_THREADS - 1) / VMSE_THREADS);
+        if (blocks > VMSE_BLOCKS) blocks = VMSE_BLOCKS;
+        video_avg_kernel<<<blocks, VMSE_THREADS, 0, st>>>(x, y, tx, ty, hw, grad_out, partials);
+        if (int e = check_launch("video_avg")) return e;
+        finalize_mean_kernel<<<1, 1024, 0, st>>>(partials, blocks, (double)n, loss_out);
+    }
+    return check_launch("video_loss_finalize");
 }
 
 extern "C" int vl3d_patch_l1(const vl3d_loss_desc* desc, const float* x, const float* y, const int32_t* nn, float* err_out,

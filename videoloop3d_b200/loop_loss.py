@@ -95,23 +95,39 @@ def _check_dist(kwargs):
         raise NotImplementedError("dist_fn='ssim' is never configured by the reference and is out of scope")
 
 
-class Patch3DGPNNLowMemDownSampleLoss:
-    """Registered under 'gpnn_down' (MPV.py:137) but used by no shipped config; out of scope."""
+class _VideoLoss(torch.autograd.Function):
+    """Patch3DMSE / Patch3DAvg on (1,3,t,h,w) videos through `vl3d_video_loss` (value + dL/dx in one launch)."""
 
-    def __init__(self):
-        self.last_y2x = None
-        self.last_weight = None
+    @staticmethod
+    def forward(ctx, x, y, kind):
+        for v in (x, y):
+            if v.dim() != 5 or v.shape[0] != 1 or v.shape[1] != 3:
+                raise Vl3dError(f"expected a (1,3,t,h,w) video, got {tuple(v.shape)}")
+        if not x.is_cuda:
+            raise Vl3dError("the looping losses run on CUDA only (no CPU fallback)")
+        if tuple(x.shape[-2:]) != tuple(y.shape[-2:]):
+            raise ValueError("x and y must have the same spatial size")
+        xc, yc = x[0].contiguous().float(), y[0].detach().contiguous().float()
+        grad = torch.empty_like(xc) if x.requires_grad else None
+        lib = ops._lib
+        part = torch.empty(lib.load().vl3d_video_loss_partials(), dtype=torch.float64, device=x.device)
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+        lib.call("vl3d_video_loss", int(kind), lib.ptr(xc), lib.ptr(yc), int(xc.shape[1]), int(yc.shape[1]), int(xc.shape[2]),
+                 int(xc.shape[3]), lib.ptr(grad), lib.ptr(part), lib.ptr(out), lib.stream_ptr())
+        ctx.save_for_backward(grad)
+        return out.reshape(())
 
-    def __call__(self, *a, **k):
-        raise NotImplementedError("gpnn_down is not used by any reference config (SURVEY.md §2 row 3)")
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return (None if grad is None else (grad * g)[None]), None, None
 
 
 def Patch3DMSE(x, y, **kwargs):
-    """utils_vid.py:437-440 (trivial; plain torch)."""
-    frm = min(x.shape[2], y.shape[2])
-    return ((x[:, :, :frm] - y[:, :, :frm]) ** 2).mean()
+    """utils_vid.py:437-440: mean squared difference over the frames both videos have."""
+    return _VideoLoss.apply(x, y, 0)
 
 
 def Patch3DAvg(x, y, **kwargs):
-    """utils_vid.py:443-445 (trivial; plain torch)."""
-    return ((x.mean(dim=2) - y.mean(dim=2)) ** 2).mean()
+    """utils_vid.py:443-445: mean squared difference of the temporal means."""
+    return _VideoLoss.apply(x, y, 1)

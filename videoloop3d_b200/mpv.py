@@ -21,10 +21,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, tiles
 from ._lib import Vl3dError
-from .loop_loss import (Patch3DAvg, Patch3DGPNNDirectLoss, Patch3DGPNNLowMemDownSampleLoss, Patch3DGPNNLowMemLoss,
-                        Patch3DMSE, _check_dist)
+from .loop_loss import Patch3DAvg, Patch3DGPNNDirectLoss, Patch3DGPNNLowMemLoss, Patch3DMSE, _check_dist
 from .optim import FusedAdam
 
 
@@ -110,94 +109,92 @@ class LazyVariables(dict):
 
 
 class MPMeshVid(nn.Module):
+    """State contract (what checkpoints, optimisers and the kernels' host side rely on; reference: MPV.py:26-138):
+    parameters `atlas (1,4,Hs,Ws)`, `atlas_dyn (T,4,Hd,Wd)`, `uvs`, `uvs_dyn`, `_verts`; buffers `ref_extrin`,
+    `ref_intrin`, `planedepth`, `faces(_dyn)`, `uvfaces(_dyn)`.  A fresh model is dense: every quad dynamic, plane d in
+    cell (d // grid_w, d % grid_w) of the dynamic atlas."""
+
+    UNSUPPORTED = "unsupported by the vl3d kernels (and unused by every shipped stage-2 config)"
+
     def __init__(self, args, H, W, ref_extrin, ref_intrin, near, far):
         super().__init__()
+        self._check_supported(args)
         self.args = args
-        self.frm_num = args.mpv_frm_num
-        self.isloop = args.mpv_isloop
-        mpi_h, mpi_w = int(args.mpi_h_scale * H), int(args.mpi_w_scale * W)
-        self.mpi_d, self.near, self.far = args.mpi_d, near, far
-        self.mpi_h_verts, self.mpi_w_verts = args.mpi_h_verts, args.mpi_w_verts
-        self.H, self.W = H, W
+        self.H, self.W, self.near, self.far = H, W, near, far
+        self.frm_num, self.isloop = args.mpv_frm_num, args.mpv_isloop
+        self.mpi_d, self.mpi_h_verts, self.mpi_w_verts = args.mpi_d, args.mpi_h_verts, args.mpi_w_verts
+        self.rgb_mlp_type, self.use_viewdirs, self.optimize_geometry = args.rgb_mlp_type, False, False
+        for k in ("swd_patch_size", "swd_patcht_size", "swd_stride", "swd_stridet"):
+            setattr(self, k, getattr(args, k))
+        self._init_cameras(ref_extrin, ref_intrin)
+        self._init_plane_mesh(H, W, near, far)
+        self._init_atlases(H, W)
+        self.losses = {                                             # same keys as MPV.py:131-138 minus 'gpnn_down'
+            'swd': None,                                            # (see INTEGRATION.md: the reference's gpnn_down cannot run)
+            'gpnn': Patch3DGPNNDirectLoss(),
+            'gpnn_lm': Patch3DGPNNLowMemLoss(),
+            'mse': Patch3DMSE,
+            'avg': Patch3DAvg,
+        }
+        self._pack = None
+        self._pack_key = None
+
+    @classmethod
+    def _check_supported(cls, args):
         if getattr(args, "fp16", False):
             raise Vl3dError("fp16 is marked 'do NOT use' in the reference (config_parser.py:32-33); fp32 only")
         if getattr(args, "atlas_cnl", 4) != 4 or getattr(args, "rgb_mlp_type", "direct") != "direct":
-            raise Vl3dError("only atlas_cnl=4 / rgb_mlp_type=direct is supported (every shipped config)")
+            raise Vl3dError(f"atlas_cnl != 4 / rgb_mlp_type != direct: {cls.UNSUPPORTED}")
         if args.rgb_activate != "sigmoid" or args.alpha_activate != "sigmoid":
-            raise Vl3dError("only sigmoid activations are supported (every shipped config)")
-        if self.mpi_d > 32:
+            raise Vl3dError(f"non-sigmoid activations: {cls.UNSUPPORTED}")
+        if args.mpi_d > 32:
             raise Vl3dError("mpi_d > 32 is not supported by the composite kernel")
+        if args.mpi_d % args.atlas_grid_h:
+            raise AssertionError("mpi_d and atlas_grid_h should match")
 
-        # dense layout: planes on an atlas_grid_h x (D / atlas_grid_h) grid (MPV.py:37-44)
-        self.atlas_grid_dyn_h, self.atlas_grid_dyn_w = args.atlas_grid_h, self.mpi_d // args.atlas_grid_h
-        assert self.mpi_d % self.atlas_grid_dyn_h == 0, "mpi_d and atlas_grid_h should match"
-        self.is_sparse = False
-        self.has_dyn = False
-        self.atlas_full_dyn_h = int(self.atlas_grid_dyn_h * mpi_h)
-        self.atlas_full_dyn_w = int(self.atlas_grid_dyn_w * mpi_w)
-        self.atlas_grid_h, self.atlas_grid_w = self.atlas_grid_dyn_h, self.atlas_grid_dyn_w
-        self.atlas_full_h, self.atlas_full_w = self.atlas_full_dyn_h, self.atlas_full_dyn_w
-
+    def _init_cameras(self, ref_extrin, ref_intrin):
         ref_extrin, ref_intrin = np.asarray(ref_extrin), np.asarray(ref_intrin)
         assert ref_extrin.shape == (4, 4) and ref_intrin.shape == (3, 3)
         self.register_buffer("ref_extrin", torch.tensor(ref_extrin))
         self.register_buffer("ref_intrin", torch.tensor(ref_intrin).float())
 
-        planedepth = make_depths(self.mpi_d, near, far).float().flip(0)          # nearest plane first (MPV.py:51)
-        self.register_buffer("planedepth", planedepth)
-        self.H_start, self.W_start = (mpi_h - H) // 2, (mpi_w - W) // 2
-        ref_intrin_mpi = get_new_intrin(self.ref_intrin, -self.H_start, -self.W_start)
-        verts = gen_mpi_vertices(mpi_h, mpi_w, ref_intrin_mpi, args.mpi_h_verts, args.mpi_w_verts, planedepth)
+    def _init_plane_mesh(self, H, W, near, far):
+        """D fronto-parallel planes, uniform in disparity, nearest first; each a regular (hv x wv) vertex grid that spans
+        the scaled image rectangle, centred on the reference view (MPV.py:47-71)."""
+        args, D, hv, wv = self.args, self.mpi_d, self.mpi_h_verts, self.mpi_w_verts
+        self._mpi_hw = (int(args.mpi_h_scale * H), int(args.mpi_w_scale * W))
+        self.H_start, self.W_start = (self._mpi_hw[0] - H) // 2, (self._mpi_hw[1] - W) // 2
+        self.register_buffer("planedepth", make_depths(D, near, far).float().flip(0))
+        centred = get_new_intrin(self.ref_intrin, -self.H_start, -self.W_start)
+        verts = gen_mpi_vertices(*self._mpi_hw, centred, hv, wv, self.planedepth)
         if args.normalize_verts:
-            verts = (verts.reshape(self.mpi_d, -1) / planedepth[:, None]).reshape_as(verts)
+            verts = (verts.reshape(D, -1) / self.planedepth[:, None]).reshape_as(verts)
+        self._verts = nn.Parameter(verts, requires_grad=True)
+        quads = torch.from_numpy(tiles.quad_grid_faces(D, hv, wv))
+        self.register_buffer("faces", quads[:0].clone())           # no static tiles until init_from_mpi
+        self.register_buffer("faces_dyn", quads)
+        self.register_buffer("uvfaces", quads[:0].clone())
+        self.register_buffer("uvfaces_dyn", quads.clone())          # dense layout: uv vertices == mesh vertices
 
-        hv, wv = args.mpi_h_verts, args.mpi_w_verts
-        vid = torch.arange(len(verts)).reshape(self.mpi_d, hv, wv)
-        tri_a = torch.stack([vid[:, :-1, :-1], vid[:, :-1, 1:], vid[:, 1:, 1:]], -1)      # (v00, v01, v11)
-        tri_b = torch.stack([vid[:, 1:, 1:], vid[:, 1:, :-1], vid[:, :-1, :-1]], -1)      # (v11, v10, v00)
-        faces = torch.cat([tri_a.reshape(-1, 1, 3), tri_b.reshape(-1, 1, 3)], dim=1).reshape(-1, 3)
-
-        gy, gx = torch.meshgrid(torch.arange(self.atlas_grid_dyn_h) / self.atlas_grid_dyn_h,
-                                torch.arange(self.atlas_grid_dyn_w) / self.atlas_grid_dyn_w, indexing="ij")
-        uv_plane = torch.stack([gx, gy], dim=-1) * 2 - 1
-        cell = (1 - uv_plane[-1, -1]).reshape(1, 1, 2)
-        vy, vx = torch.meshgrid(torch.linspace(0, 1, hv), torch.linspace(0, 1, wv), indexing="ij")
-        uv_vox = torch.stack([vx, vy], dim=-1).reshape(1, -1, 2) * cell
-        uvs = (uv_plane.reshape(-1, 1, 2) + uv_vox.reshape(1, -1, 2)).reshape(-1, 2)
-
-        atlas = torch.rand((1, 4, int(self.atlas_full_h), int(self.atlas_full_w)))
-        atlas_dyn = torch.randn((self.frm_num, 4, int(self.atlas_full_dyn_h), int(self.atlas_full_dyn_w))) \
-            * args.init_std
+    def _init_atlases(self, H, W):
+        """Dense layout: the planes tile the dynamic atlas on an atlas_grid_h x (D / atlas_grid_h) grid (MPV.py:37-44,
+        75-104); texels N(0, init_std), alpha logits -2.  The static atlas has the same size and is unused until a
+        stage-1 result is loaded.  RNG order (static first) as in the reference, so seeded runs start identically."""
+        args = self.args
+        gh, gw = args.atlas_grid_h, self.mpi_d // args.atlas_grid_h
+        self.is_sparse = self.has_dyn = False
+        self.atlas_grid_dyn_h, self.atlas_grid_dyn_w = self.atlas_grid_h, self.atlas_grid_w = gh, gw
+        full = (int(gh * self._mpi_hw[0]), int(gw * self._mpi_hw[1]))
+        self.atlas_full_dyn_h, self.atlas_full_dyn_w = self.atlas_full_h, self.atlas_full_w = full
+        uv = tiles.dense_atlas_uvs(gh, gw, self.mpi_h_verts, self.mpi_w_verts)
+        self.register_parameter("uvs", nn.Parameter(uv[:0].clone(), requires_grad=True))
+        self.register_parameter("uvs_dyn", nn.Parameter(uv, requires_grad=True))
+        atlas = torch.rand((1, 4) + full)
+        atlas_dyn = torch.randn((self.frm_num, 4) + full) * args.init_std
         atlas[:, -1] = -2                                                          # MPV.py:109-110
         atlas_dyn[:, -1] = -2
-
-        self.register_parameter("uvs", nn.Parameter(uvs[:0].clone(), requires_grad=True))
-        self.register_parameter("uvs_dyn", nn.Parameter(uvs, requires_grad=True))
-        self.register_buffer("uvfaces", faces[:0].clone().long())
-        self.register_buffer("uvfaces_dyn", faces.clone().long())
-        self._verts = nn.Parameter(verts, requires_grad=True)
-        self.register_buffer("faces", faces[:0].long())
-        self.register_buffer("faces_dyn", faces.long())
-        self.optimize_geometry = False
         self.register_parameter("atlas_dyn", nn.Parameter(ops.as_texels(atlas_dyn), requires_grad=True))
         self.register_parameter("atlas", nn.Parameter(ops.as_texels(atlas), requires_grad=True))
-
-        self.rgb_mlp_type = args.rgb_mlp_type
-        self.use_viewdirs = False
-        self.swd_patch_size = args.swd_patch_size
-        self.swd_patcht_size = args.swd_patcht_size
-        self.swd_stride = args.swd_stride
-        self.swd_stridet = args.swd_stridet
-        self.losses = {                                                            # MPV.py:131-138
-            'swd': None,
-            'gpnn': Patch3DGPNNDirectLoss(),
-            'gpnn_lm': Patch3DGPNNLowMemLoss(),
-            'mse': Patch3DMSE,
-            'avg': Patch3DAvg,
-            'gpnn_down': Patch3DGPNNLowMemDownSampleLoss(),
-        }
-        self._pack = None
-        self._pack_key = None
 
     # ------------------------------------------------------------------ geometry cache
     @property
