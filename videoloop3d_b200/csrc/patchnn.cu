@@ -624,21 +624,30 @@ __global__ void __launch_bounds__(VOTE_THREADS) vote_loss_batched_kernel(const _
             float v0 = 0.f, v1 = 0.f, v2 = 0.f;
             const int cnt = max(iy1 - iy0 + 1, 0) * max(ix1 - ix0 + 1, 0) * max(k1 - k0 + 1, 0);
             const float* yb = P.y + (size_t)py * L.y_sr + px;
-            const int* nn0 = P.nn + ((size_t)iy0 * L.wo + ix0) * L.n1 + k0;
             const size_t nn_row = (size_t)L.wo * L.n1;
+            // Patch columns are visited by PHASE (column index mod NX), not by offset from the first covering column:
+            // windows of one phase are NX*s >= p pixels apart, so every pixel lies in at most one of them and the
+            // 32 adjacent pixels of a warp meet only ~32/(NX*s) + 1 distinct patches per step instead of 32/s — the
+            // gathered target texels form ~3 runs of p pixels instead of 8 runs of s pixels (fewer L1 wavefronts per
+            // load, and the NN indices are broadcast loads).  The set of patches per pixel is unchanged.
+            const int cx = px / s;                                  // last patch column that starts at or before px
 #pragma unroll
             for (int jy = 0; jy < NY; ++jy) {
                 const bool vy = iy0 + jy <= iy1;
+                const int* nny = P.nn + (size_t)(iy0 + jy) * nn_row + k0;
                 int fr[NX][NK];
 #pragma unroll
-                for (int jx = 0; jx < NX; ++jx)
+                for (int jx = 0; jx < NX; ++jx) {
+                    const int ix = cx - (cx - jx + NX) % NX;        // largest column <= cx of phase jx
+                    const bool vx = vy && ix >= ix0 && ix <= ix1;
 #pragma unroll
                     for (int jk = 0; jk < NK; ++jk) {
-                        const bool ok = vy && ix0 + jx <= ix1 && k0 + jk <= k1;
+                        const bool ok = vx && k0 + jk <= k1;
                         int nnv = 0;
-                        if (ok) nnv = __ldg(nn0 + jy * nn_row + jx * L.n1 + jk);
+                        if (ok) nnv = __ldg(nny + (size_t)ix * L.n1 + jk);
                         fr[jx][jk] = ok ? nnv * st + (tf - (k0 + jk) * st) : -1;
                     }
+                }
                 float a0[NX][NK], a1[NX][NK], a2[NX][NK];
 #pragma unroll
                 for (int jx = 0; jx < NX; ++jx)
