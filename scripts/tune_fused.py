@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Sweep of the fused backward + Adam kernel's schedule knobs at the bench workload (one process, one model).
 
-    python scripts/tune_fused.py [--workload step720p] [--steps 3] [--configs "mode:ctas:row_block:zero_ahead:adam_lag,..."]
+    python scripts/tune_fused.py [--workload step720p] [--steps 3] [--configs "mode:ctas:row_block:zero_ahead:adam_lag:seg_texels,..."]
 
 Prints one line per configuration: CUDA-event ms of the fused kernel.  Run it under
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum -k regex:fused_bwd_adam
@@ -47,7 +47,7 @@ def main():
         mode = f[0]
         ctas = int(f[1]) if len(f) > 1 else 3
         opts = dict(ctas_per_sm=ctas)
-        for name, i in (("row_block", 2), ("zero_ahead", 3), ("adam_lag", 4)):
+        for name, i in (("row_block", 2), ("zero_ahead", 3), ("adam_lag", 4), ("seg_texels", 5)):
             if len(f) > i and f[i] != "":
                 opts[name] = int(f[i])
         step.fused, step.fused_opts = mode, opts

@@ -1184,6 +1184,7 @@ extern "C" int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const 
     const bool batched = !vote_v1;
     if (batched && ms <= 2 && mt <= 3) vote_loss_batched_kernel<2, 2, 3><<<grid, VOTE_THREADS, 0, st>>>(P);
     else if (batched && ms <= 3 && mt <= 3) vote_loss_batched_kernel<3, 3, 3><<<grid, VOTE_THREADS, 0, st>>>(P);
+    else if (batched && ms <= 4 && mt <= 3) vote_loss_batched_kernel<4, 4, 3><<<grid, VOTE_THREADS, 0, st>>>(P);   // p = 15, s = 4
     else vote_loss_kernel<<<grid, VOTE_THREADS, 0, st>>>(P);
     if (int e = check_launch("vote_loss")) return e;
     finalize_mean_kernel<<<1, 1024, 0, st>>>(partials, nblocks, denom, loss_out);
