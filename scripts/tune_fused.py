@@ -47,7 +47,7 @@ def main():
         mode = f[0]
         ctas = int(f[1]) if len(f) > 1 else 3
         opts = dict(ctas_per_sm=ctas)
-        for name, i in (("row_block", 2), ("zero_ahead", 3), ("adam_lag", 4), ("seg_texels", 5)):
+        for name, i in (("row_block", 2), ("zero_ahead", 3), ("adam_lag", 4), ("seg_texels", 5)):   # e.g. generic:3::::65536
             if len(f) > i and f[i] != "":
                 opts[name] = int(f[i])
         step.fused, step.fused_opts = mode, opts
