@@ -375,7 +375,24 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
 
     const int D = p.view.D;
     const float qwf = (float)p.view.qw, qhf = (float)p.view.qh;
-    int d = 0;                                                    // next plane to test
+    // per-thread path: which planes does this pixel's ray hit on an existing quad?  All D tests up front — their
+    // quad-table loads are independent and overlap; walking the planes lazily inside the slot loop chained up to D
+    // dependent loads per pixel and made the backward of a tile-culled model as slow as the dense one (18.4 ms at
+    // 720p for a quarter of the samples).
+    unsigned hits = 0u;
+    if (!use_tma) {
+#pragma unroll 8
+        for (int dd = 0; dd < D; ++dd) {
+            float gx, gy;
+            int kind = 0;
+            if (plane_grid_lean(&p.view.hom[dd * 9], u, v, qwf, qhf, gx, gy)) {
+                int qx, qy;
+                const float4* qp = quad_at(p, dd, gx, gy, qx, qy);
+                kind = __ldg(&reinterpret_cast<const int4*>(qp + 1)->z);
+            }
+            hits |= (kind != 0 ? 1u : 0u) << dd;
+        }
+    }
     // MODE 2: planes of this tile in order, TMA issue state of thread 0
     const int nplanes = __popc(in_mask);
     unsigned rem_planes = in_mask, rem_issue = in_mask;
@@ -437,20 +454,18 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
                 for (int f = 0; f < TF; ++f) val[f] = sv;
             }
         } else {
-            // slot k of this pixel = its k-th hit plane along the ray (utils.py:64-69): advance to the next plane
-            // whose quad under the ray exists.  Nothing is known in advance; the loop ends when no thread of the
-            // tile (warp, without the regulariser) has a slot left.
-            while (d < D) {
+            // slot k of this pixel = its k-th hit plane along the ray (utils.py:64-69): the next set bit of the hit mask
+            // built in the prologue.  The loop ends when no thread of the tile (warp, without the regulariser) has a
+            // slot left.
+            if (hits != 0u) {
+                const int dd = __ffs(hits) - 1;
+                hits &= hits - 1u;
                 float gx, gy;
-                const bool hit = plane_grid_lean(&p.view.hom[d * 9], u, v, qwf, qhf, gx, gy);
-                const int dd = d++;
-                if (!hit) continue;
+                plane_grid_lean(&p.view.hom[dd * 9], u, v, qwf, qhf, gx, gy);
                 int qx, qy;
                 const float4* qp = quad_at(p, dd, gx, gy, qx, qy);
                 const int4 qb = __ldg(reinterpret_cast<const int4*>(qp + 1));
-                if (qb.z == 0) continue;
                 tp = geo_from_quad(p, qp, qb, qx, qy, gx, gy);
-                break;
             }
             if (tp.kind == 2) {
 #pragma unroll
