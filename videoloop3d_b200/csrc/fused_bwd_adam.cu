@@ -67,6 +67,10 @@ __device__ __forceinline__ void adam4(float4& pp, const float4 gg, float4& mm, f
 }
 
 // Adam on rows x width texels starting at texel `base` of frames [t0, t0 + FUSED_TF) (row stride = dyn_w).
+// A CTA's streaming rate is set by the bytes it keeps in flight: every thread loads ADAM_U texels x FUSED_TF frames x
+// (p, m, v, g) = 16 x 16 B before it computes (with 8 loads the fused pass was limited by Adam's per-CTA rate, not by DRAM).
+constexpr int ADAM_U = 2;
+
 __device__ __forceinline__ void adam_rect(const FusedParams& F, const int t0, const int base, const int width, const int rows,
                                           const int flags) {
     const CompositeParams& p = F.R.p;
@@ -78,33 +82,38 @@ __device__ __forceinline__ void adam_rect(const FusedParams& F, const int t0, co
     float4* const M0 = F.m + (size_t)t0 * frame + base;
     float4* const V0 = F.v + (size_t)t0 * frame + base;
     const bool has_grad = (flags & FLAG_HAS_GRAD) != 0;
+    const bool rezero = has_grad && (flags & FLAG_REZERO);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int NT = BX * BY, NV = ADAM_U * FUSED_TF;
     for (int r = 0; r < rows; ++r) {
         const size_t ro = (size_t)r * stride;
-        for (int c0 = 0; c0 < width; c0 += BX * BY) {
-            const int c = c0 + tid;
-            const bool in = c < width;
-            float4 pp[FUSED_TF], gg[FUSED_TF], mm[FUSED_TF], vv[FUSED_TF];
+        for (int c0 = tid; c0 < width; c0 += NT * ADAM_U) {
+            float4 pp[NV], gg[NV], mm[NV], vv[NV];
+            size_t off[NV];
+            bool in[NV];
 #pragma unroll
-            for (int f = 0; f < FUSED_TF; ++f) {
-                const size_t o = (size_t)f * frame + ro + c;
-                pp[f] = mm[f] = vv[f] = gg[f] = zero4;
-                if (in) {                                           // streams: evict-first; the gradient: L2 only
-                    pp[f] = __ldcs(P0 + o);
-                    mm[f] = __ldcs(M0 + o);
-                    vv[f] = __ldcs(V0 + o);
-                    if (has_grad) gg[f] = __ldcg(G0 + o);
-                }
-            }
-            if (in) {
+            for (int u = 0; u < ADAM_U; ++u)
 #pragma unroll
                 for (int f = 0; f < FUSED_TF; ++f) {
-                    const size_t o = (size_t)f * frame + ro + c;
-                    adam4(pp[f], gg[f], mm[f], vv[f], F);
-                    __stcs(P0 + o, pp[f]);
-                    __stcs(M0 + o, mm[f]);
-                    __stcs(V0 + o, vv[f]);
-                    if (has_grad && (flags & FLAG_REZERO)) G0[o] = zero4;
+                    const int c = c0 + u * NT, k = u * FUSED_TF + f;
+                    in[k] = c < width;
+                    off[k] = (size_t)f * frame + ro + c;
+                    pp[k] = mm[k] = vv[k] = gg[k] = zero4;
+                    if (in[k]) {                                    // streams: evict-first; the gradient: L2 only
+                        pp[k] = __ldcs(P0 + off[k]);
+                        mm[k] = __ldcs(M0 + off[k]);
+                        vv[k] = __ldcs(V0 + off[k]);
+                        if (has_grad) gg[k] = __ldcg(G0 + off[k]);
+                    }
+                }
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                if (in[k]) {
+                    adam4(pp[k], gg[k], mm[k], vv[k], F);
+                    __stcs(P0 + off[k], pp[k]);
+                    __stcs(M0 + off[k], mm[k]);
+                    __stcs(V0 + off[k], vv[k]);
+                    if (rezero) G0[off[k]] = zero4;
                 }
             }
         }
