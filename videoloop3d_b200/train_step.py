@@ -233,9 +233,11 @@ class FusedLoopStep:
         "band" / "band-zero": the same kernel walking the screen in row bands so that a band's gradient rows stay
         L2-resident between accumulation and Adam (dense layout only; "-zero": rows are zeroed just ahead of the
         band and dropped after Adam instead of living in HBM as zeros);
-        None: VL3D_FUSED from the environment (read once, here), else "auto" = generic (on B200 the band schedules do
-        not keep the gradient on chip under the DRAM-saturating Adam traffic and are slower:
-        profiles/r02_fused_bwd_adam.md)."""
+        None: VL3D_FUSED from the environment (read once, here), else "auto" = band for the dense layout, generic
+        otherwise.  (On B200 the band schedules do NOT keep the gradient on chip under the DRAM-saturating Adam traffic
+        — profiles/r02_fused_bwd_adam.md — but with Adam lagging one wave of resident tiles behind they match the
+        generic schedule in steady state and shorten its pipeline fill / drain from one frame chunk to ~1/8 of one,
+        which matters when a rank owns few chunks.)"""
         if not model.atlas_dyn.is_cuda:
             raise Vl3dError("FusedLoopStep needs the model on a CUDA device")
         self.model = model
@@ -311,6 +313,14 @@ class FusedLoopStep:
             self._buf[key] = b
         return b
 
+    def _adam_lag(self, w, smooth):
+        """Tile rows the queue advances while one wave of resident tiles runs (+1): an Adam item placed that far behind
+        the last tile row it depends on is claimed when those tiles are done, so no CTA spins on a counter."""
+        gx = schedule.tile_grid(1, w, smooth)[0]
+        sms = torch.cuda.get_device_properties(self.model.atlas_dyn.device).multi_processor_count
+        per_sm = self.fused_opts.get("ctas_per_sm", 0) or 3
+        return -(-sms * per_sm // gx) + 1
+
     def _schedule_for(self, mode, view, pack, h, w, smooth, dyn_hw):
         """Work-item table of the fused kernel for this view (cached: a table depends on the view only)."""
         key = (mode, bytes(view), bool(smooth), tuple(dyn_hw))
@@ -323,7 +333,7 @@ class FusedLoopStep:
                 homs = np.ctypeslib.as_array(view.hom).reshape(-1)[:pack.D * 9].astype(np.float64)
                 sched = schedule.band_schedule(homs, view.cx, view.cy, h, w, pack.table, pack.D, pack.qh, pack.qw, dyn_hw[0],
                                                dyn_hw[1], smooth, row_block=o.get("row_block", 8),
-                                               zero_ahead=o.get("zero_ahead", 2), adam_lag=o.get("adam_lag", 2),
+                                               zero_ahead=o.get("zero_ahead", 2), adam_lag=o.get("adam_lag", self._adam_lag(w, smooth)),
                                                use_zero=(mode == "band-zero"))
             dev = self.model.atlas_dyn.device
             sched.dev_items = torch.from_numpy(np.ascontiguousarray(sched.items)).to(dev)
@@ -601,7 +611,7 @@ class FusedLoopStep:
         self.t += 1
         mode = self.fused
         if mode == "auto":
-            mode = "generic"
+            mode = "band" if pack.rect_planes else "generic"
         if mode.startswith("band") and not pack.rect_planes:
             mode = "generic"
         Te = Tl // 2 * 2 if mode != "off" else 0                   # frames handled by the fused kernel (chunks of 2)
