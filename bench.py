@@ -795,7 +795,7 @@ def main():
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-operators-on-GPU leg")
     ap.add_argument("--quick", action="store_true", help="headline workload only (no sparse / patch180 / sweep / config0 legs)")
     ap.add_argument("--no-smooth", action="store_true", help="tuning aid: drop the smoothness regularisers")
-    ap.add_argument("--fused", default=None, choices=["off", "generic", "band", "band-zero", "auto"],
+    ap.add_argument("--fused", default=None, choices=["off", "generic", "band", "band-zero", "own", "auto"],
                     help="backward + Adam: separate kernels or one persistent kernel (default: VL3D_FUSED, else auto)")
     args = ap.parse_args()
     global _OUT

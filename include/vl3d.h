@@ -213,6 +213,35 @@ int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads, float* at
                         int32_t n_items, int32_t n_rounds, int32_t* counters, int32_t n_counters,
                         int32_t* ticket, int32_t ctas_per_sm, void* stream);
 
+/* ---- the same pass in "owner" mode (dense layout = VL3D_VIEW_RECT_PLANES, regulariser weights given) -------------------
+ * A texel whose bilinear footprint is met by the pixels of one screen tile only gets its complete gradient inside that
+ * tile: the tile accumulates it in a per-CTA scratch box (L2-resident), runs Adam on it there and never touches
+ * grad_dyn; only texels near tile borders go through grad_dyn and the queue's ADAM items, which skip the owned texels.
+ * Ownership is decided per (plane, texel) from `own`:
+ *   hinv[d]  row-major 3x3: plane-local texel (x - rect[d].x0, y - rect[d].y0, 1) -> (px*w, py*w, w), the continuous pixel
+ *            index of the texel centre in the target view (pixel p's centre = p), w > 0 where visible;
+ *   reach[d] >= the largest distance (L-inf, pixels) between a pixel and the screen position of a texel it taps
+ *            (>= 16 disables ownership on the plane);
+ *   rect[d]  x0, y0, x1, y1 (inclusive): the atlas texels tapped by plane d and by no other plane.
+ * ADAM items carry the plane of their rectangle in the 12th int32 of the item (-1 = no plane: nothing is skipped).
+ * own_table: workspace of vl3d_fused_own_table_bytes(H, W) bytes (per screen tile the planes it owns and where; filled by
+ * a small kernel in front of the pass); scratch: vl3d_fused_own_scratch_bytes(ctas) bytes for `ctas` resident CTAs
+ * (SMs x 3 is always enough), ALL-ZERO on entry and all-zero on exit.  Both 16-byte aligned. */
+typedef struct vl3d_own {
+    float   hinv[VL3D_MAX_PLANES * 9];
+    float   reach[VL3D_MAX_PLANES];
+    int32_t rect[VL3D_MAX_PLANES * 4];
+} vl3d_own;
+int64_t vl3d_fused_own_scratch_bytes(int32_t ctas);
+int64_t vl3d_fused_own_table_bytes(int32_t H, int32_t W);
+int vl3d_fused_bwd_adam_own(const vl3d_view* view, const vl3d_quad* quads, float* atlas_dyn, const float* atlas_sta,
+                            int32_t T, const float* grad_rgb, const float* rgb, const float* w_smooth,
+                            double* smooth_sums, float* grad_dyn, float* grad_sta, float* adam_m, float* adam_v,
+                            int32_t step, float lr, float beta1, float beta2, float eps, const int32_t* items,
+                            int32_t n_items, int32_t n_rounds, int32_t* counters, int32_t n_counters,
+                            int32_t* ticket, int32_t ctas_per_sm, const vl3d_own* own, uint32_t* own_table,
+                            int64_t own_table_bytes, float* scratch, int64_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

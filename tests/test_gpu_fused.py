@@ -74,7 +74,7 @@ def test_fused_gradient_equals_classic_backward(layout, vname, T):
     g_ref = s0._state["atlas_dyn"][0] / 0.1                         # m = (1 - beta1) * g after the first step
     scale = float(g_ref.abs().max())
     assert scale > 0
-    modes = ["generic"] + (["band", "band-zero"] if layout == "dense" else [])
+    modes = ["generic"] + (["band", "band-zero", "own"] if layout == "dense" else [])
     for mode in modes:
         for opts in ({}, dict(row_block=3, zero_ahead=1, adam_lag=0, ctas_per_sm=1)):
             m1, s1, o1 = _run_steps(st, H, W, mode, vname, 1, 0.0, dev, opts)
@@ -89,7 +89,8 @@ def test_fused_gradient_equals_classic_backward(layout, vname, T):
                 assert float(s1._buf["g_dyn"].abs().max()) == 0.0     # re-zeroed by the Adam items
 
 
-@pytest.mark.parametrize("layout,mode", [("dense", "generic"), ("dense", "band"), ("dense", "band-zero"), ("sparse", "generic")])
+@pytest.mark.parametrize("layout,mode", [("dense", "generic"), ("dense", "band"), ("dense", "band-zero"), ("dense", "own"),
+                                         ("sparse", "generic")])
 def test_fused_steps_equal_separate_kernels(layout, mode):
     dev = torch.device("cuda:0")
     H, W, D, T = 64, 96, 8, 6

@@ -25,6 +25,11 @@ class View(C.Structure):
 VIEW_RECT_PLANES = 1
 
 
+class Own(C.Structure):
+    """vl3d_own: per-plane texel -> screen maps for the owner mode of the fused backward + Adam."""
+    _fields_ = [("hinv", C.c_float * (MAX_PLANES * 9)), ("reach", C.c_float * MAX_PLANES), ("rect", C.c_int32 * (MAX_PLANES * 4))]
+
+
 class LossDesc(C.Structure):
     _fields_ = [("t", C.c_int32), ("F", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
                 ("p", C.c_int32), ("pt", C.c_int32), ("s", C.c_int32), ("st", C.c_int32),
@@ -61,13 +66,18 @@ _SIGNATURES = {
     "vl3d_fused_bwd_adam": (C.c_int, [C.POINTER(View), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32,
                                       C.c_float, C.c_float, C.c_float, C.c_float, _P, C.c_int32, C.c_int32, _P, C.c_int32,
                                       _P, C.c_int32, _P]),
+    "vl3d_fused_own_scratch_bytes": (C.c_int64, [C.c_int32]),
+    "vl3d_fused_own_table_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "vl3d_fused_bwd_adam_own": (C.c_int, [C.POINTER(View), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32,
+                                          C.c_float, C.c_float, C.c_float, C.c_float, _P, C.c_int32, C.c_int32, _P, C.c_int32,
+                                          _P, C.c_int32, C.POINTER(Own), _P, C.c_int64, _P, C.c_int64, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 
 _lib = None
 LAUNCHES = 0          # kernels launched through this binding (bench.py's gpu_launches)
 _LAUNCHES_PER_CALL = {"vl3d_composite_fwd": 1, "vl3d_composite_bwd": 1, "vl3d_scale_invariant": 2, "vl3d_frame_sum": 1, "vl3d_scale_invariant_presum": 2, "vl3d_scale_log_sum": 2, "vl3d_scale_finish": 1,
-                      "vl3d_patchnn_search": 1, "vl3d_scale_video": 1, "vl3d_patch_l1": 1, "vl3d_to8b": 1, "vl3d_u8_to_unit": 1, "vl3d_vote_loss": 2, "vl3d_video_loss": 2, "vl3d_adam_step": 1, "vl3d_fused_bwd_adam": 1}
+                      "vl3d_patchnn_search": 1, "vl3d_scale_video": 1, "vl3d_patch_l1": 1, "vl3d_to8b": 1, "vl3d_u8_to_unit": 1, "vl3d_vote_loss": 2, "vl3d_video_loss": 2, "vl3d_adam_step": 1, "vl3d_fused_bwd_adam": 1, "vl3d_fused_bwd_adam_own": 2}
 
 
 class Vl3dError(RuntimeError):

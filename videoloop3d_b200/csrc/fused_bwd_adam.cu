@@ -39,7 +39,8 @@ struct alignas(64) FusedParams {
     int* ticket;           // queue head, zeroed by the caller
     float4* m;
     float4* v;
-    float b1, b2, step_size, inv_sqrt_bc2, eps;
+    AdamK k;
+    OwnParams own;         // owner mode only (see composite_lean.cuh)
 };
 
 __device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
@@ -56,23 +57,63 @@ __device__ __forceinline__ void red_release_gpu_inc(int* p) {
     asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
 }
 
-// same arithmetic, in the same order, as adam_kernel (optim.cu)
-__device__ __forceinline__ void adam4(float4& pp, const float4 gg, float4& mm, float4& vv, const FusedParams& F) {
-#define VL3D_ADAM1(c)                                                       \
-    mm.c = F.b1 * mm.c + (1.f - F.b1) * gg.c;                               \
-    vv.c = F.b2 * vv.c + (1.f - F.b2) * gg.c * gg.c;                        \
-    pp.c -= F.step_size * (mm.c / (sqrtf(vv.c) * F.inv_sqrt_bc2 + F.eps));
-    VL3D_ADAM1(x) VL3D_ADAM1(y) VL3D_ADAM1(z) VL3D_ADAM1(w)
-#undef VL3D_ADAM1
-}
-
 // Adam on rows x width texels starting at texel `base` of frames [t0, t0 + FUSED_TF) (row stride = dyn_w).
 // A CTA's streaming rate is set by the bytes it keeps in flight: every thread loads ADAM_U texels x FUSED_TF frames x
 // (p, m, v, g) = 16 x 16 B before it computes (with 8 loads the fused pass was limited by Adam's per-CTA rate, not by DRAM).
 constexpr int ADAM_U = 2;
 
+// Adam on an explicit list of texels (offsets from `base`, the same for every frame of the chunk): ADAM_U texels x
+// FUSED_TF frames x (p, m, v, g) loads in flight per thread, like the dense loop below.
+__device__ __forceinline__ void adam_list(const FusedParams& F, float4* const P0, float4* const G0, float4* const M0, float4* const V0,
+                                          const size_t frame, const int* list, const int n, const bool has_grad, const bool rezero) {
+    const int tid = threadIdx.y * BX + threadIdx.x;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int NT = BX * BY, NV = ADAM_U * FUSED_TF;
+    for (int q0 = tid; q0 < n; q0 += NT * ADAM_U) {
+        float4 pp[NV], gg[NV], mm[NV], vv[NV];
+        size_t off[NV];
+        bool in[NV];
+#pragma unroll
+        for (int u = 0; u < ADAM_U; ++u) {
+            const int q = q0 + u * NT;
+            const bool todo = q < n;
+            const int o = todo ? list[q] : 0;
+#pragma unroll
+            for (int f = 0; f < FUSED_TF; ++f) {
+                const int k = u * FUSED_TF + f;
+                in[k] = todo;
+                off[k] = (size_t)f * frame + o;
+                pp[k] = mm[k] = vv[k] = gg[k] = zero4;
+                if (todo) {
+                    pp[k] = __ldcs(P0 + off[k]);
+                    mm[k] = __ldcs(M0 + off[k]);
+                    vv[k] = __ldcs(V0 + off[k]);
+                    if (has_grad) gg[k] = __ldcg(G0 + off[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            if (in[k]) {
+                adam4(pp[k], gg[k], mm[k], vv[k], F.k);
+                __stcs(P0 + off[k], pp[k]);
+                __stcs(M0 + off[k], mm[k]);
+                __stcs(V0 + off[k], vv[k]);
+                if (rezero) G0[off[k]] = zero4;
+            }
+        }
+    }
+}
+
+// OWN: `plane` >= 0 says the rectangle lies in that plane's atlas cell; texels a screen tile owns were updated by the tile
+// (bwd_tile's own_flush) and are skipped here.  Only ~1/3 of the texels are left, two or three per tile and atlas row
+// plus whole rows between the tile rows: the CTA first compacts the texels it has to do (OWN_LIST positions at a time,
+// classification only) and then runs Adam over the list with every lane busy.
+constexpr int OWN_LIST = 2048;
+
+template <bool OWN>
 __device__ __forceinline__ void adam_rect(const FusedParams& F, const int t0, const int base, const int width, const int rows,
-                                          const int flags) {
+                                          const int flags, const int plane) {
     const CompositeParams& p = F.R.p;
     const int tid = threadIdx.y * BX + threadIdx.x;
     const size_t frame = (size_t)p.view.dyn_h * p.view.dyn_w;
@@ -85,6 +126,32 @@ __device__ __forceinline__ void adam_rect(const FusedParams& F, const int t0, co
     const bool rezero = has_grad && (flags & FLAG_REZERO);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     constexpr int NT = BX * BY, NV = ADAM_U * FUSED_TF;
+    if (OWN && plane >= 0) {
+        __shared__ int s_list[OWN ? OWN_LIST : 1];
+        __shared__ int s_n;
+        const int y0 = base / stride, x0 = base - y0 * stride;
+        const int n = rows * width;
+        const int lane = tid & 31;
+        for (int b0 = 0; b0 < n; b0 += OWN_LIST) {
+            if (tid == 0) s_n = 0;
+            __syncthreads();
+#pragma unroll 2
+            for (int i = b0 + tid; i < min(b0 + OWN_LIST, n); i += NT) {   // (the trip count is warp-uniform up to the tail)
+                const int r = i / width, c = i - r * width;
+                const bool keep = !own_texel_of_any(F.own, plane, x0 + c, y0 + r);
+                const unsigned act = __activemask();
+                const unsigned m = __ballot_sync(act, keep);
+                int pos = 0;
+                if (lane == __ffs(act) - 1) pos = atomicAdd(&s_n, __popc(m));
+                pos = __shfl_sync(act, pos, __ffs(act) - 1);
+                if (keep) s_list[pos + __popc(m & ((1u << lane) - 1u))] = r * stride + c;
+            }
+            __syncthreads();
+            adam_list(F, P0, G0, M0, V0, frame, s_list, s_n, has_grad, rezero);
+            __syncthreads();
+        }
+        return;
+    }
     for (int r = 0; r < rows; ++r) {
         const size_t ro = (size_t)r * stride;
         for (int c0 = tid; c0 < width; c0 += NT * ADAM_U) {
@@ -109,7 +176,7 @@ __device__ __forceinline__ void adam_rect(const FusedParams& F, const int t0, co
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
                 if (in[k]) {
-                    adam4(pp[k], gg[k], mm[k], vv[k], F);
+                    adam4(pp[k], gg[k], mm[k], vv[k], F.k);
                     __stcs(P0 + off[k], pp[k]);
                     __stcs(M0 + off[k], mm[k]);
                     __stcs(V0 + off[k], vv[k]);
@@ -134,7 +201,28 @@ __device__ __forceinline__ void zero_rect(const FusedParams& F, const int t0, co
         }
 }
 
-template <bool SMOOTH, int MODE>
+// one warp per screen tile (regulariser tiling): zone[tile][plane] = where the tile owns texels of the plane (x = -1: it
+// does not), table[tile] = the planes it owns.  The only place where ownership of a (tile, plane) pair is decided.
+static __global__ void own_table_kernel(const __grid_constant__ FusedParams F, unsigned* __restrict__ table, int2* __restrict__ zone) {
+    const CompositeParams& p = F.R.p;
+    const int gx = F.own.gx, gy = F.own.gy;
+    const int tile = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (tile >= gx * gy) return;
+    const int by = tile / gx, bx = tile - by * gx;
+    int cls = 0;
+    int4 box = make_int4(0, 0, 0, 0);
+    if (lane < p.view.D)
+        cls = tile_plane_class(p, lane, bx * (BX - 1), min(bx * (BX - 1) + BX - 1, p.view.W - 1), by * (BY - 1),
+                               min(by * (BY - 1) + BY - 1, p.view.H - 1), box);
+    const unsigned m_mixed = __ballot_sync(0xffffffffu, cls == 2);
+    int2 z = make_int2(-1, -1);
+    if (lane < p.view.D && m_mixed == 0u) z = tile_own_zone(p, F.own, lane, bx, by, cls, box);
+    zone[(size_t)tile * VL3D_MAX_PLANES + lane] = z;
+    const unsigned m_own = __ballot_sync(0xffffffffu, z.x >= 0);
+    if (lane == 0) table[tile] = m_own;
+}
+
+template <bool SMOOTH, int MODE, bool OWN>
 __global__ void __launch_bounds__(BX* BY, 3) fused_bwd_adam_kernel(const __grid_constant__ FusedParams F) {
     __shared__ int s_item;
     const int tid = threadIdx.y * BX + threadIdx.x;
@@ -170,10 +258,10 @@ __global__ void __launch_bounds__(BX* BY, 3) fused_bwd_adam_kernel(const __grid_
         }
         const int t0 = chunk * FUSED_TF;
         if (type == ITEM_BWD) {
-            bwd_tile<FUSED_TF, SMOOTH, MODE>(F.R, a.y, a.z, t0, kbase, first);
+            bwd_tile<FUSED_TF, SMOOTH, MODE, OWN>(F.R, a.y, a.z, t0, kbase, first, &F.own);
             first = false;
         } else if (type == ITEM_ADAM) {
-            adam_rect(F, t0, a.y, a.z, a.w, flags);
+            adam_rect<OWN>(F, t0, a.y, a.z, a.w, flags, c.w);
         } else {
             zero_rect(F, t0, a.y, a.z, a.w);
         }
@@ -187,10 +275,13 @@ __global__ void __launch_bounds__(BX* BY, 3) fused_bwd_adam_kernel(const __grid_
     }
 }
 
-template <bool SMOOTH, int MODE>
-static int launch_fused(const FusedParams& F, int ctas_per_sm, cudaStream_t st) {
+// bytes of scratch one CTA of the owner-mode kernel needs, and how many CTAs a launch may use (occupancy x SMs)
+static size_t own_scratch_per_cta() { return (size_t)2 * FUSED_TF * OWN_ZN * sizeof(float4); }
+
+template <bool SMOOTH, int MODE, bool OWN>
+static int launch_fused(const FusedParams& F, int ctas_per_sm, cudaStream_t st, size_t scratch_bytes = 0) {
     const size_t smem = MODE >= 2 ? (size_t)BWD_TMA_STAGES * FUSED_TF * TMA_BOX_BYTES : 0;
-    auto kern = fused_bwd_adam_kernel<SMOOTH, MODE>;
+    auto kern = fused_bwd_adam_kernel<SMOOTH, MODE, OWN>;
     if (smem) {
         cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return set_err((int)ce, "fused_bwd_adam: cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
@@ -204,6 +295,14 @@ static int launch_fused(const FusedParams& F, int ctas_per_sm, cudaStream_t st) 
     long long grid = (long long)sms * occ;
     const long long total = (long long)F.n_rounds * F.n_items;
     if (grid > total) grid = total;
+    if (OWN) {
+        if ((size_t)grid * own_scratch_per_cta() > scratch_bytes)
+            return set_err(VL3D_EINVAL, "fused_bwd_adam_own: scratch of %zu bytes is too small for %lld CTAs x %zu bytes", scratch_bytes,
+                           grid, own_scratch_per_cta());
+        const int tiles = F.own.gx * F.own.gy;
+        own_table_kernel<<<(tiles * 32 + 255) / 256, 256, 0, st>>>(F, const_cast<unsigned*>(F.own.table), const_cast<int2*>(F.own.zone));
+        if (int e = check_launch("own_table")) return e;
+    }
     kern<<<(unsigned)grid, dim3(BX, BY), smem, st>>>(F);
     return check_launch("fused_bwd_adam");
 }
@@ -212,12 +311,17 @@ static int launch_fused(const FusedParams& F, int ctas_per_sm, cudaStream_t st) 
 
 using namespace vl3d;
 
-extern "C" int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads, float* atlas_dyn, const float* atlas_sta,
-                                   int32_t T, const float* grad_rgb, const float* rgb, const float* w_smooth,
-                                   double* smooth_sums, float* grad_dyn, float* grad_sta, float* adam_m, float* adam_v,
-                                   int32_t step, float lr, float beta1, float beta2, float eps, const int32_t* items,
-                                   int32_t n_items, int32_t n_rounds, int32_t* counters, int32_t n_counters,
-                                   int32_t* ticket, int32_t ctas_per_sm, void* stream) {
+extern "C" int64_t vl3d_fused_own_table_bytes(int32_t H, int32_t W) {
+    const int64_t tiles = (int64_t)((W + BX - 2) / (BX - 1)) * ((H + BY - 2) / (BY - 1));
+    return 4 * (((tiles + 3) & ~(int64_t)3) + tiles * VL3D_MAX_PLANES * 2);
+}
+
+static int fused_entry(const vl3d_view* view, const vl3d_quad* quads, float* atlas_dyn, const float* atlas_sta, int32_t T,
+                       const float* grad_rgb, const float* rgb, const float* w_smooth, double* smooth_sums, float* grad_dyn,
+                       float* grad_sta, float* adam_m, float* adam_v, int32_t step, float lr, float beta1, float beta2, float eps,
+                       const int32_t* items, int32_t n_items, int32_t n_rounds, int32_t* counters, int32_t n_counters,
+                       int32_t* ticket, int32_t ctas_per_sm, const vl3d_own* own, uint32_t* own_table, int64_t own_table_bytes,
+                       float* scratch, int64_t scratch_bytes, void* stream) {
     if (int e = validate_view(view, quads, atlas_dyn, atlas_sta)) return e;
     VL3D_REQUIRE(grad_rgb && rgb && grad_dyn && adam_m && adam_v && atlas_dyn, VL3D_ENULL, "fused_bwd_adam: NULL pointer");
     VL3D_REQUIRE(grad_sta != nullptr || atlas_sta == nullptr, VL3D_ENULL, "grad_sta is NULL");
@@ -244,13 +348,62 @@ extern "C" int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads
     F.m = reinterpret_cast<float4*>(adam_m); F.v = reinterpret_cast<float4*>(adam_v);
     const double bc1 = 1.0 - pow((double)beta1, (double)step);
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
-    F.b1 = beta1; F.b2 = beta2; F.eps = eps;
-    F.step_size = (float)((double)lr / bc1);
-    F.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    F.k.b1 = beta1; F.k.b2 = beta2; F.k.eps = eps;
+    F.k.step_size = (float)((double)lr / bc1);
+    F.k.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     cudaStream_t st = (cudaStream_t)stream;
     const bool smooth = w_smooth != nullptr;
+    if (own != nullptr) {
+        VL3D_REQUIRE(smooth && (view->flags & VL3D_VIEW_RECT_PLANES), VL3D_EINVAL,
+                     "fused_bwd_adam_own needs the dense layout (VL3D_VIEW_RECT_PLANES) and the regulariser weights");
+        VL3D_REQUIRE(own_table && scratch, VL3D_ENULL, "fused_bwd_adam_own: own_table / scratch is NULL");
+        VL3D_REQUIRE((((uintptr_t)scratch | (uintptr_t)own_table) & 15) == 0, VL3D_EALIGN,
+                     "fused_bwd_adam_own: scratch / own_table must be 16-byte aligned");
+        VL3D_REQUIRE(own_table_bytes >= vl3d_fused_own_table_bytes(view->H, view->W), VL3D_EINVAL,
+                     "fused_bwd_adam_own: own_table of %lld bytes is too small (%lld needed)", (long long)own_table_bytes,
+                     (long long)vl3d_fused_own_table_bytes(view->H, view->W));
+        VL3D_REQUIRE(make_atlas_tmap(&F.R.tmap, p.view, atlas_dyn, T), VL3D_EINVAL, "fused_bwd_adam_own: no tensor map for the atlas");
+        OwnParams& O = F.own;
+        for (int i = 0; i < VL3D_MAX_PLANES * 9; ++i) O.hinv[i] = own->hinv[i];
+        for (int d = 0; d < VL3D_MAX_PLANES; ++d) {
+            O.L[d] = own->reach[d];
+            O.rect[d] = make_int4(own->rect[4 * d], own->rect[4 * d + 1], own->rect[4 * d + 2], own->rect[4 * d + 3]);
+        }
+        O.scratch = reinterpret_cast<float4*>(scratch);
+        O.gx = (view->W + BX - 2) / (BX - 1); O.gy = (view->H + BY - 2) / (BY - 1);
+        O.table = own_table;
+        O.zone = reinterpret_cast<const int2*>(own_table + (((size_t)O.gx * O.gy + 3) & ~(size_t)3));
+        O.m = F.m; O.v = F.v; O.k = F.k;
+        return launch_fused<true, 3, true>(F, ctas_per_sm, st, (size_t)(scratch_bytes < 0 ? 0 : scratch_bytes));
+    }
     if (smooth && (view->flags & VL3D_VIEW_RECT_PLANES) && make_atlas_tmap(&F.R.tmap, p.view, atlas_dyn, T))
-        return launch_fused<true, 3>(F, ctas_per_sm, st);
-    if (smooth) return launch_fused<true, 0>(F, ctas_per_sm, st);
-    return launch_fused<false, 0>(F, ctas_per_sm, st);
+        return launch_fused<true, 3, false>(F, ctas_per_sm, st);
+    if (smooth) return launch_fused<true, 0, false>(F, ctas_per_sm, st);
+    return launch_fused<false, 0, false>(F, ctas_per_sm, st);
+}
+
+extern "C" int vl3d_fused_bwd_adam(const vl3d_view* view, const vl3d_quad* quads, float* atlas_dyn, const float* atlas_sta,
+                                   int32_t T, const float* grad_rgb, const float* rgb, const float* w_smooth,
+                                   double* smooth_sums, float* grad_dyn, float* grad_sta, float* adam_m, float* adam_v,
+                                   int32_t step, float lr, float beta1, float beta2, float eps, const int32_t* items,
+                                   int32_t n_items, int32_t n_rounds, int32_t* counters, int32_t n_counters,
+                                   int32_t* ticket, int32_t ctas_per_sm, void* stream) {
+    return fused_entry(view, quads, atlas_dyn, atlas_sta, T, grad_rgb, rgb, w_smooth, smooth_sums, grad_dyn, grad_sta, adam_m,
+                       adam_v, step, lr, beta1, beta2, eps, items, n_items, n_rounds, counters, n_counters, ticket, ctas_per_sm,
+                       nullptr, nullptr, 0, nullptr, 0, stream);
+}
+
+extern "C" int64_t vl3d_fused_own_scratch_bytes(int32_t ctas) { return (int64_t)ctas * (int64_t)own_scratch_per_cta(); }
+
+extern "C" int vl3d_fused_bwd_adam_own(const vl3d_view* view, const vl3d_quad* quads, float* atlas_dyn, const float* atlas_sta,
+                                       int32_t T, const float* grad_rgb, const float* rgb, const float* w_smooth,
+                                       double* smooth_sums, float* grad_dyn, float* grad_sta, float* adam_m, float* adam_v,
+                                       int32_t step, float lr, float beta1, float beta2, float eps, const int32_t* items,
+                                       int32_t n_items, int32_t n_rounds, int32_t* counters, int32_t n_counters,
+                                       int32_t* ticket, int32_t ctas_per_sm, const vl3d_own* own, uint32_t* own_table,
+                                       int64_t own_table_bytes, float* scratch, int64_t scratch_bytes, void* stream) {
+    VL3D_REQUIRE(own != nullptr, VL3D_ENULL, "fused_bwd_adam_own: own is NULL");
+    return fused_entry(view, quads, atlas_dyn, atlas_sta, T, grad_rgb, rgb, w_smooth, smooth_sums, grad_dyn, grad_sta, adam_m,
+                       adam_v, step, lr, beta1, beta2, eps, items, n_items, n_rounds, counters, n_counters, ticket, ctas_per_sm,
+                       own, own_table, own_table_bytes, scratch, scratch_bytes, stream);
 }

@@ -3,6 +3,7 @@
 // Replaces torch.optim.Adam(betas=(0.9,0.999), eps=6e-8) as configured by MPMeshVid.get_optimizer
 // (MPV.py:200-218); no weight decay, no amsgrad.  Same operation order as torch's single-tensor path:
 //   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// (adam1 in vl3d_common.cuh: MUFU sqrt / reciprocal)
 // Pure streaming kernel: 4 reads + 3 writes of 4 bytes per element, float4-vectorised.
 #include <stdarg.h>
 #include <string.h>
@@ -34,12 +35,10 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
                                                    float b1, float b2, float step_size, float inv_sqrt_bc2, float eps) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
-#define VL3D_ADAM1(c)                                                   \
-    mm.c = b1 * mm.c + (1.f - b1) * gg.c;                               \
-    vv.c = b2 * vv.c + (1.f - b2) * gg.c * gg.c;                        \
-    pp.c -= step_size * (mm.c / (sqrtf(vv.c) * inv_sqrt_bc2 + eps));
-        VL3D_ADAM1(x) VL3D_ADAM1(y) VL3D_ADAM1(z) VL3D_ADAM1(w)
-#undef VL3D_ADAM1
+        adam1(pp.x, gg.x, mm.x, vv.x, b1, b2, step_size, inv_sqrt_bc2, eps);
+        adam1(pp.y, gg.y, mm.y, vv.y, b1, b2, step_size, inv_sqrt_bc2, eps);
+        adam1(pp.z, gg.z, mm.z, vv.z, b1, b2, step_size, inv_sqrt_bc2, eps);
+        adam1(pp.w, gg.w, mm.w, vv.w, b1, b2, step_size, inv_sqrt_bc2, eps);
         p[i] = pp; m[i] = mm; v[i] = vv;
     }
 }
@@ -48,11 +47,9 @@ __global__ void adam_tail_kernel(float* p, const float* g, float* m, float* v, s
                                  float b2, float step_size, float inv_sqrt_bc2, float eps) {
     const size_t i = start + threadIdx.x;
     if (i < n) {
-        const float gg = g[i];
-        const float mm = b1 * m[i] + (1.f - b1) * gg;
-        const float vv = b2 * v[i] + (1.f - b2) * gg * gg;
-        p[i] -= step_size * (mm / (sqrtf(vv) * inv_sqrt_bc2 + eps));
-        m[i] = mm; v[i] = vv;
+        float pp = p[i], mm = m[i], vv = v[i];
+        adam1(pp, g[i], mm, vv, b1, b2, step_size, inv_sqrt_bc2, eps);
+        p[i] = pp; m[i] = mm; v[i] = vv;
     }
 }
 

@@ -305,6 +305,40 @@ def fused_bwd_adam(view, pack, atlas_dyn, atlas_sta, T, grad_rgb, rgb, w_smooth,
               _lib.ptr(state), int(ctas_per_sm), _lib.stream_ptr())
 
 
+def fused_own_scratch(device, ctas=None):
+    """All-zero scratch for `vl3d_fused_bwd_adam_own` (one box pair per resident CTA; the kernel leaves it all-zero)."""
+    if ctas is None:
+        ctas = 3 * torch.cuda.get_device_properties(device).multi_processor_count
+    n = int(_lib.load().vl3d_fused_own_scratch_bytes(int(ctas)))
+    return torch.zeros(n // 4, dtype=torch.float32, device=device)
+
+
+def fused_own_table(device, H, W):
+    """Workspace for the ownership tables of `vl3d_fused_bwd_adam_own` (filled by the call itself)."""
+    return torch.empty(int(_lib.load().vl3d_fused_own_table_bytes(int(H), int(W))) // 4, dtype=torch.int32, device=device)
+
+
+def fused_bwd_adam_own(view, pack, atlas_dyn, atlas_sta, T, grad_rgb, rgb, w_smooth, smooth_sums, grad_dyn, grad_sta, m, v,
+                       step, lr, beta1, beta2, eps, items, n_items, n_rounds, state, n_counters, own, own_table, scratch,
+                       ctas_per_sm=0):
+    """`fused_bwd_adam` in owner mode (dense layout): `own` = `_lib.Own` from `tiles.own_descriptor`, `own_table` = int32
+    workspace with one entry per screen tile, `scratch` from `fused_own_scratch` (ADAM items carry their plane)."""
+    for t in (grad_dyn, m, v):
+        if tuple(t.stride()) != tuple(atlas_dyn.stride()) or t.shape != atlas_dyn.shape:
+            raise _lib.Vl3dError("fused_bwd_adam_own: atlas_dyn, grad_dyn, m, v must share shape and strides")
+    if (items.dtype != torch.int32 or not items.is_contiguous() or items.numel() != 12 * n_items or state.dtype != torch.int32
+            or state.numel() < 16 + n_rounds * n_counters):
+        raise _lib.Vl3dError("fused_bwd_adam_own: bad schedule buffers")
+    if own_table.dtype != torch.int32 or scratch.dtype != torch.float32:
+        raise _lib.Vl3dError("fused_bwd_adam_own: bad own_table / scratch")
+    _lib.call("vl3d_fused_bwd_adam_own", C.byref(view), _lib.ptr(pack.quads), _lib.ptr(atlas_dyn), _lib.ptr(atlas_sta), int(T),
+              _lib.ptr(grad_rgb), _lib.ptr(rgb), _lib.ptr(w_smooth), _lib.ptr(smooth_sums), _lib.ptr(grad_dyn),
+              _lib.ptr(grad_sta), _lib.ptr(m), _lib.ptr(v), int(step), float(lr), float(beta1), float(beta2), float(eps),
+              _lib.ptr(items), int(n_items), int(n_rounds), C.c_void_p(state.data_ptr() + 64), int(n_counters),
+              _lib.ptr(state), int(ctas_per_sm), C.byref(own), _lib.ptr(own_table), int(own_table.numel() * 4), _lib.ptr(scratch),
+              int(scratch.numel() * 4), _lib.stream_ptr())
+
+
 # ------------------------------------------------------------------------------------------------
 # autograd Functions (the reference-compatible path: loss.backward(); optimizer.step())
 # ------------------------------------------------------------------------------------------------

@@ -26,7 +26,7 @@ ITEM_BWD, ITEM_ADAM, ITEM_ZERO = 0, 1, 2
 FLAG_HAS_GRAD, FLAG_REZERO, FLAG_PREV_ROUND = 1, 2, 8
 BX, BY, TF = 32, 8, 2                  # tile shape / frames per chunk of the kernels (composite_common.cuh)
 # item columns (12 int32 = three int4 of the kernel)
-C_TYPE, C_A, C_B, C_C, C_W0, C_WN, C_WT, C_SIG, C_V0, C_VN, C_VT = range(11)
+C_TYPE, C_A, C_B, C_C, C_W0, C_WN, C_WT, C_SIG, C_V0, C_VN, C_VT, C_PLANE = range(12)
 
 
 @dataclass
@@ -57,17 +57,28 @@ def _rows(n, kind, flags=0):
     it[:, C_W0] = -1
     it[:, C_SIG] = -1
     it[:, C_V0] = -1
+    it[:, C_PLANE] = -1
     return it
 
 
-def generic_schedule(H, W, dyn_h, dyn_w, smooth=True, seg_texels=32768, lead_tiles=888):
-    """Any layout.  Counter 0 = finished tiles of the chunk."""
+def generic_schedule(H, W, dyn_h, dyn_w, smooth=True, seg_texels=32768, lead_tiles=888, cells=None):
+    """Any layout.  Counter 0 = finished tiles of the chunk.  `cells` (owner mode, tiles.atlas_cells): the Adam
+    rectangles are cut along the atlas cells and carry their cell's plane, so that the kernel can skip the texels a
+    screen tile owns (and has already updated)."""
     gx, gy, _, _ = tile_grid(H, W, smooth)
     n_tiles = gx * gy
-    rows_per = max(1, seg_texels // max(dyn_w, 1))
-    r0 = np.arange(0, dyn_h, rows_per)
-    adam = _rows(len(r0), ITEM_ADAM, FLAG_HAS_GRAD | FLAG_REZERO | FLAG_PREV_ROUND)
-    adam[:, C_A], adam[:, C_B], adam[:, C_C] = r0 * dyn_w, dyn_w, np.minimum(rows_per, dyn_h - r0)
+    kind = "generic" if cells is None else "own"
+    if cells is None:
+        cells = [(0, 0, dyn_w - 1, dyn_h - 1, -1)]
+    recs = []
+    for (x0, y0, x1, y1, plane) in cells:
+        cw = x1 - x0 + 1
+        rows_per = max(1, seg_texels // max(cw, 1))
+        for r in range(y0, y1 + 1, rows_per):
+            recs.append((r * dyn_w + x0, cw, min(rows_per, y1 + 1 - r), plane))
+    recs = np.asarray(recs, dtype=np.int64).reshape(-1, 4)
+    adam = _rows(len(recs), ITEM_ADAM, FLAG_HAS_GRAD | FLAG_REZERO | FLAG_PREV_ROUND)
+    adam[:, C_A], adam[:, C_B], adam[:, C_C], adam[:, C_PLANE] = recs[:, 0], recs[:, 1], recs[:, 2], recs[:, 3]
     adam[:, C_W0], adam[:, C_WN], adam[:, C_WT] = 0, 1, n_tiles
     tiles = _rows(n_tiles, ITEM_BWD)
     tiles[:, C_A], tiles[:, C_B] = np.tile(np.arange(gx), gy), np.repeat(np.arange(gy), gx)
@@ -77,7 +88,7 @@ def generic_schedule(H, W, dyn_h, dyn_w, smooth=True, seg_texels=32768, lead_til
     pos = lead + (np.arange(len(adam)) + 0.5) * (n_tiles - lead) / max(len(adam), 1)
     order = np.argsort(np.concatenate([np.arange(n_tiles, dtype=np.float64), pos]), kind="stable")
     items = np.concatenate([tiles, adam])[order].astype(np.int32)
-    return Schedule(items=items, counter_init=np.zeros(1, np.int32), extra_round=True, kind="generic",
+    return Schedule(items=items, counter_init=np.zeros(1, np.int32), extra_round=True, kind=kind,
                     stats=dict(tiles=n_tiles, adam=len(adam), zero=0))
 
 

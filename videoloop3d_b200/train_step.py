@@ -18,9 +18,10 @@ from argparse import Namespace
 import numpy as np
 import torch
 
+import ctypes as C
 import os
 
-from . import ops, schedule
+from . import _lib, ops, schedule, tiles
 from ._lib import Vl3dError
 from .loop_loss import Patch3DGPNNDirectLoss, Patch3DGPNNLowMemLoss, _check_dist
 from .mpv import MPMeshVid, pose2extrin_torch
@@ -272,7 +273,7 @@ class FusedLoopStep:
         if self.loss_shard not in ("rows", "frames"):
             raise ValueError(f"loss_shard={self.loss_shard!r}")
         self.fused = (fused or os.environ.get("VL3D_FUSED", "auto")).lower()
-        if self.fused not in ("off", "generic", "band", "band-zero", "auto"):
+        if self.fused not in ("off", "generic", "band", "band-zero", "own", "auto"):
             raise ValueError(f"fused={self.fused!r}")
         self.fused_opts = dict(fused_opts or {})
         for k, cast in (("ctas_per_sm", int), ("row_block", int), ("zero_ahead", int), ("adam_lag", int), ("seg_texels", int)):
@@ -329,6 +330,17 @@ class FusedLoopStep:
             o = self.fused_opts
             if mode == "generic":
                 sched = schedule.generic_schedule(h, w, dyn_hw[0], dyn_hw[1], smooth, seg_texels=o.get("seg_texels", 32768))
+            elif mode == "own":
+                homs = np.ctypeslib.as_array(view.hom).reshape(-1)[:pack.D * 9].reshape(pack.D, 9)
+                hinv, reach, rect, cells = tiles.own_descriptor(pack.table, pack.D, pack.qh, pack.qw, homs, view.cx, view.cy, h, w,
+                                                                dyn_hw, max_reach=o.get("max_reach", 3.0))
+                sched = schedule.generic_schedule(h, w, dyn_hw[0], dyn_hw[1], smooth, seg_texels=o.get("seg_texels", 32768),
+                                                  cells=cells)
+                own = _lib.Own()
+                C.memmove(own.hinv, np.ascontiguousarray(hinv).ctypes.data, hinv.nbytes)
+                C.memmove(own.reach, np.ascontiguousarray(reach).ctypes.data, reach.nbytes)
+                C.memmove(own.rect, np.ascontiguousarray(rect).ctypes.data, rect.nbytes)
+                sched.own = own
             else:
                 homs = np.ctypeslib.as_array(view.hom).reshape(-1)[:pack.D * 9].astype(np.float64)
                 sched = schedule.band_schedule(homs, view.cx, view.cy, h, w, pack.table, pack.D, pack.qh, pack.qw, dyn_hw[0],
@@ -612,7 +624,9 @@ class FusedLoopStep:
         mode = self.fused
         if mode == "auto":
             mode = "band" if pack.rect_planes else "generic"
-        if mode.startswith("band") and not pack.rect_planes:
+        if (mode.startswith("band") or mode == "own") and not pack.rect_planes:
+            mode = "generic"
+        if mode == "own" and w_smooth is None:                      # the owner path rides on the regulariser tiling
             mode = "generic"
         Te = Tl // 2 * 2 if mode != "off" else 0                   # frames handled by the fused kernel (chunks of 2)
         if Te > 0:
@@ -626,10 +640,23 @@ class FusedLoopStep:
             state[:16].zero_()                                      # [0] = queue head
             state[16:].view(n_rounds, sched.n_counters).copy_(sched.dev_init)   # every round's counters
             with self._timed("fused_bwd_adam"):
-                ops.fused_bwd_adam(view, pack, dyn_local[:Te], atlas.data, Te, grad_rgb[t0:t0 + Te], rgb_pad[t0:t0 + Te],
-                                   w_smooth, bwd_sums, g_dyn[:Te], g_sta, st[0][:Te], st[1][:Te], self.t, lr,
-                                   self.betas[0], self.betas[1], self.eps, sched.dev_items, sched.n_items, n_rounds,
-                                   state, sched.n_counters, ctas_per_sm=self.fused_opts.get("ctas_per_sm", 0))
+                if mode == "own":
+                    scratch = self._buf.get("own_scratch")
+                    if scratch is None:
+                        scratch = self._buf["own_scratch"] = ops.fused_own_scratch(dyn_local.device)
+                    table = self._buf.get(("own_table", h, w))
+                    if table is None:
+                        table = self._buf[("own_table", h, w)] = ops.fused_own_table(dyn_local.device, h, w)
+                    ops.fused_bwd_adam_own(view, pack, dyn_local[:Te], atlas.data, Te, grad_rgb[t0:t0 + Te], rgb_pad[t0:t0 + Te],
+                                           w_smooth, bwd_sums, g_dyn[:Te], g_sta, st[0][:Te], st[1][:Te], self.t, lr,
+                                           self.betas[0], self.betas[1], self.eps, sched.dev_items, sched.n_items, n_rounds,
+                                           state, sched.n_counters, sched.own, table, scratch,
+                                           ctas_per_sm=self.fused_opts.get("ctas_per_sm", 0))
+                else:
+                    ops.fused_bwd_adam(view, pack, dyn_local[:Te], atlas.data, Te, grad_rgb[t0:t0 + Te], rgb_pad[t0:t0 + Te],
+                                       w_smooth, bwd_sums, g_dyn[:Te], g_sta, st[0][:Te], st[1][:Te], self.t, lr,
+                                       self.betas[0], self.betas[1], self.eps, sched.dev_items, sched.n_items, n_rounds,
+                                       state, sched.n_counters, ctas_per_sm=self.fused_opts.get("ctas_per_sm", 0))
         if Te < Tl:
             # separate kernels: everything when fused == "off", else the odd last frame
             g_dyn = self._buf.get("g_dyn")
