@@ -2,7 +2,7 @@
 candidates, both alpha modes) plus the odd corners (temporal stride 2, pt = 1, patches that do not overlap,
 the un-fitted direct loss, non-contiguous inputs) — each against the CPU oracle on a small spatial extent.
 Every kernel variant is hit: strip kernel M = 0..3, 16-byte and 4-byte staging, the 4x8-tile strip kernel with
-TMA and with LDGSTS staging, the one-patch-per-CTA fallback (more than 64 query frames)."""
+TMA and with LDGSTS staging, the one-patch-per-CTA fallback (more than 64 query frames), the small-patch kernel."""
 import pytest
 import torch
 
@@ -37,6 +37,16 @@ CASES = [
     ("T96_p15",       98, 110, 23, 27, 15, 3, 4, 1, 1e4, "-2", "lm"),
     ("T96_p3_s2",     98, 100, 11, 15, 3, 3, 2, 1, 1e4, "-2", "lm"),
     ("T48_p3_s2",     50, 66,  21, 27, 3, 3, 2, 1, 1e4, "-2", "lm"),
+    # small-patch kernel (patchnn_diag.cuh: diagonal sums / arg-min in registers): every instantiation, with and without
+    # the column-minimum normaliser, ragged query / candidate blocks, more than one candidate sweep, odd window starts
+    ("diag_p3_s2_a0",   11, 37,  17, 25, 3, 3, 2, 1, 0.0, "-2", "lm"),     # M = 1, one extra row, alpha normaliser
+    ("diag_p3_s3",      9,  20,  18, 24, 3, 3, 3, 1, 1e4, "-2", "lm"),     # M = 1, no extra row
+    ("diag_p4_s4",      14, 23,  20, 28, 4, 3, 4, 1, 0.5, "0", "lm"),      # M = 1, full chunk
+    ("diag_p4_s3",      7,  19,  22, 25, 4, 3, 3, 1, 1e4, "abs", "lm"),    # M = 1, one extra row, full chunk
+    ("diag_p4_s2",      10, 41,  16, 22, 4, 3, 2, 1, 0.0, "-2", "lm"),     # M = 2 (ring in local memory)
+    ("diag_p3_s1",      6,  13,  9,  12, 3, 3, 1, 1, 1e4, "-2", "lm"),     # M = 3
+    ("diag_2sweeps",    6,  300, 11, 13, 3, 3, 2, 1, 0.0, "-2", "lm"),     # 298 candidates: two sweeps of 256
+    ("diag_T96_2sw",    98, 150, 9,  11, 3, 3, 2, 1, 0.0, "-2", "lm"),     # 96 query positions: 24 x 16 threads, two sweeps
 ]
 
 

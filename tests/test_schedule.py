@@ -118,3 +118,79 @@ def test_band_dependencies_cover_exact_footprints():
                     cx = np.clip(np.floor(lx).astype(int) + dx, 0, wd - 1)
                     cy = np.clip(np.floor(ly).astype(int) + dy, 0, hd - 1)
                     assert np.all(first[cy, cx] <= R) and np.all(last[cy, cx] >= R), (R, d)
+
+
+# ------------------------------------------------------------------------------------------------
+# owner mode (tiles.own_descriptor): the host-side facts the kernel's ownership predicate rests on
+# ------------------------------------------------------------------------------------------------
+def _taps_of_pixels(pack, homs_d, cx, cy, H, W, d, D, qh, qw):
+    """float64 restatement of the kernels' tap geometry: per pixel the top-left tap (ix, iy) on plane d, or -1."""
+    t = pack.table.reshape(D, qh, qw)
+    px, py = np.meshgrid(np.arange(W), np.arange(H))
+    u, v = px + 0.5 - cx, py + 0.5 - cy
+    Hm = homs_d.reshape(3, 3)
+    w = Hm[2, 0] * u + Hm[2, 1] * v + Hm[2, 2]
+    ok = w > 1e-12
+    ws = np.where(ok, w, 1.0)
+    gx = (Hm[0, 0] * u + Hm[0, 1] * v + Hm[0, 2]) / ws
+    gy = (Hm[1, 0] * u + Hm[1, 1] * v + Hm[1, 2]) / ws
+    ok &= (gx > 0) & (gx < qw) & (gy > 0) & (gy < qh)
+    qx = np.clip(gx.astype(np.int64), 0, qw - 1)
+    qy = np.clip(gy.astype(np.int64), 0, qh - 1)
+    q = t[d][qy, qx]
+    lx = q["x0i"] + (q["x0f"].astype(np.float64) + (gx - qx) * q["sx"])
+    ly = q["y0i"] + (q["y0f"].astype(np.float64) + (gy - qy) * q["sy"])
+    return np.where(ok, np.floor(lx), -1).astype(np.int64), np.where(ok, np.floor(ly), -1).astype(np.int64), ok
+
+
+@pytest.mark.parametrize("vname", sorted(VIEWS))
+def test_own_descriptor_reach_bound_and_partition(vname):
+    """(1) private rectangles are disjoint, lie inside their cell and the cells partition the atlas; (2) for every pixel
+    and each of its four taps, the screen position of the tapped texel (inverse map of the descriptor) is closer than
+    `reach` to the pixel — the property that makes 'texel centre >= reach inside the tile' imply 'every contributing
+    pixel is inside the tile'; (3) the owner-mode schedule covers every texel exactly once."""
+    from videoloop3d_b200 import tiles
+    H, W, D = 75, 133, 6
+    pack, view, homs, hd, wd = _geometry(H, W, D, vname)
+    qh, qw = pack.qh, pack.qw
+    hinv, reach, rect, cells = tiles.own_descriptor(pack.table, D, qh, qw, homs.reshape(D, 9).astype(np.float32), view.cx, view.cy,
+                                                    H, W, (hd, wd))
+    cover = np.zeros((hd, wd), dtype=np.int32)
+    for (x0, y0, x1, y1, plane) in cells:
+        cover[y0:y1 + 1, x0:x1 + 1] += 1
+        if plane >= 0 and rect[plane, 2] >= rect[plane, 0]:
+            assert x0 <= rect[plane, 0] and rect[plane, 2] <= x1 and y0 <= rect[plane, 1] and rect[plane, 3] <= y1
+    assert cover.min() == 1 and cover.max() == 1
+    planes_in_cells = [c[4] for c in cells if c[4] >= 0]
+    assert len(planes_in_cells) == len(set(planes_in_cells))
+    touched_by = np.zeros((hd, wd), dtype=np.int32)
+    for d in range(D):
+        ix, iy, ok = _taps_of_pixels(pack, homs[d * 9:(d + 1) * 9], view.cx, view.cy, H, W, d, D, qh, qw)
+        if not ok.any():
+            continue
+        mark = np.zeros((hd, wd), dtype=bool)
+        for dx in (0, 1):
+            for dy in (0, 1):
+                tx, ty = np.minimum(ix[ok] + dx, wd - 1), np.minimum(iy[ok] + dy, hd - 1)
+                mark[ty, tx] = True
+                if reach[d] < 16:
+                    # screen position of the tapped texel vs the pixel that taps it
+                    Mi = hinv[d].astype(np.float64).reshape(3, 3)
+                    lxx, lyy = tx - rect[d, 0], ty - rect[d, 1]
+                    wq = Mi[2, 0] * lxx + Mi[2, 1] * lyy + Mi[2, 2]
+                    inside = (tx >= rect[d, 0]) & (tx <= rect[d, 2]) & (ty >= rect[d, 1]) & (ty <= rect[d, 3])
+                    assert np.all(wq[inside] > 0)
+                    qx = (Mi[0, 0] * lxx + Mi[0, 1] * lyy + Mi[0, 2]) / wq
+                    qy = (Mi[1, 0] * lxx + Mi[1, 1] * lyy + Mi[1, 2]) / wq
+                    pxs, pys = np.meshgrid(np.arange(W), np.arange(H))
+                    dist = np.maximum(np.abs(qx - pxs[ok]), np.abs(qy - pys[ok]))
+                    assert float(dist[inside].max(initial=0.0)) < reach[d] - 0.03, (d, float(dist[inside].max()), reach[d])
+        touched_by += mark
+        # texels inside the private rectangle are tapped by this plane only (checked below via touched_by)
+    for d in range(D):
+        if rect[d, 2] >= rect[d, 0]:
+            assert touched_by[rect[d, 1]:rect[d, 3] + 1, rect[d, 0]:rect[d, 2] + 1].max() <= 1
+    s = schedule.generic_schedule(H, W, hd, wd, True, seg_texels=2048, cells=cells)
+    assert s.kind == "own" and schedule.validate(s)
+    gx, gy, _, _ = schedule.tile_grid(H, W, True)
+    _coverage(s, gx, gy, hd, wd)

@@ -501,6 +501,7 @@ static size_t strip_smem_bytes(const vl3d_loss_desc* L, int nta, int ntb, int SL
 }  // namespace vl3d
 
 #include "patchnn_strip8.cuh"
+#include "patchnn_diag.cuh"
 
 namespace vl3d {
 
@@ -979,11 +980,12 @@ __global__ void __launch_bounds__(VMSE_THREADS) video_avg_kernel(const float* __
 }
 
 // tuning knobs (scripts/tune_search.py), read from the environment ONCE per process
-struct Knobs { bool tile8, tma, vote_v1; int sl; };
+struct Knobs { bool tile8, tma, vote_v1, diag; int sl, ntb; };
 static const Knobs& knobs() {
     static const Knobs k = [] {
         auto geti = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
-        return Knobs{geti("VL3D_NN_TILE8", 1) != 0, geti("VL3D_NN_TMA", 1) != 0, geti("VL3D_VOTE_V1", 0) != 0, geti("VL3D_NN_SL", 0)};
+        return Knobs{geti("VL3D_NN_TILE8", 1) != 0, geti("VL3D_NN_TMA", 1) != 0, geti("VL3D_VOTE_V1", 0) != 0, geti("VL3D_NN_DIAG", 1) != 0,
+                     geti("VL3D_NN_SL", 0), geti("VL3D_NN_NTB", 0)};
     }();
     return k;
 }
@@ -1003,6 +1005,39 @@ extern "C" int vl3d_patchnn_search(const vl3d_loss_desc* desc, const float* x, c
     const int tx_used = (desc->n1 - 1) * desc->st + desc->pt;
     const int M = desc->p / desc->s;
     const bool strip_ok = M <= 3 && desc->p <= 32;
+    if (strip_ok && M >= 1 && desc->p <= 4 && desc->pt == 3 && desc->st == 1 && knobs().diag &&
+        ((desc->x_sf | desc->x_sc | desc->x_sr | desc->y_sf | desc->y_sc | desc->y_sr) >= 0)) {
+        // small patches (the other-view loss configuration p = 3, s = 2): diagonal sums and arg-min in registers
+        // (patchnn_diag.cuh); VL3D_NN_DIAG=0: tuning aid
+        const int tail = desc->p;
+        void (*kern)(StripParams) = nullptr;
+        if (M == 1 && tail == 3) kern = patchnn_diag_kernel<3, 1, 3>;
+        else if (M == 1 && tail == 4) kern = patchnn_diag_kernel<3, 1, 4>;
+        else if (M == 2 && tail == 4) kern = patchnn_diag_kernel<3, 2, 4>;
+        else if (M == 3 && tail == 3) kern = patchnn_diag_kernel<3, 3, 3>;
+        StripParams P{};
+        P.d = *desc; P.x = x; P.y = y; P.nn = nn_out; P.groups = 3;
+        P.row0 = row_begin; P.row1 = row_end;
+        P.nta = (desc->n1 + DG_I - 1) / DG_I;
+        P.ntb = (desc->n2 + DG_J - 1) / DG_J;
+        if (P.ntb > 16) P.ntb = 16;                                 // two CTAs of <= 192 threads per SM (measured: 15.2 vs 16.5 ms with 32)
+        if (knobs().ntb >= 1 && knobs().ntb <= 32) P.ntb = min(knobs().ntb, (desc->n2 + DG_J - 1) / DG_J);   // tuning aid
+        if (P.nta * P.ntb > DG_MAXT) P.ntb = DG_MAXT / (P.nta > 0 ? P.nta : 1);
+        const int rows = row_end - row_begin;
+        int SL = knobs().sl >= 2 ? knobs().sl : 24;
+        while (SL > 4 && (long long)desc->wo * ((rows + SL - 1) / SL) < 148 * 3) SL >>= 1;   // small grids: more strips
+        SL = (rows + (rows + SL - 1) / SL - 1) / ((rows + SL - 1) / SL);
+        if (SL > rows) SL = rows;
+        P.SL = SL;
+        const size_t smem = P.ntb >= 1 ? diag_smem_bytes(desc, P.nta, P.ntb, SL) : (size_t)1 << 30;
+        if (kern != nullptr && P.ntb >= 1 && P.nta * P.ntb >= 32 && smem <= 200 * 1024) {
+            cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (ce != cudaSuccess) return set_err((int)ce, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
+            dim3 grid(desc->wo, (rows + SL - 1) / SL);
+            kern<<<grid, P.nta * P.ntb, smem, st>>>(P);
+            return check_launch("patchnn_search(diag)");
+        }
+    }
     if (strip_ok && tx_used <= 2 * NN_CF) {
         // strip kernels: rows shared between vertically overlapping patches
         {   // 4 x 8 register tiles (patchnn_strip8.cuh) for the common shapes, up to 128 query frames (T = 96 of BASELINE
