@@ -234,11 +234,15 @@ class FusedLoopStep:
         "band" / "band-zero": the same kernel walking the screen in row bands so that a band's gradient rows stay
         L2-resident between accumulation and Adam (dense layout only; "-zero": rows are zeroed just ahead of the
         band and dropped after Adam instead of living in HBM as zeros);
-        None: VL3D_FUSED from the environment (read once, here), else "auto" = band for the dense layout, generic
-        otherwise.  (On B200 the band schedules do NOT keep the gradient on chip under the DRAM-saturating Adam traffic
-        — profiles/r02_fused_bwd_adam.md — but with Adam lagging one wave of resident tiles behind they match the
-        generic schedule in steady state and shorten its pipeline fill / drain from one frame chunk to ~1/8 of one,
-        which matters when a rank owns few chunks.)"""
+        "own": the generic queue in owner mode (`vl3d_fused_bwd_adam_own`, dense layout + regulariser): texels met by the
+        pixels of one screen tile only are optimised inside that tile and never cross HBM as gradients — correct and
+        tested, but latency-bound and slower on B200 (profiles/r02_fused_bwd_adam.md);
+        None: VL3D_FUSED from the environment (read once, here), else "auto" = generic, except band for a dense model when
+        this rank owns at most 6 frame chunks of a large image.  (On B200 the band schedules do NOT keep the gradient on
+        chip under the DRAM-saturating Adam traffic — profiles/r02_fused_bwd_adam.md — but with Adam lagging one wave
+        of resident tiles behind they match the generic schedule in steady state at 720p (42.9 vs 43.7 ms) and shorten
+        its pipeline fill / drain from one frame chunk to ~1/8 of one, which matters when a rank owns few chunks; at
+        180x320 / 360x640 the finer dependencies cost more than they save: 4.3 vs 3.2 ms / 12.0 vs 11.4 ms.)"""
         if not model.atlas_dyn.is_cuda:
             raise Vl3dError("FusedLoopStep needs the model on a CUDA device")
         self.model = model
@@ -623,7 +627,7 @@ class FusedLoopStep:
         self.t += 1
         mode = self.fused
         if mode == "auto":
-            mode = "band" if pack.rect_planes else "generic"
+            mode = "band" if (pack.rect_planes and Tl // 2 <= 6 and h * w >= 512 * 512) else "generic"
         if (mode.startswith("band") or mode == "own") and not pack.rect_planes:
             mode = "generic"
         if mode == "own" and w_smooth is None:                      # the owner path rides on the regulariser tiling
