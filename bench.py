@@ -532,7 +532,8 @@ def measure_main(args, world, rank, local, dev, group, barrier, extras):
     H, W = wl["H"], wl["W"]
     res_dev = make_target(wl, dev)
     lr = margs.lrate * 0.01
-    step = FusedLoopStep(model, group=group, global_frames=T, timers=True, fused=args.fused)
+    step = FusedLoopStep(model, group=group, global_frames=T, timers=True, fused=args.fused, exchange=args.exchange,
+                         gather_nn=False)
     ya, yb = step.band_rows(H, cfg)                                    # this rank's rows of the target (N > 1: its loss band)
     res_main = res_dev if (ya, yb) == (0, H) else res_dev[:, :, :, ya:yb].contiguous()
 
@@ -649,6 +650,9 @@ def measure_main(args, world, rank, local, dev, group, barrier, extras):
                        "loss": "gpnn_lm p=11 pt=3 s=4 alpha=0 rou=-2 gain=3.5 + rgb/a smooth 0.2 + scale-invariant",
                        "optimizer": "Adam eps=6e-8 over all texels",
                        "parallelism": f"T-shard x{world} (render / backward / Adam by frames, looping loss by pixel-row bands)",
+                       "exchange": (None if world == 1 else
+                                    ("peer-memory stores (vl3d_copy_boxes into symmetric memory)" if step._peer is not None
+                                     else "NCCL all-to-all")),
                        "l2": "inputs (>= 22 GB of texels per step) far exceed the 126 MB L2; no explicit flush"},
             "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms / args.steps,
@@ -692,7 +696,8 @@ def measure_extras(args, world, rank, dev, group, barrier):
     ext, intr = view_for(wl)
     res = make_target(wl, dev)
     lr = model.args.lrate * 0.01
-    step = FusedLoopStep(model, group=group, global_frames=T, timers=True, fused=args.fused)
+    step = FusedLoopStep(model, group=group, global_frames=T, timers=True, fused=args.fused, exchange=args.exchange,
+                         gather_nn=False)
     H, W = wl["H"], wl["W"]
     ms_s, kms_s, out_s = time_steps(step, lambda: step.step(H, W, ext, intr, res, cfg, lr), 5, 2, barrier)
     pack = model.mesh_pack()
@@ -795,6 +800,8 @@ def main():
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-operators-on-GPU leg")
     ap.add_argument("--quick", action="store_true", help="headline workload only (no sparse / patch180 / sweep / config0 legs)")
     ap.add_argument("--no-smooth", action="store_true", help="tuning aid: drop the smoothness regularisers")
+    ap.add_argument("--exchange", default=None, choices=["p2p", "nccl", "auto"],
+                    help="N > 1: exchanges of the band-sharded loss (default: peer-memory stores when available)")
     ap.add_argument("--fused", default=None, choices=["off", "generic", "band", "band-zero", "own", "auto"],
                     help="backward + Adam: separate kernels or one persistent kernel (default: VL3D_FUSED, else auto)")
     args = ap.parse_args()

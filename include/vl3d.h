@@ -242,6 +242,22 @@ int vl3d_fused_bwd_adam_own(const vl3d_view* view, const vl3d_quad* quads, float
                             int32_t* ticket, int32_t ctas_per_sm, const vl3d_own* own, uint32_t* own_table,
                             int64_t own_table_bytes, float* scratch, int64_t scratch_bytes, void* stream);
 
+/* ---- exchanges of the T-sharded step over peer memory ----------------------------------------------
+ * vl3d_copy_boxes: up to VL3D_MAX_BOXES strided box copies in ONE launch.  A box is (n_frames, n_planes, n_rows, n_cols)
+ * floats with element strides (frame, plane, row) on each side, columns contiguous; dst may be memory of a peer GPU mapped
+ * into this process (NVLink stores).  src2 (optional, same strides as src) is added on the fly (adjoint of the loop pad,
+ * MPV.py:490-492); without it the copy is bit-exact for any 32-bit payload.  `boxes` is HOST memory (copied into the launch). */
+#define VL3D_MAX_BOXES 32
+typedef struct vl3d_box {
+    const float* src;
+    const float* src2;
+    float*       dst;
+    int32_t n_frames, n_planes, n_rows, n_cols;
+    int64_t src_sf, src_sp, src_sr;
+    int64_t dst_sf, dst_sp, dst_sr;
+} vl3d_box;
+int vl3d_copy_boxes(const vl3d_box* boxes, int32_t n_boxes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

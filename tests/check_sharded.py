@@ -54,14 +54,15 @@ def run_case(H, W, D, T, F, rank, world, dev):
     cfg = dict(loss_name="gpnn_lm", loss_gain=3.5, patch_size=5, patcht_size=3, stride=2, stridet=1, alpha=0.0,
                rou="-2", scaling=0.1, dist_fn="mse", macro_block=65, factor=1)
     ok = True
-    for variant in ("replicated", "memory-sharded"):
+    # exchanges through NCCL all-to-alls and through stores into the peers' symmetric-memory buffers (PeerExchange)
+    for variant, exchange in (("replicated", "nccl"), ("memory-sharded", "nccl"), ("replicated", "p2p"), ("memory-sharded", "p2p")):
         m = model_from_tensors(tensors(st), H, W, dev)
         if variant == "replicated":
-            step = FusedLoopStep(m, group=dist.group.WORLD)
+            step = FusedLoopStep(m, group=dist.group.WORLD, exchange=exchange)
         else:
             b = [(T * r) // world for r in range(world + 1)]
             m.atlas_dyn.data = m.atlas_dyn.data[b[rank]:b[rank + 1]].clone(memory_format=torch.preserve_format)
-            step = FusedLoopStep(m, group=dist.group.WORLD, global_frames=T)
+            step = FusedLoopStep(m, group=dist.group.WORLD, global_frames=T, exchange=exchange)
         losses = [step.step(H, W, ext.to(dev), intr.to(dev), res, cfg, lr=0.01)["loss"] for _ in range(3)]
         t0, t1 = step.t0, step.t1
         mine = m.atlas_dyn.data if variant == "memory-sharded" else m.atlas_dyn.data[t0:t1]
@@ -78,7 +79,7 @@ def run_case(H, W, D, T, F, rank, world, dev):
             nn_eq = bool(torch.equal(nn_sh, s1._buf["nn"]))
             good = dp < 2e-5 and ds < 2e-5 and dl < 1e-5 and nn_eq
             ok &= good
-            print(f"[{variant}] T={T} H={H} world={world}: max|d atlas_dyn|={dp:.2e} max|d atlas|={ds:.2e} rel d loss={dl:.2e} "
+            print(f"[{variant}/{exchange}] T={T} H={H} world={world}: max|d atlas_dyn|={dp:.2e} max|d atlas|={ds:.2e} rel d loss={dl:.2e} "
                   f"nn identical={nn_eq} -> {'OK' if good else 'MISMATCH'}", flush=True)
     return ok
 

@@ -39,6 +39,15 @@ class LossDesc(C.Structure):
                 ("use_alpha", C.c_int32), ("alpha", C.c_float)]
 
 
+class Box(C.Structure):
+    """vl3d_box: one strided (frames, planes, rows, cols) copy of vl3d_copy_boxes."""
+    _fields_ = [("src", C.c_void_p), ("src2", C.c_void_p), ("dst", C.c_void_p),
+                ("n_frames", C.c_int32), ("n_planes", C.c_int32), ("n_rows", C.c_int32), ("n_cols", C.c_int32),
+                ("src_sf", C.c_int64), ("src_sp", C.c_int64), ("src_sr", C.c_int64),
+                ("dst_sf", C.c_int64), ("dst_sp", C.c_int64), ("dst_sr", C.c_int64)]
+
+
+MAX_BOXES = 32
 _P = C.c_void_p
 _SIGNATURES = {
     "vl3d_version": (C.c_int, []),
@@ -66,6 +75,7 @@ _SIGNATURES = {
     "vl3d_fused_bwd_adam": (C.c_int, [C.POINTER(View), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32,
                                       C.c_float, C.c_float, C.c_float, C.c_float, _P, C.c_int32, C.c_int32, _P, C.c_int32,
                                       _P, C.c_int32, _P]),
+    "vl3d_copy_boxes": (C.c_int, [C.POINTER(Box), C.c_int32, _P]),
     "vl3d_fused_own_scratch_bytes": (C.c_int64, [C.c_int32]),
     "vl3d_fused_own_table_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "vl3d_fused_bwd_adam_own": (C.c_int, [C.POINTER(View), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32,
@@ -77,7 +87,7 @@ EXPORTS = tuple(_SIGNATURES)
 _lib = None
 LAUNCHES = 0          # kernels launched through this binding (bench.py's gpu_launches)
 _LAUNCHES_PER_CALL = {"vl3d_composite_fwd": 1, "vl3d_composite_bwd": 1, "vl3d_scale_invariant": 2, "vl3d_frame_sum": 1, "vl3d_scale_invariant_presum": 2, "vl3d_scale_log_sum": 2, "vl3d_scale_finish": 1,
-                      "vl3d_patchnn_search": 1, "vl3d_scale_video": 1, "vl3d_patch_l1": 1, "vl3d_to8b": 1, "vl3d_u8_to_unit": 1, "vl3d_vote_loss": 2, "vl3d_video_loss": 2, "vl3d_adam_step": 1, "vl3d_fused_bwd_adam": 1, "vl3d_fused_bwd_adam_own": 2}
+                      "vl3d_patchnn_search": 1, "vl3d_scale_video": 1, "vl3d_patch_l1": 1, "vl3d_to8b": 1, "vl3d_u8_to_unit": 1, "vl3d_vote_loss": 2, "vl3d_video_loss": 2, "vl3d_adam_step": 1, "vl3d_fused_bwd_adam": 1, "vl3d_fused_bwd_adam_own": 2, "vl3d_copy_boxes": 1}
 
 
 class Vl3dError(RuntimeError):

@@ -305,6 +305,28 @@ def fused_bwd_adam(view, pack, atlas_dyn, atlas_sta, T, grad_rgb, rgb, w_smooth,
               _lib.ptr(state), int(ctas_per_sm), _lib.stream_ptr())
 
 
+def copy_boxes(boxes):
+    """One launch of strided 4-D box copies (csrc/exchange.cu).  `boxes`: list of (src, dst, src2) with src / src2 4-D
+    float32 (or int32) tensors whose last dimension is contiguous and dst a tensor of the same shape — possibly a view
+    of a PEER GPU's symmetric-memory buffer (then the copy is a stream of NVLink stores)."""
+    if not boxes:
+        return
+    for k in range(0, len(boxes), _lib.MAX_BOXES):
+        part = boxes[k:k + _lib.MAX_BOXES]
+        arr = (_lib.Box * len(part))()
+        for b, (src, dst, src2) in zip(arr, part):
+            if src.dim() != 4 or tuple(dst.shape) != tuple(src.shape) or src.element_size() != 4 or dst.element_size() != 4:
+                raise _lib.Vl3dError("copy_boxes: src / dst must be 4-D tensors of 32-bit elements with equal shapes")
+            if (src.numel() and (src.stride(3) != 1 or dst.stride(3) != 1)) or (src2 is not None and src2.stride() != src.stride()):
+                raise _lib.Vl3dError("copy_boxes: columns must be contiguous and src2 strided like src")
+            b.src, b.dst = src.data_ptr(), dst.data_ptr()
+            b.src2 = src2.data_ptr() if src2 is not None else None
+            b.n_frames, b.n_planes, b.n_rows, b.n_cols = (int(v) for v in src.shape)
+            b.src_sf, b.src_sp, b.src_sr = (int(v) for v in src.stride()[:3])
+            b.dst_sf, b.dst_sp, b.dst_sr = (int(v) for v in dst.stride()[:3])
+        _lib.call("vl3d_copy_boxes", arr, len(part), _lib.stream_ptr())
+
+
 def fused_own_scratch(device, ctas=None):
     """All-zero scratch for `vl3d_fused_bwd_adam_own` (one box pair per resident CTA; the kernel leaves it all-zero)."""
     if ctas is None:

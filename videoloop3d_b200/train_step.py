@@ -210,6 +210,112 @@ def bands_to_frames(band_grad, frames_grad_out, bounds, bands, rank, group, send
     return send_ws, recv_ws
 
 
+class PeerExchange:
+    """The band-sharded loss's exchanges over NVLink peer memory instead of NCCL all-to-alls.
+
+    Every rank owns one symmetric-memory allocation (torch.distributed._symmetric_memory: the same virtual layout on every
+    rank, each rank's copy mapped into all the others) that holds its row band of the rendered video, the NN index map
+    and the loss gradient of its own frames.  A rank then STORES its rows of its frames directly into the band buffers of
+    the ranks that need them (`vl3d_copy_boxes`: one launch, no staging copies, no collective call), and later its band's
+    gradient rows into the frame owners' gradient buffers; a device-side barrier on the symmetric allocation's signal
+    pads (stream-ordered, no host sync) separates writers from readers.  Buffer reuse across steps is safe with the three
+    barriers of a step: a rank can only write into a peer's band (NN map, gradient) buffer of step k+1 after that peer has
+    passed the barrier that follows its last read of step k's content."""
+
+    def __init__(self, group, device):
+        import torch.distributed as dist
+        self.group, self.device = group, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.key, self.buf, self.hdl = None, None, None
+
+    def layout(self, T, pad, h, w, bands, bounds, nn_shape):
+        """(Re)allocate for this problem shape (collective: shapes are the same on every rank).  Word offsets of the three
+        regions inside the allocation; every region is sized for the largest rank so that the layout is symmetric."""
+        key = (T, pad, h, w, tuple((b["ya"], b["yb"]) for b in bands), tuple(bounds), tuple(nn_shape))
+        if key != self.key:
+            import torch.distributed._symmetric_memory as symm
+            hb_max = max(b["yb"] - b["ya"] for b in bands)
+            tl_max = max(b1 - b0 for b0, b1 in zip(bounds[:-1], bounds[1:]))
+            n_x = (T + pad) * 3 * hb_max * w
+            n_nn = int(np.prod(nn_shape))
+            n_g = tl_max * 3 * h * w
+            al = lambda n: (n + 63) // 64 * 64
+            self.off = (0, al(n_x), al(n_x) + al(n_nn))
+            self.buf = symm.empty(al(n_x) + al(n_nn) + al(n_g), dtype=torch.float32, device=self.device)
+            self.hdl = symm.rendezvous(self.buf, self.group)
+            self.key = key
+            self.bands, self.bounds, self.dims, self.nn_shape = bands, bounds, (T, pad, h, w), tuple(nn_shape)
+        return self
+
+    def _region(self, rank, which, shape):
+        n = int(np.prod(shape))
+        if rank == self.rank:
+            return self.buf[self.off[which]:self.off[which] + n].view(shape)
+        return self.hdl.get_buffer(rank, (n,), torch.float32, self.off[which]).view(shape)
+
+    def x_band(self, rank):
+        T, pad, h, w = self.dims
+        b = self.bands[rank]
+        return self._region(rank, 0, (T + pad, 3, b["yb"] - b["ya"], w))
+
+    def nn(self, rank):
+        return self._region(rank, 1, self.nn_shape).view(torch.int32)
+
+    def grad_frames(self, rank):
+        T, pad, h, w = self.dims
+        return self._region(rank, 2, (self.bounds[rank + 1] - self.bounds[rank], 3, h, w))
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
+
+    def frames_to_bands(self, frames_local):
+        """My frames (Tl,3,h,w) -> every rank's band buffer (frames [t0,t1) and, for t < pad, their looped copies T + t)."""
+        T, pad, h, w = self.dims
+        t0, t1 = self.bounds[self.rank], self.bounds[self.rank + 1]
+        boxes = []
+        for q, b in enumerate(self.bands):
+            dst = self.x_band(q)
+            src = frames_local[:, :, b["ya"]:b["yb"]]
+            boxes.append((src, dst[t0:t1], None))
+            if t0 < pad:
+                n = min(t1, pad) - t0
+                boxes.append((src[:n], dst[T + t0:T + t0 + n], None))
+        ops.copy_boxes(boxes)
+        self.barrier()
+
+    def share_nn(self, rows, everything=True):
+        """My patch rows [rows[rank], rows[rank+1]) of the NN map -> the other ranks' maps: all of them (`everything`: every
+        rank ends up with the whole map), or only the halo rows a rank's vote needs from the ranks above it."""
+        r0, r1 = rows[self.rank], rows[self.rank + 1]
+        mine = self.nn(self.rank)
+        boxes = []
+        for q, b in enumerate(self.bands):
+            if q == self.rank:
+                continue
+            a0, a1 = (r0, r1) if everything else (max(r0, b["pr0"] - b["halo"]), min(r1, b["pr0"]))
+            if a1 > a0:
+                boxes.append((mine[a0:a1].view(torch.float32)[None], self.nn(q)[a0:a1].view(torch.float32)[None], None))
+        ops.copy_boxes(boxes)
+        self.barrier()
+
+    def bands_to_frames(self, g_band):
+        """dL/dx of my band's owned rows, all frames -> the frame owners' gradient buffers (loop-pad adjoint folded in)."""
+        T, pad, h, w = self.dims
+        me = self.bands[self.rank]
+        lo, hi = me["own0"] - me["ya"], me["own1"] - me["ya"]
+        boxes = []
+        for q in range(self.world):
+            b0, b1 = self.bounds[q], self.bounds[q + 1]
+            dst = self.grad_frames(q)[:, :, me["own0"]:me["own1"]]
+            nf = max(0, min(b1, pad) - b0)                           # frames of q that have a looped copy
+            if nf > 0:
+                boxes.append((g_band[b0:b0 + nf, :, lo:hi], dst[:nf], g_band[T + b0:T + b0 + nf, :, lo:hi]))
+            if b1 - b0 > nf:
+                boxes.append((g_band[b0 + nf:b1, :, lo:hi], dst[nf:], None))
+        ops.copy_boxes(boxes)
+        self.barrier()
+
+
 class FusedLoopStep:
     """render + looping loss + backward + Adam for one (view, patch) item, fused and sync-free.
 
@@ -227,7 +333,7 @@ class FusedLoopStep:
     """
 
     def __init__(self, model: MPMeshVid, group=None, betas=(0.9, 0.999), eps=6e-8, global_frames=None, timers=False,
-                 overlap_chunks=1, fused=None, fused_opts=None, loss_shard="rows"):
+                 overlap_chunks=1, fused=None, fused_opts=None, loss_shard="rows", exchange=None, gather_nn=True):
         """`fused`: how backward + Adam of the dynamic atlas run —
         "off": separate kernels (zero-fill, vl3d_composite_bwd, vl3d_adam_step);
         "generic": one persistent kernel, tiles of chunk c interleaved with Adam of chunk c-1 (any layout);
@@ -276,6 +382,15 @@ class FusedLoopStep:
         self.loss_shard = os.environ.get("VL3D_LOSS_SHARD", loss_shard)
         if self.loss_shard not in ("rows", "frames"):
             raise ValueError(f"loss_shard={self.loss_shard!r}")
+        # exchanges of the band-sharded loss: "p2p" = stores into the peers' symmetric-memory buffers (PeerExchange),
+        # "nccl" = all-to-all collectives; None: VL3D_EXCHANGE, else p2p when symmetric memory can be set up.
+        # gather_nn: give every rank the whole NN index map (`_buf["nn"]`); False (p2p only): a rank receives just the halo
+        # patch rows its vote needs from the ranks above it.
+        self.exchange = (exchange or os.environ.get("VL3D_EXCHANGE", "auto")).lower()
+        if self.exchange not in ("p2p", "nccl", "auto"):
+            raise ValueError(f"exchange={self.exchange!r}")
+        self.gather_nn = bool(gather_nn)
+        self._peer = None
         self.fused = (fused or os.environ.get("VL3D_FUSED", "auto")).lower()
         if self.fused not in ("off", "generic", "band", "band-zero", "own", "auto"):
             raise ValueError(f"fused={self.fused!r}")
@@ -396,12 +511,18 @@ class FusedLoopStep:
         else:
             y_band = src if src.is_contiguous() else self._get("y_band", (F_, 3, hb, w), torch.float32).copy_(src)
         # ---- rendered frames -> row bands
-        x_band = self._get("x_band", (T + pad, 3, hb, w), torch.float32)
-        with self._timed("frames_to_bands"):
-            self._buf["a2a_send"] = frames_to_bands(rgb_pad[t0:t1], x_band, self.bounds, bands, self.rank, self.group,
-                                                    self._buf.get("a2a_send"))
-            if pad:
-                x_band[T:T + pad].copy_(x_band[:pad])                # loop pad (MPV.py:490-492)
+        peer = self._peer_exchange(T, pad, h, w, bands, (dg.ho, dg.wo, dg.n1))
+        if peer is not None:
+            x_band = peer.x_band(self.rank)
+            with self._timed("frames_to_bands"):
+                peer.frames_to_bands(rgb_pad[t0:t1])                 # NVLink stores into every rank's band (+ loop pad)
+        else:
+            x_band = self._get("x_band", (T + pad, 3, hb, w), torch.float32)
+            with self._timed("frames_to_bands"):
+                self._buf["a2a_send"] = frames_to_bands(rgb_pad[t0:t1], x_band, self.bounds, bands, self.rank, self.group,
+                                                        self._buf.get("a2a_send"))
+                if pad:
+                    x_band[T:T + pad].copy_(x_band[:pad])            # loop pad (MPV.py:490-492)
         # ---- scale-invariant gain: partial log-sum over the owned rows, one all-reduce of a double
         xscale = None
         own = (me["own0"] - ya, me["own1"] - ya)
@@ -417,16 +538,22 @@ class FusedLoopStep:
                                   dg.alpha if dg.use_alpha else 1e10, fit=lossobj.fit)
         if desc.ho != me["pr1"] - (me["pr0"] - me["halo"]) or desc.wo != dg.wo or desc.n1 != dg.n1:
             raise Vl3dError("band layout does not match the loss descriptor")
-        nn = self._get("nn", (dg.ho, dg.wo, dg.n1), torch.int32)
         rows = [b["pr0"] for b in bands] + [dg.ho]
-        if not rows_equal(rows):
-            nn.zero_()
+        if peer is not None:
+            nn = self._buf["nn"] = peer.nn(self.rank)
+        else:
+            nn = self._get("nn", (dg.ho, dg.wo, dg.n1), torch.int32)
+            if not rows_equal(rows):
+                nn.zero_()
         nn_band = nn[me["pr0"] - me["halo"]:me["pr1"]]
         x_scaled = self._get("xb_scaled", tuple(x_band.shape), torch.float32)
         with self._timed("patchnn_search"):
             ops.patchnn_search(desc, x_band, xscale, y_band, nn_out=nn_band, rows=(me["halo"], desc.ho), scaled_ws=x_scaled)
-        with self._timed("exchange_nn"):
-            exchange_row_bands(nn, rows, self.rank, self.group)
+        with self._timed("exchange_nn"):                            # the vote needs the halo rows of the ranks above
+            if peer is not None:
+                peer.share_nn(rows, everything=self.gather_nn)
+            else:
+                exchange_row_bands(nn, rows, self.rank, self.group)
         # ---- votes, robust loss and its gradient for the owned rows of every frame
         g_band = self._get("g_band", (T + pad, 3, hb, w), torch.float32)
         vote_part = self._get("vote_part_band", (ops._lib.load().vl3d_vote_partials(T + pad, hb, w),), torch.float64)
@@ -438,11 +565,32 @@ class FusedLoopStep:
             sums[4] += lo[0]
         # ---- dL/drgb back to the frame owners (adjoint of the loop pad first)
         with self._timed("bands_to_frames"):
-            if pad:
-                g_band[:pad] += g_band[T:T + pad]
-            self._buf["a2a_send2"], self._buf["a2a_recv2"] = bands_to_frames(
-                g_band, grad_rgb[t0:t1], self.bounds, bands, self.rank, self.group, self._buf.get("a2a_send2"),
-                self._buf.get("a2a_recv2"))
+            if peer is not None:
+                peer.bands_to_frames(g_band)                        # NVLink stores into the frame owners' buffers
+                grad_rgb[t0:t1].copy_(peer.grad_frames(self.rank))
+            else:
+                if pad:
+                    g_band[:pad] += g_band[T:T + pad]
+                self._buf["a2a_send2"], self._buf["a2a_recv2"] = bands_to_frames(
+                    g_band, grad_rgb[t0:t1], self.bounds, bands, self.rank, self.group, self._buf.get("a2a_send2"),
+                    self._buf.get("a2a_recv2"))
+
+    def _peer_exchange(self, T, pad, h, w, bands, nn_shape):
+        """PeerExchange laid out for this problem, or None when the exchanges go through NCCL."""
+        if self.exchange == "nccl":
+            return None
+        if self._peer is None:
+            try:
+                self._peer = PeerExchange(self.group, self.model.atlas_dyn.device)
+                self._peer.layout(T, pad, h, w, bands, self.bounds, nn_shape)
+            except Exception as e:                                  # no symmetric memory on this system / build
+                if self.exchange == "p2p":
+                    raise
+                import warnings
+                warnings.warn(f"peer-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL all-to-alls")
+                self.exchange, self._peer = "nccl", None
+                return None
+        return self._peer.layout(T, pad, h, w, bands, self.bounds, nn_shape)
 
     def _adam(self, name, p, g, lr):
         st = self._state.get(name)
