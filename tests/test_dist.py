@@ -150,6 +150,78 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world,T,pad,h,p,s", [(2, 7, 2, 46, 5, 2), (3, 8, 2, 43, 11, 4), (4, 6, 0, 30, 3, 2)])
+def test_peer_exchange_box_lists_single_process(world, T, pad, h, p, s, monkeypatch):
+    """PeerExchange (the NVLink peer-memory exchanges) with every rank simulated in ONE process on the CPU: the symmetric
+    buffers are plain tensors, `vl3d_copy_boxes` is replaced by the torch copy it stands for.  After frames_to_bands every
+    rank's band buffer holds its rows of cat(video, video[:pad]); after bands_to_frames every rank's gradient buffer holds,
+    for its frames, the owned rows of every band with the loop-pad adjoint folded in; share_nn delivers whole maps or just
+    the halo rows."""
+    from videoloop3d_b200 import ops, train_step
+    from videoloop3d_b200.train_step import PeerExchange, partition
+    w = 12
+    ho = (h - p) // s + 1
+    bands = band_layout(h, p, s, ho, world)
+    bounds = partition(T, world)
+    nn_shape = (ho, 5, 3)
+    store = {}
+
+    class FakePeer(PeerExchange):
+        def __init__(self, rank):
+            self.rank, self.world = rank, world
+            self.key = None
+
+        def layout(self, *a):
+            self.bands, self.bounds, self.dims, self.nn_shape = bands, bounds, (T, pad, h, w), nn_shape
+            return self
+
+        def _region(self, rank, which, shape):
+            key = (rank, which)
+            if key not in store:
+                store[key] = torch.zeros(int(torch.tensor(shape).prod()), dtype=torch.float32)
+            return store[key].view(shape)
+
+        def barrier(self):
+            pass
+
+    def copy_boxes(boxes):
+        for src, dst, src2 in boxes:
+            dst.copy_(src if src2 is None else src + src2)
+    monkeypatch.setattr(ops, "copy_boxes", copy_boxes)
+    g = torch.Generator().manual_seed(5)
+    video = torch.rand(T, 3, h, w, generator=g)
+    peers = [FakePeer(r).layout() for r in range(world)]
+    for r, pe in enumerate(peers):
+        pe.frames_to_bands(video[bounds[r]:bounds[r + 1]])
+    padded = torch.cat([video, video[:pad]])
+    for r, b in enumerate(bands):
+        assert torch.equal(peers[r].x_band(r), padded[:, :, b["ya"]:b["yb"]])
+    # gradient: every rank produces dL/dx for its band (only owned rows matter)
+    gfull = torch.rand(T + pad, 3, h, w, generator=g)
+    for r, (pe, b) in enumerate(zip(peers, bands)):
+        pe.bands_to_frames(gfull[:, :, b["ya"]:b["yb"]].contiguous())
+    want = gfull[:T].clone()
+    want[:pad] += gfull[T:T + pad]
+    for r in range(world):
+        assert torch.allclose(peers[r].grad_frames(r), want[bounds[r]:bounds[r + 1]])
+    # NN maps
+    rows = [b["pr0"] for b in bands] + [ho]
+    truth = torch.randint(0, 1000, nn_shape, generator=g, dtype=torch.int32)
+    for everything in (True, False):
+        for key in [k for k in store if k[1] == 1]:
+            store[key].zero_()
+        for r, pe in enumerate(peers):
+            pe.nn(r)[rows[r]:rows[r + 1]] = truth[rows[r]:rows[r + 1]]
+        for pe in peers:
+            pe.share_nn(rows, everything=everything)
+        for r, b in enumerate(bands):
+            got = peers[r].nn(r)
+            if everything:
+                assert torch.equal(got, truth)
+            else:
+                assert torch.equal(got[b["pr0"] - b["halo"]:b["pr1"]], truth[b["pr0"] - b["halo"]:b["pr1"]])
+
+
 def test_collective_pattern_gloo_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
