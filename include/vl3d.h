@@ -258,6 +258,15 @@ typedef struct vl3d_box {
 } vl3d_box;
 int vl3d_copy_boxes(const vl3d_box* boxes, int32_t n_boxes, void* stream);
 
+/* ---- optional placement helper ------------------------------------------------------------------------------------------
+ * Device memory with the GENERIC compression attribute (CUDA virtual memory management), for buffers that are mostly
+ * zeros when they cross HBM (grad_dyn of vl3d_fused_bwd_adam: written back as zeros by the Adam items, fetched again by
+ * the first RED).  Results never depend on it.  Fails with VL3D_EINVAL when the device / driver does not support it.
+ * bytes_out: the mapped size (rounded up to the allocation granularity); compressed_out: 1 if the driver granted the
+ * attribute.  The only state the library keeps besides the last error: the handles needed by vl3d_free_compressible. */
+int vl3d_alloc_compressible(int64_t bytes, void** ptr_out, int64_t* bytes_out, int32_t* compressed_out);
+int vl3d_free_compressible(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,3 +146,29 @@ def test_fused_step_matches_oracle_step():
     bad = (upd[big] - upd_ref[big]).abs() > 1e-3 * lr
     assert float(bad.float().mean()) < 1e-3, float(bad.float().mean())
     assert float((upd - upd_ref).abs().mean()) <= 1e-2 * lr
+
+
+def test_compressible_gradient_buffer_is_a_placement_hint(monkeypatch):
+    """ops.compressible_zeros_like: same shape / strides / zeros as zeros_like (or None where the device does not offer
+    compressible memory), and a step gives bit-identical parameters with and without it."""
+    from videoloop3d_b200 import ops
+    dev = torch.device("cuda:0")
+    ref = torch.empty((3, 4, 17, 23), device=dev).contiguous(memory_format=torch.channels_last)
+    t, granted = ops.compressible_zeros_like(ref)
+    if t is not None:
+        assert t.shape == ref.shape and t.stride() == ref.stride() and t.device == ref.device
+        assert float(t.abs().max()) == 0.0
+        t[1, 2, 3, 4] = 5.0
+        assert float(t.sum()) == 5.0
+        del t
+    H, W, D, T = 64, 96, 8, 4
+    st = _dense(H, W, D, T, seed=3)
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("VL3D_GRAD_COMPRESS", flag)
+        m, s_, o = _run_steps(st, H, W, "generic", "near_identity", 2, 0.01, dev)
+        outs[flag] = (m.atlas_dyn.data.clone(), float(o[-1]["loss"]), s_.grad_compressed)
+    assert outs["0"][2] is False
+    assert abs(outs["1"][1] - outs["0"][1]) <= 1e-6 * abs(outs["0"][1])
+    d = (outs["1"][0] - outs["0"][0]).abs()
+    assert float((d > 1e-5).float().mean()) < 2e-4 and float(d.median()) < 1e-7    # (RED order is not deterministic)

@@ -76,6 +76,8 @@ _SIGNATURES = {
                                       C.c_float, C.c_float, C.c_float, C.c_float, _P, C.c_int32, C.c_int32, _P, C.c_int32,
                                       _P, C.c_int32, _P]),
     "vl3d_copy_boxes": (C.c_int, [C.POINTER(Box), C.c_int32, _P]),
+    "vl3d_alloc_compressible": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "vl3d_free_compressible": (C.c_int, [_P]),
     "vl3d_fused_own_scratch_bytes": (C.c_int64, [C.c_int32]),
     "vl3d_fused_own_table_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "vl3d_fused_bwd_adam_own": (C.c_int, [C.POINTER(View), _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32,

@@ -305,6 +305,40 @@ def fused_bwd_adam(view, pack, atlas_dyn, atlas_sta, T, grad_rgb, rgb, w_smooth,
               _lib.ptr(state), int(ctas_per_sm), _lib.stream_ptr())
 
 
+class _CompressibleBlock:
+    """A vl3d_alloc_compressible allocation exposed through __cuda_array_interface__ (freed with the last tensor view)."""
+
+    def __init__(self, n_floats, device):
+        ptr, size, comp = C.c_void_p(), C.c_int64(), C.c_int32()
+        with torch.cuda.device(device):
+            _lib.call("vl3d_alloc_compressible", int(n_floats) * 4, C.byref(ptr), C.byref(size), C.byref(comp))
+        self.ptr, self.bytes, self.compressed, self.device = ptr.value, size.value, bool(comp.value), device
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (self.ptr, False), "version": 3,
+                                         "strides": None}
+
+    def __del__(self):
+        try:
+            _lib.load().vl3d_free_compressible(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+def compressible_zeros_like(ref):
+    """All-zero float32 tensor with `ref`'s shape and strides in compressible device memory (include/vl3d.h: placement
+    helper), or None when the device / driver does not offer it.  Returns (tensor, granted)."""
+    try:
+        n = max(1 + sum((s - 1) * st for s, st in zip(ref.shape, ref.stride())), 1) if ref.numel() else 1
+        blk = _CompressibleBlock(n, ref.device)
+    except _lib.Vl3dError:
+        return None, False
+    with torch.cuda.device(ref.device):
+        flat = torch.as_tensor(blk, device=ref.device)
+        flat.zero_()
+        t = flat.as_strided(tuple(ref.shape), tuple(ref.stride()))
+    t._vl3d_block = blk                                            # keep the allocation alive with the view
+    return t, blk.compressed
+
+
 def copy_boxes(boxes):
     """One launch of strided 4-D box copies (csrc/exchange.cu).  `boxes`: list of (src, dst, src2) with src / src2 4-D
     float32 (or int32) tensors whose last dimension is contiguous and dst a tensor of the same shape — possibly a view
