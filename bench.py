@@ -164,8 +164,13 @@ class ClockSampler:
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu capture of this
 # same workload (source file named in the line); None where nothing was captured.  A bench run cannot read DRAM
 # counters itself, so this is the capture's value, not a measurement of the run that prints it.
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the named ncu capture of this very
+# command (a capture cannot run inside the timed bench); keyed by what the run actually used.
 NCU_TRAFFIC_BYTES = {
-    ("step720p", 1, "fused_bwd_adam"): (139.9e9 + 112.9e9, "profiles/r02_fused_bwd_adam.md (run r02g, generic schedule)"),
+    ("step720p", 1, "fused_bwd_adam"): (121.506735e9 + 96.185975e9,
+                                        "profiles/r03h_fused_720p_compress1.csv (generic schedule, compressible gradient buffer)"),
+    ("step720p", 1, "fused_bwd_adam", "plain"): (139.307588e9 + 112.821573e9,
+                                                 "profiles/r03h_fused_720p_compress0.csv (generic schedule, plain gradient buffer)"),
     ("step720p", 1, "composite_bwd"): (42.817052e9 + 20.455665e9, "profiles/r01c_ncu_full_step720p.md"),
     ("step720p", 1, "composite_fwd"): (21.071395e9 + 0.553144e9, "profiles/r01c_ncu_full_step720p.md"),
 }
@@ -641,6 +646,10 @@ def measure_main(args, world, rank, local, dev, group, barrier, extras):
             f_ach = fused_b / (kernel_ms["fused_bwd_adam"] * 1e-3) / 1e9
             comp.update({"fused_bwd_adam_GBps": f_ach, "fused_bwd_adam_frac": f_ach / peak,
                          "fused_schedule": step.last_schedule.kind if step.last_schedule is not None else None})
+        traffic_key = (args.workload, world, dom)
+        if dom == "fused_bwd_adam" and not step.grad_compressed:
+            traffic_key += ("plain",)
+        comp["grad_buffer"] = "compressible device memory" if step.grad_compressed else "plain device memory"
         line = {
             "metric": METRIC, "value": 1000.0 / ms_per_step, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -662,8 +671,8 @@ def measure_main(args, world, rank, local, dev, group, barrier, extras):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, world, dom), (None, None))[0],
-                         "traffic_source": NCU_TRAFFIC_BYTES.get((args.workload, world, dom), (None, None))[1], "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes),
+                         "traffic": NCU_TRAFFIC_BYTES.get(traffic_key, (None, None))[0],
+                         "traffic_source": NCU_TRAFFIC_BYTES.get(traffic_key, (None, None))[1], "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes),
                          "ms_per_launch": kernel_ms[dom]},
             "kernels_ms": {k: round(v, 4) for k, v in kernel_ms.items()},
             "composite": comp,
