@@ -58,9 +58,14 @@ __device__ __forceinline__ void red_release_gpu_inc(int* p) {
 }
 
 // Adam on rows x width texels starting at texel `base` of frames [t0, t0 + FUSED_TF) (row stride = dyn_w).
-// A CTA's streaming rate is set by the bytes it keeps in flight: every thread loads ADAM_U texels x FUSED_TF frames x
-// (p, m, v, g) = 16 x 16 B before it computes (with 8 loads the fused pass was limited by Adam's per-CTA rate, not by DRAM).
-constexpr int ADAM_U = 2;
+// Every thread loads ADAM_U texels x FUSED_TF frames x (p, m, v, g) before it computes.  While the pass was pinned at the
+// DRAM limit (plain gradient buffer, 253 GB) 16 loads in flight per thread beat 8; with the compressible gradient
+// buffer (218 GB, DRAM at 65 %) the lighter items win: 40.9 vs 41.9 ms at 720p, 3.04 vs 3.13 ms at 180x320 (-DVL3D_ADAM_U=2
+// builds the other variant).
+#ifndef VL3D_ADAM_U
+#define VL3D_ADAM_U 1
+#endif
+constexpr int ADAM_U = VL3D_ADAM_U;
 
 // Adam on an explicit list of texels (offsets from `base`, the same for every frame of the chunk): ADAM_U texels x
 // FUSED_TF frames x (p, m, v, g) loads in flight per thread, like the dense loop below.
