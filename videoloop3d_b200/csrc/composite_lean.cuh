@@ -531,14 +531,19 @@ __device__ __forceinline__ void own_flush(const CompositeParams& p, const OwnPar
 // MODE 0: per-thread loads for every tile.  MODE 3 (VL3D_VIEW_RECT_PLANES): each tile decides at run time — if
 // all its pixels hit the same planes (slot k == k-th plane for every pixel, so the planes can be walked in
 // lockstep) it stages each plane's atlas footprint with TMA exactly like composite_render_tma_kernel: thread 0
-// issues the box of plane k+2 right after the exchange barrier of slot k, which is also what frees that stage;
+// issues the box of plane k+NST-1 right after the exchange barrier of slot k, which is also what frees that stage;
 // the remaining (image-border) tiles use the per-thread loads.
 //
 // bwd_tile = one (screen tile, chunk of TF frames) of the backward, as a device function: composite_bwd_kernel runs
 // it once per CTA, the persistent fused backward + Adam kernel (fused_bwd_adam.cu) once per work item.  `kbase`
 // counts the TMA stage uses of this CTA so far (the mbarrier phases carry over from tile to tile); `first` = the
 // CTA's first tile (initialises the mbarriers).  Callers separate two tiles by a __syncthreads().
-constexpr int BWD_TMA_STAGES = 3;
+// stages of the box ring (boxes in flight = stages - 1).  Two are enough and leave 15 KB per CTA to L1: fused pass
+// 40.1 vs 40.7 ms at 720p, 2.96 vs 3.04 ms at 180x320, standalone backward unchanged (18.6 ms).
+#ifndef VL3D_BWD_STAGES
+#define VL3D_BWD_STAGES 2
+#endif
+constexpr int BWD_TMA_STAGES = VL3D_BWD_STAGES;
 
 template <int TF, bool SMOOTH, int MODE, bool OWN = false>
 __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx, const int by, const int t0, unsigned& kbase,
@@ -677,8 +682,9 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
         ++k_issue;
     };
     if (use_tma && tx == 0 && ty == 0) {
-        if (nplanes > 0) issue_plane();
-        if (nplanes > 1) issue_plane();
+#pragma unroll
+        for (int i = 0; i < NST - 1; ++i)
+            if (nplanes > i) issue_plane();
     }
     for (int k = 0;; ++k) {
         Geo tp;
@@ -769,7 +775,7 @@ __device__ __forceinline__ void bwd_tile(const TmaRenderParams& P, const int bx,
             for (int f = 0; f < TF; ++f) ex[f * (BX * BY) + o_c] = val[f];
             if (MODE >= 2 && use_tma) {
                 __syncthreads();                                    // also: everybody is done with the stage of slot k-1
-                if (tx == 0 && ty == 0 && k + 2 < nplanes) issue_plane();
+                if (tx == 0 && ty == 0 && k + NST - 1 < nplanes) issue_plane();
             } else if (!__syncthreads_or(has)) break;              // (block-uniform)
 #pragma unroll
             for (int f = 0; f < TF; ++f) {
