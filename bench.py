@@ -167,8 +167,8 @@ class ClockSampler:
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the named ncu capture of this very
 # command (a capture cannot run inside the timed bench); keyed by what the run actually used.
 NCU_TRAFFIC_BYTES = {
-    ("step720p", 1, "fused_bwd_adam"): (121.506735e9 + 96.185975e9,
-                                        "profiles/r03h_fused_720p_compress1.csv (generic schedule, compressible gradient buffer)"),
+    ("step720p", 1, "fused_bwd_adam"): (117.592024e9 + 94.954704e9,
+                                        "profiles/r03p_fused_720p_metrics.csv (generic schedule, compressible gradient buffer)"),
     ("step720p", 1, "fused_bwd_adam", "plain"): (139.307588e9 + 112.821573e9,
                                                  "profiles/r03h_fused_720p_compress0.csv (generic schedule, plain gradient buffer)"),
     ("step720p", 1, "composite_bwd"): (42.817052e9 + 20.455665e9, "profiles/r01c_ncu_full_step720p.md"),

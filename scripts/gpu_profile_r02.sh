@@ -1,7 +1,7 @@
 #!/bin/bash
-# gpurun --timeout 1500 -- 'bash scripts/gpu_profile_r02.sh r02p'
+# gpurun --timeout 1500 -- 'bash scripts/gpu_profile_r02.sh r03p'
 # Evidence kept under profiles/: launch list of the default bench command, full-set captures of the hot kernels.
-tag=${1:-r02p}
+tag=${1:-r03p}
 out=gpurun_out
 mkdir -p $out
 python -c "from videoloop3d_b200 import build; import sys; sys.exit(1 if build.needs_build() else 0)" || { echo "libvl3d.so is stale"; exit 9; }
