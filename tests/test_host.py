@@ -386,3 +386,31 @@ def test_constructor_state_equals_reference_state():
     for k in ("self.is_sparse", "self.atlas_full_w", "self.atlas_full_h", "self.atlas_grid_h", "self.atlas_grid_w", "self.has_dyn",
               "self.atlas_full_dyn_w", "self.atlas_full_dyn_h", "self.atlas_grid_dyn_h", "self.atlas_grid_dyn_w"):
         assert k in sd
+
+
+def test_argument_validation_of_the_round2_entry_points():
+    """vl3d_copy_boxes / vl3d_fused_bwd_adam_own / the sizing helpers reject bad arguments before touching the device."""
+    lib = _lib.load()
+    p16 = ctypes.c_void_p(16)
+    assert _lib.call("vl3d_copy_boxes", None, 0, None) == 0                     # nothing to do
+    with pytest.raises(_lib.Vl3dError, match="boxes"):
+        _lib.call("vl3d_copy_boxes", None, _lib.MAX_BOXES + 1, None)
+    with pytest.raises(_lib.Vl3dError, match="NULL"):
+        _lib.call("vl3d_copy_boxes", None, 2, None)
+    arr = (_lib.Box * 1)()
+    arr[0].n_frames, arr[0].n_planes, arr[0].n_rows, arr[0].n_cols = 1, 1, 2, 4
+    with pytest.raises(_lib.Vl3dError, match="NULL pointer"):
+        _lib.call("vl3d_copy_boxes", arr, 1, None)                              # a non-empty box without pointers
+    arr[0].n_rows = 0
+    assert _lib.call("vl3d_copy_boxes", arr, 1, None) == 0                      # an empty box is skipped
+    # sizing helpers: per-CTA scratch is two (36 x 7)-texel grids x 2 frames; the table holds a mask + 32 zones per tile
+    assert lib.vl3d_fused_own_scratch_bytes(3) == 3 * 2 * 2 * 36 * 7 * 16
+    tiles = ((1280 + 30) // 31) * ((720 + 6) // 7)
+    assert lib.vl3d_fused_own_table_bytes(720, 1280) == 4 * (((tiles + 3) // 4) * 4 + tiles * 64)
+    with pytest.raises(_lib.Vl3dError, match="own is NULL"):
+        _lib.call("vl3d_fused_bwd_adam_own", None, p16, p16, None, 4, p16, p16, p16, None, p16, None, p16, p16, 1, 0.01, 0.9,
+                  0.999, 6e-8, p16, 1, 2, p16, 1, p16, 0, None, p16, 0, p16, 0, None)
+    ptr, size, comp = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int32()
+    with pytest.raises(_lib.Vl3dError, match="bad arguments"):
+        _lib.call("vl3d_alloc_compressible", 0, ctypes.byref(ptr), ctypes.byref(size), ctypes.byref(comp))
+    assert lib.vl3d_free_compressible(None) == 0

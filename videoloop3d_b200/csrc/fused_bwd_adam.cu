@@ -58,17 +58,17 @@ __device__ __forceinline__ void red_release_gpu_inc(int* p) {
 }
 
 // Adam on rows x width texels starting at texel `base` of frames [t0, t0 + FUSED_TF) (row stride = dyn_w).
-// Every thread loads ADAM_U texels x FUSED_TF frames x (p, m, v, g) before it computes.  While the pass was pinned at the
-// DRAM limit (plain gradient buffer, 253 GB) 16 loads in flight per thread beat 8; with the compressible gradient
-// buffer (218 GB, DRAM at 65 %) the lighter items win: 40.9 vs 41.9 ms at 720p, 3.04 vs 3.13 ms at 180x320 (-DVL3D_ADAM_U=2
-// builds the other variant).
-#ifndef VL3D_ADAM_U
-#define VL3D_ADAM_U 1
-#endif
-constexpr int ADAM_U = VL3D_ADAM_U;
+// Every thread loads ADAM_U texels x FUSED_TF frames x (p, m, v, g) before it computes.  Where the Adam items set the pace
+// (tile-culled models: few samples per tile; or the dense layout while it was pinned at the DRAM limit with the plain
+// gradient buffer) 16 loads in flight per thread beat 8: 17.8 vs 18.6 ms for the sparse bench model.  For the dense
+// layout with the compressible gradient buffer (212 GB, DRAM at 65 %) the lighter items win: 40.9 vs 41.9 ms at 720p,
+// 3.04 vs 3.13 ms at 180x320.
+template <int MODE>
+struct AdamLoads { static constexpr int U = MODE >= 2 ? 1 : 2; };
 
 // Adam on an explicit list of texels (offsets from `base`, the same for every frame of the chunk): ADAM_U texels x
 // FUSED_TF frames x (p, m, v, g) loads in flight per thread, like the dense loop below.
+template <int ADAM_U>
 __device__ __forceinline__ void adam_list(const FusedParams& F, float4* const P0, float4* const G0, float4* const M0, float4* const V0,
                                           const size_t frame, const int* list, const int n, const bool has_grad, const bool rezero) {
     const int tid = threadIdx.y * BX + threadIdx.x;
@@ -116,7 +116,7 @@ __device__ __forceinline__ void adam_list(const FusedParams& F, float4* const P0
 // classification only) and then runs Adam over the list with every lane busy.
 constexpr int OWN_LIST = 2048;
 
-template <bool OWN>
+template <bool OWN, int ADAM_U>
 __device__ __forceinline__ void adam_rect(const FusedParams& F, const int t0, const int base, const int width, const int rows,
                                           const int flags, const int plane) {
     const CompositeParams& p = F.R.p;
@@ -152,7 +152,7 @@ __device__ __forceinline__ void adam_rect(const FusedParams& F, const int t0, co
                 if (keep) s_list[pos + __popc(m & ((1u << lane) - 1u))] = r * stride + c;
             }
             __syncthreads();
-            adam_list(F, P0, G0, M0, V0, frame, s_list, s_n, has_grad, rezero);
+            adam_list<ADAM_U>(F, P0, G0, M0, V0, frame, s_list, s_n, has_grad, rezero);
             __syncthreads();
         }
         return;
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(BX* BY, 3) fused_bwd_adam_kernel(const __grid_
             bwd_tile<FUSED_TF, SMOOTH, MODE, OWN>(F.R, a.y, a.z, t0, kbase, first, &F.own);
             first = false;
         } else if (type == ITEM_ADAM) {
-            adam_rect<OWN>(F, t0, a.y, a.z, a.w, flags, c.w);
+            adam_rect<OWN, AdamLoads<MODE>::U>(F, t0, a.y, a.z, a.w, flags, c.w);
         } else {
             zero_rect(F, t0, a.y, a.z, a.w);
         }
