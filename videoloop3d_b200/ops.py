@@ -333,6 +333,8 @@ def compressible_zeros_like(ref):
         return None, False
     with torch.cuda.device(ref.device):
         flat = torch.as_tensor(blk, device=ref.device)
+        if flat.data_ptr() != blk.ptr:                              # (torch copied instead of wrapping: no point)
+            return None, False
         flat.zero_()
         t = flat.as_strided(tuple(ref.shape), tuple(ref.stride()))
     t._vl3d_block = blk                                            # keep the allocation alive with the view
