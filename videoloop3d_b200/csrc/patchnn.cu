@@ -528,9 +528,12 @@ __device__ __forceinline__ void robust(float r, int kind, float rou, float scale
     if (rou == 2.f) { val = 0.5f * sq; der = q / scale; return; }
     const float b = fabsf(rou - 2.f) + 1e-6f;
     const float dd = rou >= 0.f ? rou + 1e-6f : rou - 1e-6f;
-    const float base = sq / b + 1.f;
-    val = (b / dd) * (powf(base, 0.5f * dd) - 1.f) * (scale * 10.f);
-    der = 10.f * q * powf(base, 0.5f * dd - 1.f);
+    const float base = sq / b + 1.f;                                // >= 1
+    // base^(d/2) through MUFU lg2 / ex2 (relative error ~1e-6; two IEEE powf calls per channel were ~40 % of the vote
+    // kernel's instructions); the derivative's base^(d/2 - 1) is the same power divided by the base
+    const float pw = __powf(base, 0.5f * dd);
+    val = (b / dd) * (pw - 1.f) * (scale * 10.f);
+    der = 10.f * q * __fdividef(pw, base);
 }
 
 constexpr int VOTE_THREADS = 256;
@@ -606,7 +609,9 @@ __global__ void __launch_bounds__(VOTE_THREADS) vote_loss_kernel(const __grid_co
 // handled together: all their NN indices are requested first (predicated loads, nothing is fetched for
 // combinations that do not exist), then all 3*NX*NK target texels, then the sums.  Up to 9 / 27 loads in flight
 // per thread instead of 1 / 3.  The host picks the instantiation from ceil(p/s) and ceil(pt/st).
-template <int NY, int NX, int NK>
+// IDX32: every element offset into y and nn fits 31 bits (the host checks), so the gather addresses are one IMAD.WIDE
+// per load instead of 64-bit multiply / add chains.
+template <int NY, int NX, int NK, bool IDX32>
 __global__ void __launch_bounds__(VOTE_THREADS) vote_loss_batched_kernel(const __grid_constant__ VoteParams P) {
     const vl3d_loss_desc& L = P.d;
     const int tf = P.f0 + blockIdx.x;
@@ -636,6 +641,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) vote_loss_batched_kernel(const _
             for (int jy = 0; jy < NY; ++jy) {
                 const bool vy = iy0 + jy <= iy1;
                 const int* nny = P.nn + (size_t)(iy0 + jy) * nn_row + k0;
+                const int n1i = L.n1, ysf = (int)L.y_sf, ysc = (int)L.y_sc;
                 int fr[NX][NK];
 #pragma unroll
                 for (int jx = 0; jx < NX; ++jx) {
@@ -645,7 +651,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) vote_loss_batched_kernel(const _
                     for (int jk = 0; jk < NK; ++jk) {
                         const bool ok = vx && k0 + jk <= k1;
                         int nnv = 0;
-                        if (ok) nnv = __ldg(nny + (size_t)ix * L.n1 + jk);
+                        if (ok) nnv = IDX32 ? __ldg(nny + (ix * n1i + jk)) : __ldg(nny + (size_t)ix * L.n1 + jk);
                         fr[jx][jk] = ok ? nnv * st + (tf - (k0 + jk) * st) : -1;
                     }
                 }
@@ -656,8 +662,13 @@ __global__ void __launch_bounds__(VOTE_THREADS) vote_loss_batched_kernel(const _
                     for (int jk = 0; jk < NK; ++jk) {
                         a0[jx][jk] = a1[jx][jk] = a2[jx][jk] = 0.f;
                         if (fr[jx][jk] >= 0) {
-                            const float* src = yb + (size_t)fr[jx][jk] * L.y_sf;
-                            a0[jx][jk] = __ldg(src); a1[jx][jk] = __ldg(src + L.y_sc); a2[jx][jk] = __ldg(src + 2 * L.y_sc);
+                            if (IDX32) {
+                                const int o = fr[jx][jk] * ysf;
+                                a0[jx][jk] = __ldg(yb + o); a1[jx][jk] = __ldg(yb + (o + ysc)); a2[jx][jk] = __ldg(yb + (o + 2 * ysc));
+                            } else {
+                                const float* src = yb + (size_t)fr[jx][jk] * L.y_sf;
+                                a0[jx][jk] = __ldg(src); a1[jx][jk] = __ldg(src + L.y_sc); a2[jx][jk] = __ldg(src + 2 * L.y_sc);
+                            }
                         }
                     }
 #pragma unroll
@@ -1217,9 +1228,14 @@ extern "C" int vl3d_vote_loss(const vl3d_loss_desc* desc, const float* x, const 
     const int ms = (desc->p + desc->s - 1) / desc->s, mt = (desc->pt + desc->st - 1) / desc->st;
     const bool vote_v1 = knobs().vote_v1;                             // tuning aid: the one-gather-at-a-time kernel
     const bool batched = !vote_v1;
-    if (batched && ms <= 2 && mt <= 3) vote_loss_batched_kernel<2, 2, 3><<<grid, VOTE_THREADS, 0, st>>>(P);
-    else if (batched && ms <= 3 && mt <= 3) vote_loss_batched_kernel<3, 3, 3><<<grid, VOTE_THREADS, 0, st>>>(P);
-    else if (batched && ms <= 4 && mt <= 3) vote_loss_batched_kernel<4, 4, 3><<<grid, VOTE_THREADS, 0, st>>>(P);   // p = 15, s = 4
+    // 32-bit gather offsets when the target video and the NN map are smaller than 2^31 elements
+    const long long y_span = (long long)desc->F * desc->y_sf + 3 * desc->y_sc;
+    const bool idx32 = y_span < (1LL << 31) && (long long)desc->wo * desc->n1 + desc->n1 < (1LL << 31);
+#define VL3D_VOTE(A, B, C) (idx32 ? vote_loss_batched_kernel<A, B, C, true> : vote_loss_batched_kernel<A, B, C, false>)
+    if (batched && ms <= 2 && mt <= 3) VL3D_VOTE(2, 2, 3)<<<grid, VOTE_THREADS, 0, st>>>(P);
+    else if (batched && ms <= 3 && mt <= 3) VL3D_VOTE(3, 3, 3)<<<grid, VOTE_THREADS, 0, st>>>(P);
+    else if (batched && ms <= 4 && mt <= 3) VL3D_VOTE(4, 4, 3)<<<grid, VOTE_THREADS, 0, st>>>(P);   // p = 15, s = 4
+#undef VL3D_VOTE
     else vote_loss_kernel<<<grid, VOTE_THREADS, 0, st>>>(P);
     if (int e = check_launch("vote_loss")) return e;
     finalize_mean_kernel<<<1, 1024, 0, st>>>(partials, nblocks, denom, loss_out);
