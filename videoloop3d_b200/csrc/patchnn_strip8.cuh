@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __g
         __syncthreads();                                            // previous chunk's readers are done (and the barriers exist)
         if (TMA) { if (tid == 0) stage_tma(c0, 0, it); }
         else stage(c0, 0, 0);
+        int grp = 0, rin = 0;                                       // group of s rows, row inside the group (no division per row)
         for (int row = 0; row < nrows; ++row, ++it) {
             const int buf = TMA ? (int)(it & 1u) : (row & 1);
             if (TMA) {
@@ -149,7 +150,6 @@ __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __g
                 __syncthreads();                                    // row `row` landed; buffer buf^1 is free
                 if (row + 1 < nrows) stage(c0, row + 1, buf ^ 1);   // overlaps the arithmetic below
             }
-            const int grp = row / s, rin = row - grp * s;           // group of s rows, row inside the group
             {
                 unsigned xa_[S8_TI], ya_[S8_TJ];
 #pragma unroll
@@ -299,6 +299,9 @@ __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __g
                         hist[slot][i * S8_TJ + j] = cur[i][j];
                         cur[i][j] = 0.f;
                     }
+                ++grp; rin = 0;
+            } else {
+                ++rin;
             }
         }
         j0 = j1;
