@@ -206,60 +206,114 @@ __global__ void __launch_bounds__(NN_THREADS, 2) patchnn_strip8_kernel(const __g
                     }
                 __syncthreads();
                 // diagonal sums D[il][jl] = sum_dt G[il*st+dt][jl*st+dt] / d, built in registers and written over G
-                constexpr int DMAX = 32;                            // entries per thread per pass
-                // entry id = base + u*nthreads + tid <-> (il, jl) = divmod(id, cj), advanced incrementally: a step of
-                // nthreads entries is (dq rows, dr columns) with one carry (an integer division per entry cost more
-                // than the three shared-memory reads it addresses)
-                const int dq_step = nthreads / cj, dr_step = nthreads - dq_step * cj;   // divmod(nthreads, cj)
-                int il_b = tid / cj, jl_b = tid - il_b * cj;                             // divmod(tid, cj)
-                for (int base = 0; base < L.n1 * cj; base += nthreads * DMAX) {
-                    float dv[DMAX];
-                    int il = il_b, jl = jl_b;
-#pragma unroll
-                    for (int u = 0; u < DMAX; ++u) {
-                        float sum = 0.f;
-                        if (il < L.n1) {
-                            const float* gp = Gs + (il * st) * (CF + 1) + jl * st;
-                            for (int dt = 0; dt < pt; ++dt) sum += gp[dt * (CF + 2)];
-                        }
-                        dv[u] = sum * inv_d;
-                        jl += dr_step; il += dq_step;
-                        if (jl >= cj) { jl -= cj; ++il; }
-                    }
-                    __syncthreads();                                // every G entry of this pass has been read
-                    il = il_b; jl = jl_b;
-#pragma unroll
-                    for (int u = 0; u < DMAX; ++u) {
-                        if (il < L.n1) Gs[il * (CF + 1) + jl] = dv[u];
-                        jl += dr_step; il += dq_step;
-                        if (jl >= cj) { jl -= cj; ++il; }
-                    }
-                    il_b = il; jl_b = jl;
-                    __syncthreads();
-                }
                 float* Ds = Gs;
-                if (L.use_alpha) {
-                    const int PA = min(8, max(1, nthreads / cj)), RA = (L.n1 + PA - 1) / PA;
-                    for (int id = tid; id < cj * PA; id += nthreads) {
-                        const int part = id / cj, jl = id - part * cj;
-                        const int i1 = min((part + 1) * RA, L.n1);
+                constexpr int RU = 16;                              // query rows per work unit
+                const int NU = (L.n1 + RU - 1) / RU, units = NU * cj;
+                if (NU <= 8 && units <= 2 * nthreads) {
+                    // Common shapes (n1 <= 128): a work unit is RU rows of ONE candidate column, a thread takes at most two
+                    // units.  The column minimum over a unit's rows is formed in registers while D is, so the separate
+                    // pass over D for the alpha normaliser (and two CTA barriers) disappear; consecutive threads read
+                    // consecutive columns (conflict-free).
+                    float dv[2 * RU];
+                    int uh[2], uj[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int wu = tid + q * nthreads;
+                        const bool on = wu < units;
+                        const int h = on ? wu / cj : 0, jl = on ? wu - h * cj : 0;
+                        uh[q] = on ? h : -1; uj[q] = jl;
                         float mn = INFINITY;
-                        for (int i = part * RA; i < i1; ++i) {
-                            const float vv = Ds[(size_t)i * (CF + 1) + jl];
-                            mn = (vv < mn || vv != vv) ? vv : mn;
+#pragma unroll
+                        for (int r = 0; r < RU; ++r) {
+                            const int il = h * RU + r;
+                            float sum = 0.f;
+                            if (on && il < L.n1) {
+                                const float* gp = Gs + (il * st) * (CF + 1) + jl * st;
+                                for (int dt = 0; dt < pt; ++dt) sum += gp[dt * (CF + 2)];
+                                sum *= inv_d;
+                                mn = (sum < mn || sum != sum) ? sum : mn;
+                            }
+                            dv[q * RU + r] = sum;
                         }
-                        part_f[part * (CF + 1) + jl] = mn;
+                        if (on && L.use_alpha) part_f[h * (CF + 1) + jl] = mn;
+                    }
+                    __syncthreads();                                // every G entry has been read; the unit minima are written
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        if (uh[q] >= 0) {
+#pragma unroll
+                            for (int r = 0; r < RU; ++r) {
+                                const int il = uh[q] * RU + r;
+                                if (il < L.n1) Ds[il * (CF + 1) + uj[q]] = dv[q * RU + r];
+                            }
+                        }
+                    }
+                    if (L.use_alpha) {
+                        for (int jl = tid; jl < cj; jl += nthreads) {
+                            float mn = INFINITY;
+                            for (int q = 0; q < NU; ++q) {
+                                const float vv = part_f[q * (CF + 1) + jl];
+                                mn = (vv < mn || vv != vv) ? vv : mn;
+                            }
+                            colmin[jl] = L.alpha + mn;
+                        }
                     }
                     __syncthreads();
-                    for (int jl = tid; jl < cj; jl += nthreads) {
-                        float mn = INFINITY;
-                        for (int q = 0; q < PA; ++q) {
-                            const float vv = part_f[q * (CF + 1) + jl];
-                            mn = (vv < mn || vv != vv) ? vv : mn;
+                } else {
+                    constexpr int DMAX = 32;                            // entries per thread per pass
+                    // entry id = base + u*nthreads + tid <-> (il, jl) = divmod(id, cj), advanced incrementally: a step of
+                    // nthreads entries is (dq rows, dr columns) with one carry (an integer division per entry cost more
+                    // than the three shared-memory reads it addresses)
+                    const int dq_step = nthreads / cj, dr_step = nthreads - dq_step * cj;   // divmod(nthreads, cj)
+                    int il_b = tid / cj, jl_b = tid - il_b * cj;                             // divmod(tid, cj)
+                    for (int base = 0; base < L.n1 * cj; base += nthreads * DMAX) {
+                        float dv[DMAX];
+                        int il = il_b, jl = jl_b;
+    #pragma unroll
+                        for (int u = 0; u < DMAX; ++u) {
+                            float sum = 0.f;
+                            if (il < L.n1) {
+                                const float* gp = Gs + (il * st) * (CF + 1) + jl * st;
+                                for (int dt = 0; dt < pt; ++dt) sum += gp[dt * (CF + 2)];
+                            }
+                            dv[u] = sum * inv_d;
+                            jl += dr_step; il += dq_step;
+                            if (jl >= cj) { jl -= cj; ++il; }
                         }
-                        colmin[jl] = L.alpha + mn;
+                        __syncthreads();                                // every G entry of this pass has been read
+                        il = il_b; jl = jl_b;
+    #pragma unroll
+                        for (int u = 0; u < DMAX; ++u) {
+                            if (il < L.n1) Gs[il * (CF + 1) + jl] = dv[u];
+                            jl += dr_step; il += dq_step;
+                            if (jl >= cj) { jl -= cj; ++il; }
+                        }
+                        il_b = il; jl_b = jl;
+                        __syncthreads();
                     }
-                    __syncthreads();
+                    if (L.use_alpha) {
+                        const int PA = min(8, max(1, nthreads / cj)), RA = (L.n1 + PA - 1) / PA;
+                        for (int id = tid; id < cj * PA; id += nthreads) {
+                            const int part = id / cj, jl = id - part * cj;
+                            const int i1 = min((part + 1) * RA, L.n1);
+                            float mn = INFINITY;
+                            for (int i = part * RA; i < i1; ++i) {
+                                const float vv = Ds[(size_t)i * (CF + 1) + jl];
+                                mn = (vv < mn || vv != vv) ? vv : mn;
+                            }
+                            part_f[part * (CF + 1) + jl] = mn;
+                        }
+                        __syncthreads();
+                        for (int jl = tid; jl < cj; jl += nthreads) {
+                            float mn = INFINITY;
+                            for (int q = 0; q < PA; ++q) {
+                                const float vv = part_f[q * (CF + 1) + jl];
+                                mn = (vv < mn || vv != vv) ? vv : mn;
+                            }
+                            colmin[jl] = L.alpha + mn;
+                        }
+                        __syncthreads();
+                    }
                 }
                 {
                     const int PB = min(8, max(1, nthreads / L.n1)), SB = (cj + PB - 1) / PB;
