@@ -116,6 +116,28 @@ int vl3d_composite_bwd(const vl3d_view* view, const vl3d_quad* quads, const floa
                        const float* grad_rgb, const float* rgb, const float* w_smooth,
                        double* smooth_sums, float* grad_dyn, float* grad_sta, void* stream);
 
+/* ---- optional per-ray terms of the composite and their backward (off in every shipped stage-2 config) --------------------
+ * Replaces: MPV.py:454 `alpha = blend_weight.sum(-1)` as a differentiable output (background blend MPV.py:455-461,
+ * density regulariser MPV.py:533-536), MPV.py:384-385,463-464 `disp = (1 / zbuf * blend_weight).sum(-1)` (d_smooth,
+ * MPV.py:538-551), the sparsity regulariser MPV.py:511-515 and autograd's backward through them; the stage-1 model uses
+ * the same terms (MPI.py:552-566,603-607,647-650).
+ * inv_depth_host: HOST array of 3*D floats (copied into the launch), per plane (a, b, c) with
+ *     1 / (view depth of the ray-plane intersection) = a * (c + 0.5 - cx) + b * (r + 0.5 - cy) + c
+ *     (exactly linear in the pixel for a plane; any affine map of it, e.g. MPI.py:553's normalisation, folds into a, b, c);
+ *     NULL when neither disp_out nor grad_disp is used.
+ * fwd: alpha_out (T,H,W) = sum_k bw_k, disp_out (T,H,W) = sum_k bw_k / depth_k, sparsity_sum[0] += sum over frames and
+ *     pixels of |a|_1 / max(|a|_2, sparsity_eps) over the ray's slot alphas (each optional).
+ * bwd: given dL/d alpha_out, dL/d disp_out (T,H,W each, optional) and w_sparsity = DEVICE float dL/d sparsity_sum
+ *     (optional), ACCUMULATES the resulting gradients of the alpha logits into grad_dyn / grad_sta (same buffers and
+ *     layout as vl3d_composite_bwd; these terms give no gradient to the colour channels). */
+int vl3d_composite_terms_fwd(const vl3d_view* view, const vl3d_quad* quads, const float* atlas_dyn,
+                             const float* atlas_sta, const int32_t* ts, int32_t T, const float* inv_depth_host,
+                             float sparsity_eps, float* alpha_out, float* disp_out, double* sparsity_sum, void* stream);
+int vl3d_composite_terms_bwd(const vl3d_view* view, const vl3d_quad* quads, const float* atlas_dyn,
+                             const float* atlas_sta, const int32_t* ts, int32_t T, const float* inv_depth_host,
+                             float sparsity_eps, const float* grad_alpha, const float* grad_disp,
+                             const float* w_sparsity, float* grad_dyn, float* grad_sta, void* stream);
+
 /* ---- scale-invariant gain (MPV.py:499-504):
  *      out[0] = (exp(mean_{c,h,w} log((mean_F res + .01)/(mean_T rgb + .01))) + 3) / 4
  * rgb (T,3,H,W) contiguous, res (F,3,H,W) contiguous. partials: workspace of >= vl3d_scale_partials()

@@ -77,7 +77,7 @@ def make_model(kind, H, W, D, hv, wv, T, seed, **kw):
     import MPV  # reference
     args = ref_env.make_args(mpi_d=D, mpi_h_verts=hv, mpi_w_verts=wv, atlas_grid_h=kw.get("grid_h", 2),
                              mpv_frm_num=T, mpi_h_scale=kw.get("scale", 1.2), mpi_w_scale=kw.get("scale", 1.2),
-                             add_intrin_noise=False)
+                             add_intrin_noise=False, **kw.get("args", {}))
     f = 0.8 * W
     ref_intrin = np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32)
     torch.manual_seed(seed)
@@ -152,6 +152,8 @@ def golden_step(name, kind, cfg, H=24, W=40, D=4, hv=5, wv=7, T=6, F=9, seed=1, 
                grad_atlas=g_atlas, grad_atlas_dyn=g_dyn, new_atlas=m.atlas.data, new_atlas_dyn=m.atlas_dyn.data,
                y2x=lossobj.last_y2x, weight=lossobj.last_weight,
                rgb_smooth_w=args.rgb_smooth_loss_weight, a_smooth_w=args.a_smooth_loss_weight,
+               sparsity_w=args.sparsity_loss_weight, density_w=args.density_loss_weight,
+               d_smooth_w=args.d_smooth_loss_weight, bg_color=str(args.bg_color),
                **{"extra_" + k: v for k, v in extra_v.items()},
                **{"cfg_" + k: v for k, v in cfg.items()}, **_state_arrays(st))
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(out))
@@ -408,6 +410,10 @@ def main():
     golden_render("render_sparse", "sparse", seed=1, D=6, hv=6, wv=9, T=2)
     golden_step("step_dense_refcfg", "dense", LOSS_CFG_REF, seed=2)
     golden_step("step_sparse_othercfg", "sparse", LOSS_CFG_OTHER, seed=3, D=6, hv=6, wv=9)
+    # the optional terms of MPV.py:455-466, 511-515, 533-551 (weight 0 / off in the shipped stage-2 configs)
+    terms = dict(sparsity_loss_weight=0.004, density_loss_weight=0.02, d_smooth_loss_weight=0.1)
+    golden_step("step_dense_terms", "dense", LOSS_CFG_REF, seed=4, args=dict(bg_color="0.2#0.5#0.9", **terms))
+    golden_step("step_sparse_terms", "sparse", LOSS_CFG_OTHER, seed=6, D=6, hv=6, wv=9, args=terms)   # (seed 5 has an NN near-tie)
     golden_loss("loss_lm_alpha0", "Patch3DGPNNLowMemLoss", macro_block=15, patch_size=5, stride=2, patcht_size=3,
                 stridet=1, rou="-2", scaling=0.1, alpha=0.0)
     golden_loss("loss_lm_noalpha", "Patch3DGPNNLowMemLoss", macro_block=11, patch_size=3, stride=2, patcht_size=3,

@@ -253,11 +253,17 @@ def _bilinear_zeros(atlas, ax, ay):
     return out
 
 
+def parse_bg_color(bg_color):
+    """'r#g#b' -> tensor (MPV.py:455-460); 'random' is drawn by the caller (it consumes torch's CPU generator)."""
+    return torch.tensor([float(v) for v in bg_color.split('#')], dtype=torch.float64)
+
+
 def render(st: MPVState, H, W, tar_extrin, tar_intrin, ts, dtype=torch.float64, atlas=None, atlas_dyn=None,
-           geo=None):
+           geo=None, bg_color=None):
     """Restates MPMeshVid.render (MPV.py:351-475).  Returns rgb (T,H,W,3) and variables with
-    slot-indexed `mpi` (T,H,W,K,4), `blend_weight`, `alpha`, `K`.  `atlas`/`atlas_dyn` may be
-    autograd leaves (dtype `dtype`)."""
+    slot-indexed `mpi` (T,H,W,K,4), `blend_weight`, `alpha`, `disp_norm` (MPV.py:385,463-464: sum of
+    blend weight / view depth), `K`.  `bg_color`: optional (3,) tensor (MPV.py:455-461).
+    `atlas`/`atlas_dyn` may be autograd leaves (dtype `dtype`)."""
     if geo is None:
         geo = geometry(st, H, W, tar_extrin, tar_intrin)
     atlas = st.atlas.to(dtype) if atlas is None else atlas
@@ -291,17 +297,27 @@ def render(st: MPVState, H, W, tar_extrin, tar_intrin, ts, dtype=torch.float64, 
     else:
         bw = alpha
     rgb = (content * bw.unsqueeze(-1)).sum(-2)                                  # utils_mpi.py:106
-    return rgb, dict(mpi=mpi, blend_weight=bw, alpha=bw.sum(-1), K=K, hitmask=hit)
+    alpha_sum = bw.sum(-1)                                                      # MPV.py:454
+    if bg_color is not None:                                                    # MPV.py:455-461
+        bg = bg_color.to(dtype)
+        rgb = rgb * alpha_sum[..., None] + bg[None, None, None] * (-alpha_sum[..., None] + 1)
+    # depths = 1 / zbuf (MPV.py:384-385), compacted into the same slots; empty slots carry weight 0
+    inv_d = torch.zeros(P, max(K, 1), dtype=dtype)
+    depth_o = geo["depth"][:, order].to(dtype)
+    inv_d = inv_d.index_put((pidx[hit_o], slot[hit_o]), 1.0 / depth_o[hit_o])
+    disp = (inv_d[:, :K].reshape(1, H, W, K) * bw).sum(-1)                      # MPV.py:463-464
+    return rgb, dict(mpi=mpi, blend_weight=bw, alpha=alpha_sum, disp_norm=disp, K=K, hitmask=hit)
 
 
 def forward_train(st: MPVState, h, w, tar_extrin, tar_intrin, res, losscfg, *, isloop=True, scale_invariant=True,
                   swd_patcht_size=3, rgb_smooth=True, a_smooth=True, dtype=torch.float64, atlas=None,
-                  atlas_dyn=None, nn_mode="exact64", ts=None):
+                  atlas_dyn=None, nn_mode="exact64", ts=None, sparsity=False, density=False, d_smooth=False,
+                  bg_color=None):
     """Restates MPMeshVid.forward, training branch (MPV.py:477-553).  `losscfg` is the un-batched
     dict (loss_name, loss_gain, patch_size, ..).  Returns dict of 0-dim tensors + aux."""
     T_all = (st.atlas_dyn if atlas_dyn is None else atlas_dyn).shape[0]
     ts = torch.arange(T_all) if ts is None else ts
-    rgb, var = render(st, h, w, tar_extrin, tar_intrin, ts, dtype, atlas, atlas_dyn)
+    rgb, var = render(st, h, w, tar_extrin, tar_intrin, ts, dtype, atlas, atlas_dyn, bg_color=bg_color)
     rgb = rgb.permute(0, 3, 1, 2)                                               # (T,3,h,w)  MPV.py:484
     cfg = dict(losscfg)
     loss_name = cfg.pop("loss_name")
@@ -330,11 +346,26 @@ def forward_train(st: MPVState, h, w, tar_extrin, tar_intrin, res, losscfg, *, i
         sm = mpi[..., -1]
         out["a_smooth"] = ((sm[:, :, :-1] - sm[:, :, 1:]).abs().mean() +
                            (sm[:, :-1] - sm[:, 1:]).abs().mean()) * (gain * K / D)
+    if sparsity:                                                                # MPV.py:511-515
+        al = mpi[..., -1]
+        sp = al.norm(dim=-1, p=1) / al.norm(dim=-1, p=2).clamp_min(1e-4)
+        out["sparsity"] = sp.mean() / math.sqrt(D) * gain
+    if density:                                                                 # MPV.py:533-536
+        out["density"] = (var["alpha"] - 1).abs().mean()
+    if d_smooth:                                                                # MPV.py:538-551
+        disp = var["disp_norm"]
+        gx = (disp[:, 1:, :-1] - disp[:, 1:, 1:]).abs()
+        gy = (disp[:, :-1, 1:] - disp[:, 1:, 1:]).abs()
+        out["d_smooth"] = (gx + gy).mean()
     return out, dict(rgb=rgb, scale=scale, K=K, **aux)
 
 
-def total_loss(extra, rgb_smooth_w=0.2, a_smooth_w=0.2):
-    """train_3dvid.py:230-240."""
+def total_loss(extra, rgb_smooth_w=0.2, a_smooth_w=0.2, **weights):
+    """train_3dvid.py:230-240.  `weights`: sparsity= / density= / d_smooth= loss weights of the optional terms."""
+    for k, wgt in weights.items():
+        if k in extra and wgt > 0:
+            extra = dict(extra)
+            extra["swd"] = extra["swd"] + extra[k] * wgt
     loss = extra["swd"]
     if "rgb_smooth" in extra and rgb_smooth_w > 0:
         loss = loss + extra["rgb_smooth"] * rgb_smooth_w

@@ -54,6 +54,8 @@ _SIGNATURES = {
     "vl3d_last_error_string": (C.c_char_p, []),
     "vl3d_composite_fwd": (C.c_int, [C.POINTER(View), _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "vl3d_composite_bwd": (C.c_int, [C.POINTER(View), _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    "vl3d_composite_terms_fwd": (C.c_int, [C.POINTER(View), _P, _P, _P, _P, C.c_int32, _P, C.c_float, _P, _P, _P, _P]),
+    "vl3d_composite_terms_bwd": (C.c_int, [C.POINTER(View), _P, _P, _P, _P, C.c_int32, _P, C.c_float, _P, _P, _P, _P, _P, _P]),
     "vl3d_scale_partials": (C.c_int, []),
     "vl3d_scale_invariant": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "vl3d_frame_sum": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
@@ -88,7 +90,7 @@ EXPORTS = tuple(_SIGNATURES)
 
 _lib = None
 LAUNCHES = 0          # kernels launched through this binding (bench.py's gpu_launches)
-_LAUNCHES_PER_CALL = {"vl3d_composite_fwd": 1, "vl3d_composite_bwd": 1, "vl3d_scale_invariant": 2, "vl3d_frame_sum": 1, "vl3d_scale_invariant_presum": 2, "vl3d_scale_log_sum": 2, "vl3d_scale_finish": 1,
+_LAUNCHES_PER_CALL = {"vl3d_composite_fwd": 1, "vl3d_composite_bwd": 1, "vl3d_composite_terms_fwd": 1, "vl3d_composite_terms_bwd": 1, "vl3d_scale_invariant": 2, "vl3d_frame_sum": 1, "vl3d_scale_invariant_presum": 2, "vl3d_scale_log_sum": 2, "vl3d_scale_finish": 1,
                       "vl3d_patchnn_search": 1, "vl3d_scale_video": 1, "vl3d_patch_l1": 1, "vl3d_to8b": 1, "vl3d_u8_to_unit": 1, "vl3d_vote_loss": 2, "vl3d_video_loss": 2, "vl3d_adam_step": 1, "vl3d_fused_bwd_adam": 1, "vl3d_fused_bwd_adam_own": 2, "vl3d_copy_boxes": 1}
 
 

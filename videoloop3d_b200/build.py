@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB_PATH = os.path.join(LIB_DIR, "libvl3d.so")
-SOURCES = ["composite.cu", "fused_bwd_adam.cu", "patchnn.cu", "optim.cu", "exchange.cu", "alloc.cu"]
+SOURCES = ["composite.cu", "fused_bwd_adam.cu", "patchnn.cu", "optim.cu", "exchange.cu", "alloc.cu", "terms.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

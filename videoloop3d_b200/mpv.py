@@ -266,11 +266,41 @@ class MPMeshVid(nn.Module):
         rgb, alpha, sums = ops.CompositeFn.apply(atlas_dyn, atlas, view, self._pack, ts_t, T, pad, smooth)
         return rgb, alpha, sums, view, ts_t, T
 
+    def _bg_color(self):
+        """None, or the (3,) background of MPV.py:455-460 ('random' draws from torch's CPU generator like the reference)."""
+        bg = getattr(self.args, "bg_color", "")
+        if len(bg) == 0:
+            return None
+        if bg == "random":
+            return torch.rand(3)
+        return torch.tensor([float(v) for v in bg.split('#')], dtype=torch.float32)
+
+    def _render_terms(self, view, ts_t, T, H, W, extrin, intrin, want_disp=False, want_sparsity=False):
+        """Differentiable alpha (T,H,W), disp (T,H,W) and sparsity sum of the same view (csrc/terms.cu): the optional
+        terms of MPV.py:454-466,511-515 that every shipped stage-2 config leaves off."""
+        atlas_dyn, atlas = self._texels()
+        inv_depth = ops.make_inv_depth(self._pack, H, W, extrin, intrin, np.eye(4)) if want_disp else None
+        return ops.CompositeTermsFn.apply(atlas_dyn, atlas, view, self._pack, ts_t, T, inv_depth, 1e-4, want_disp,
+                                          want_sparsity)
+
+    @staticmethod
+    def _blend_bg(rgb, alpha, bg):
+        """MPV.py:461 on the planar layout: rgb (T,3,H,W), alpha (T,H,W)."""
+        a = alpha[:, None]
+        return rgb * a + bg.to(rgb)[None, :, None, None] * (-a + 1)
+
     def render(self, H, W, extrin, intrin, ts):
         """rgb (len(ts),H,W,3), variables  (reference: MPV.py:351-475)."""
-        if len(getattr(self.args, "bg_color", "")) > 0:
-            raise NotImplementedError("bg_color is off in every stage-2 config and not supported")
         rgb, alpha, _, view, ts_t, T = self._render_planar(H, W, extrin, intrin, ts)
+        bg = self._bg_color()
+        want_disp = getattr(self.args, "d_smooth_loss_weight", 0) > 0
+        disp = None
+        if bg is not None or want_disp:
+            alpha, disp_t, _ = self._render_terms(view, ts_t, T, H, W, extrin, intrin, want_disp=want_disp)
+            if bg is not None:
+                rgb = self._blend_bg(rgb, alpha, bg)
+            if want_disp:
+                disp = disp_t
 
         def make_mpi():
             with torch.no_grad():
@@ -278,24 +308,28 @@ class MPMeshVid(nn.Module):
                                                     want_mpi=True, want_hits=True)
             return mpi, hits
 
-        variables = LazyVariables({"disp_norm": None, "alpha": alpha}, make_mpi)
+        variables = LazyVariables({"disp_norm": disp, "alpha": alpha}, make_mpi)
         return rgb.permute(0, 2, 3, 1), variables
 
     def forward(self, h, w, tar_extrins, tar_intrins, ts=None, res=None, losscfg=None):
-        """Train: (None, {swd, rgb_smooth, a_smooth}) each (1,1); eval: (rgb (T,3,H,W), {})
+        """Train: (None, {swd, rgb_smooth, a_smooth[, sparsity, density, d_smooth]}) each (1,1); eval: (rgb (T,3,H,W), {})
         (reference: MPV.py:477-556)."""
         # MPV.py:478, evaluated in float64 on the host (where the view descriptor is built)
         tar = tar_extrins.detach().double().cpu().numpy() if torch.is_tensor(tar_extrins) else np.asarray(tar_extrins, np.float64)
         extrins = tar.reshape(-1, 4, 4)[:1] @ self.ref_extrin_inv_host()
+        bg = self._bg_color()
         if not self.training:
-            rgb, _, _, _, _, _ = self._render_planar(h, w, extrins, tar_intrins, ts)
+            rgb, _, _, view, ts_t, T = self._render_planar(h, w, extrins, tar_intrins, ts)
+            if bg is not None:
+                alpha, _, _ = self._render_terms(view, ts_t, T, h, w, extrins, tar_intrins)
+                rgb = self._blend_bg(rgb, alpha, bg)
             return rgb, {}
 
         assert res is not None
         args = self.args
-        for k in ("sparsity", "density", "d_smooth"):
-            if getattr(args, f"{k}_loss_weight", 0) > 0:
-                raise NotImplementedError(f"{k}_loss_weight > 0 is used by no stage-2 config and is not supported")
+        want_sp = getattr(args, "sparsity_loss_weight", 0) > 0
+        want_den = getattr(args, "density_loss_weight", 0) > 0
+        want_ds = getattr(args, "d_smooth_loss_weight", 0) > 0
         cfg = {k: (v[0].item() if torch.is_tensor(v) else v[0]) for k, v in losscfg.items()}   # MPV.py:494
         _check_dist(cfg)
         loss_name = cfg.pop('loss_name')
@@ -303,7 +337,16 @@ class MPMeshVid(nn.Module):
         loss = self.losses[loss_name]
         smooth = args.rgb_smooth_loss_weight > 0 or args.a_smooth_loss_weight > 0
         pad = self.swd_patcht_size - 1 if self.isloop else 0                       # MPV.py:490-492
-        rgb_pad, _, sums, _, _, T = self._render_planar(h, w, extrins, tar_intrins, ts, pad=pad, smooth=smooth)
+        # the loop pad is written by the render kernel unless a background blend sits between render and pad
+        rgb_pad, _, sums, view, ts_t, T = self._render_planar(h, w, extrins, tar_intrins, ts, pad=0 if bg is not None else pad,
+                                                              smooth=smooth)
+        alpha = disp = sp_sum = None
+        if bg is not None or want_sp or want_den or want_ds:
+            alpha, disp, sp_sum = self._render_terms(view, ts_t, T, h, w, extrins, tar_intrins, want_disp=want_ds,
+                                                     want_sparsity=want_sp)
+        if bg is not None:                                                         # MPV.py:455-461, then MPV.py:490-492
+            rgb = self._blend_bg(rgb_pad, alpha, bg)
+            rgb_pad = torch.cat([rgb, rgb[:pad]], 0) if pad else rgb.contiguous()
         res0 = res[0]
         if not res0.is_contiguous():
             res0 = res0.contiguous()
@@ -317,6 +360,9 @@ class MPMeshVid(nn.Module):
             x = rgb_pad if xscale is None else rgb_pad * xscale
             main_loss = loss(x.permute(1, 0, 2, 3)[None], res.permute(0, 2, 1, 3, 4), **cfg)
         extra = {'swd': main_loss.reshape(1, -1) * loss_gain}
+        if want_sp:                                                                # MPV.py:511-515
+            val = sp_sum / (T * h * w) / np.sqrt(self.mpi_d) * loss_gain
+            extra["sparsity"] = val.float().reshape(1, -1)
         # slot-wise smoothness: mean|dx| + mean|dy| over (T,H,W,K,c), times gain*K/D: K cancels (MPV.py:517-531)
         nx = max(T * h * (w - 1), 1) * self.mpi_d
         ny = max(T * (h - 1) * w, 1) * self.mpi_d
@@ -326,6 +372,12 @@ class MPMeshVid(nn.Module):
         if args.a_smooth_loss_weight > 0:
             val = (sums[2] / nx + sums[3] / ny) * loss_gain
             extra["a_smooth"] = val.float().reshape(1, -1)
+        if want_den:                                                               # MPV.py:533-536
+            extra["density"] = (alpha - 1).abs().mean().reshape(1, -1)
+        if want_ds:                                                                # MPV.py:538-551
+            gx = (disp[:, 1:, :-1] - disp[:, 1:, 1:]).abs()
+            gy = (disp[:, :-1, 1:] - disp[:, 1:, 1:]).abs()
+            extra["d_smooth"] = (gx + gy).mean().reshape(1, -1)
         return None, extra
 
     # ------------------------------------------------------------------ level of detail (MPV.py:140-198)

@@ -108,6 +108,41 @@ def composite_bwd(view, pack, atlas_dyn, atlas_sta, ts, T, pad, grad_rgb, rgb, w
               _lib.ptr(smooth_sums), _lib.ptr(grad_dyn), _lib.ptr(grad_sta), _lib.stream_ptr())
 
 
+def make_inv_depth(pack: MeshPack, H, W, tar_extrin, tar_intrin, ref_extrin, scale=1.0, offset=0.0):
+    """Host (D,3) float32 coefficients of `scale / view depth + offset` per plane (tiles.view_inv_depth)."""
+    to_np = lambda a: a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    return np.ascontiguousarray(tiles.view_inv_depth(pack.grids, to_np(tar_extrin), to_np(tar_intrin), to_np(ref_extrin), H, W,
+                                                     scale, offset))
+
+
+def _host_floats(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def composite_terms_fwd(view, pack, atlas_dyn, atlas_sta, ts, T, inv_depth=None, sparsity_eps=1e-4, want_alpha=True,
+                        want_disp=False, want_sparsity=False):
+    """alpha (T,H,W), disp (T,H,W), sparsity sum (1,) float64 of vl3d_composite_terms_fwd (each None unless wanted)."""
+    _require_cuda(atlas_dyn, "atlas_dyn"); _require_cuda(atlas_sta, "atlas")
+    dev = atlas_dyn.device
+    H, W = view.H, view.W
+    if want_disp and inv_depth is None:
+        raise _lib.Vl3dError("composite_terms_fwd: disp needs the inverse-depth coefficients")
+    alpha = torch.empty((T, H, W), dtype=torch.float32, device=dev) if want_alpha else None
+    disp = torch.empty((T, H, W), dtype=torch.float32, device=dev) if want_disp else None
+    sp = torch.zeros(1, dtype=torch.float64, device=dev) if want_sparsity else None
+    _lib.call("vl3d_composite_terms_fwd", C.byref(view), _lib.ptr(pack.quads), _lib.ptr(atlas_dyn), _lib.ptr(atlas_sta),
+              _lib.ptr(ts), int(T), _host_floats(inv_depth), float(sparsity_eps), _lib.ptr(alpha), _lib.ptr(disp), _lib.ptr(sp),
+              _lib.stream_ptr())
+    return alpha, disp, sp
+
+
+def composite_terms_bwd(view, pack, atlas_dyn, atlas_sta, ts, T, inv_depth, sparsity_eps, g_alpha, g_disp, w_sparsity,
+                        grad_dyn, grad_sta):
+    _lib.call("vl3d_composite_terms_bwd", C.byref(view), _lib.ptr(pack.quads), _lib.ptr(atlas_dyn), _lib.ptr(atlas_sta),
+              _lib.ptr(ts), int(T), _host_floats(inv_depth), float(sparsity_eps), _lib.ptr(g_alpha), _lib.ptr(g_disp),
+              _lib.ptr(w_sparsity), _lib.ptr(grad_dyn), _lib.ptr(grad_sta), _lib.stream_ptr())
+
+
 def scale_invariant(rgb, T, res, out=None, partials=None):
     """MPV.py:499-504 on device: rgb (>=T,3,H,W) contiguous, res (F,3,H,W) contiguous -> (1,) float."""
     _require_cuda(rgb, "rgb"); _require_cuda(res, "res")
@@ -430,3 +465,34 @@ class CompositeFn(torch.autograd.Function):
         grad_sta = torch.zeros_like(atlas_sta)
         composite_bwd(ctx.view, ctx.pack, atlas_dyn, atlas_sta, ts, ctx.T, ctx.pad, g_rgb, rgb, w, grad_dyn, grad_sta)
         return grad_dyn, grad_sta, None, None, None, None, None, None
+
+
+class CompositeTermsFn(torch.autograd.Function):
+    """alpha (T,H,W), disp (T,H,W), sparsity_sum (1,) float64 = f(atlas_dyn, atlas): the optional, differentiable per-ray
+    terms of the composite (MPV.py:454-466, 511-515; csrc/terms.cu).  Outputs that are not wanted come back as zeros."""
+
+    @staticmethod
+    def forward(ctx, atlas_dyn, atlas_sta, view, pack, ts, T, inv_depth, sparsity_eps, want_disp, want_sparsity):
+        ctx.set_materialize_grads(False)
+        alpha, disp, sp = composite_terms_fwd(view, pack, atlas_dyn, atlas_sta, ts, T, inv_depth, sparsity_eps,
+                                              want_alpha=True, want_disp=want_disp, want_sparsity=want_sparsity)
+        ctx.save_for_backward(atlas_dyn, atlas_sta, ts)
+        ctx.view, ctx.pack, ctx.T, ctx.inv_depth, ctx.eps = view, pack, T, inv_depth, sparsity_eps
+        ctx.want_disp, ctx.want_sparsity = want_disp, want_sparsity
+        if disp is None:
+            disp = torch.zeros((), dtype=torch.float32, device=atlas_dyn.device)
+        if sp is None:
+            sp = torch.zeros(1, dtype=torch.float64, device=atlas_dyn.device)
+        return alpha, disp, sp
+
+    @staticmethod
+    def backward(ctx, g_alpha, g_disp, g_sp):
+        atlas_dyn, atlas_sta, ts = ctx.saved_tensors
+        g_alpha = None if g_alpha is None else g_alpha.to(torch.float32).contiguous()
+        g_disp = None if (g_disp is None or not ctx.want_disp) else g_disp.to(torch.float32).contiguous()
+        w = None if (g_sp is None or not ctx.want_sparsity) else g_sp.to(torch.float32).contiguous()
+        grad_dyn = torch.zeros_like(atlas_dyn)     # preserves the channels_last texel layout
+        grad_sta = torch.zeros_like(atlas_sta)
+        composite_terms_bwd(ctx.view, ctx.pack, atlas_dyn, atlas_sta, ts, ctx.T, ctx.inv_depth, ctx.eps, g_alpha, g_disp, w,
+                            grad_dyn, grad_sta)
+        return grad_dyn, grad_sta, None, None, None, None, None, None, None, None

@@ -624,6 +624,11 @@ class FusedLoopStep:
         if not isinstance(lossobj, (Patch3DGPNNLowMemLoss, Patch3DGPNNDirectLoss)):
             raise NotImplementedError(f"FusedLoopStep supports the gpnn / gpnn_lm losses, not {loss_name!r}")
         _check_dist(cfg)
+        if (len(getattr(args, "bg_color", "")) > 0
+                or any(getattr(args, f"{k}_loss_weight", 0) > 0 for k in ("sparsity", "density", "d_smooth"))):
+            raise NotImplementedError("FusedLoopStep covers the terms the shipped stage-2 configs use; bg_color / sparsity / "
+                                      "density / d_smooth run on the autograd path (MPMeshVid.forward + loss.backward(), "
+                                      "i.e. make_run_iter)")
         T, t0, t1 = self.T, self.t0, self.t1
         Tl = t1 - t0
         pad = m.swd_patcht_size - 1 if m.isloop else 0
