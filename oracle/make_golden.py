@@ -397,6 +397,48 @@ def golden_dataset(name, V=2, F=5, h_raw=20, w_raw=30, seed=7):
     print(name, {t: int(out[t + "_len"]) for t in "abc"}, out["batch_cfg_kinds"])
 
 
+def golden_stage1(name, H=24, W=40, D=4, hv=5, wv=7, seed=8, loop_mask=True, **arg_overrides):
+    """SURVEY §8(f) N4, second half: the unmodified reference's stage-1 model (`MPI.MPMesh`, configs/mpi_base.txt) rendered
+    and differentiated for one training view: rgbl, every extra term of MPI.py:596-652 and the gradients of
+    `mean(rgbl * g_up) + sum_k extra_k * weight_k` w.r.t. `atlas` / `atlas_mask`."""
+    import MPI  # reference
+    args = ref_env.make_args(config="configs/mpi_base.txt", mpi_d=D, mpi_h_verts=hv, mpi_w_verts=wv, atlas_grid_h=2,
+                             mpi_h_scale=1.2, mpi_w_scale=1.2, learn_loop_mask=loop_mask, **arg_overrides)
+    f = 0.8 * W
+    ref_intrin = np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32)
+    torch.manual_seed(seed)
+    m = MPI.MPMesh(args, H, W, np.eye(4, dtype=np.float32), ref_intrin, 1.0, 10.0)
+    st, atlas_mask = MO.stage1_state(H, W, D, hv, wv, 2, 1.0, 10.0, 1.2, 1.2, seed=seed)
+    assert torch.allclose(st.verts, m._verts.data) and torch.equal(st.faces, m.faces)
+    assert torch.allclose(st.uvs, m.uvs.data, atol=1e-7) and tuple(st.atlas.shape) == tuple(m.atlas.shape)
+    m.atlas.data = st.atlas.clone()
+    if loop_mask:
+        m.atlas_mask.data = atlas_mask.clone()
+    ext, intr = _view(seed, H, W)
+    m.train()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rgbl, extra = m(H, W, ext, intr)
+        _, var = m.render(H, W, ext @ m.ref_extrin[None].inverse(), intr)
+    g = torch.Generator().manual_seed(seed + 3)
+    g_up = torch.rand(rgbl.shape, generator=g) - 0.4
+    weights = {k: float(getattr(args, k + "_loss_weight")) for k in extra}
+    loss = (rgbl * g_up).mean()
+    for k, v in extra.items():
+        loss = loss + v.mean() * weights[k]
+    loss.backward()
+    out = dict(H=H, W=W, near=1.0, far=10.0, tar_extrin=ext, tar_intrin=intr, rgbl=rgbl, g_up=g_up, loss=loss.detach(),
+               grad_atlas=m.atlas.grad, disp_norm=var["disp_norm"], alpha=var["alpha"], mpi=var["mpi"],
+               blend_weight=var["blend_weight"], bg_color=str(args.bg_color), edge_scale=float(args.edge_scale),
+               normalize_blendweight_fordepth=bool(args.normalize_blendweight_fordepth), loop_mask=bool(loop_mask),
+               atlas_mask=atlas_mask, **{"extra_" + k: v.detach() for k, v in extra.items()},
+               **{"w_" + k: w for k, w in weights.items()}, **_state_arrays(st))
+    if loop_mask:
+        out.update(grad_atlas_mask=m.atlas_mask.grad, loopmask3d=var["loopmask3d"])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(out))
+    print(name, {k: float(v) for k, v in extra.items()}, "loss", float(loss))
+
+
 def main():
     assert ref_env.reference_available(), "needs /root/reference"
     ref_env.enable()
@@ -414,6 +456,9 @@ def main():
     terms = dict(sparsity_loss_weight=0.004, density_loss_weight=0.02, d_smooth_loss_weight=0.1)
     golden_step("step_dense_terms", "dense", LOSS_CFG_REF, seed=4, args=dict(bg_color="0.2#0.5#0.9", **terms))
     golden_step("step_sparse_terms", "sparse", LOSS_CFG_OTHER, seed=6, D=6, hv=6, wv=9, args=terms)   # (seed 5 has an NN near-tie)
+    golden_stage1("stage1_loopmask", d_smooth_loss_weight=0.1, l_smooth_loss_weight=0.05, edge_scale=0.5)
+    golden_stage1("stage1_bg_normdepth", seed=9, loop_mask=False, d_smooth_loss_weight=0.1, bg_color="0.9#0.1#0.4",
+                  normalize_blendweight_fordepth=True, edge_scale=0.5)
     golden_loss("loss_lm_alpha0", "Patch3DGPNNLowMemLoss", macro_block=15, patch_size=5, stride=2, patcht_size=3,
                 stridet=1, rou="-2", scaling=0.1, alpha=0.0)
     golden_loss("loss_lm_noalpha", "Patch3DGPNNLowMemLoss", macro_block=11, patch_size=3, stride=2, patcht_size=3,

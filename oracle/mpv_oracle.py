@@ -360,6 +360,90 @@ def forward_train(st: MPVState, h, w, tar_extrin, tar_intrin, res, losscfg, *, i
     return out, dict(rgb=rgb, scale=scale, K=K, **aux)
 
 
+# --------------------------------------------------------------------------------------
+# stage 1: MPMesh.render / forward (MPI.py:452-652) — SURVEY §8(f) N4, second half
+# --------------------------------------------------------------------------------------
+def stage1_state(H, W, D, hv, wv, grid_h, near, far, h_scale=1.0, w_scale=1.0, seed=0, alpha_mean=-1.0):
+    """The dense stage-1 model as MPMesh.__init__ lays it out (MPI.py:38-124): the same vertex grid / faces / uvs as the
+    stage-2 model, but every quad STATIC (one atlas, no dynamic part) plus a one-channel loop-mask atlas."""
+    st = dense_state(H, W, D, hv, wv, grid_h, 1, near, far, h_scale, w_scale, seed=seed, alpha_mean=alpha_mean)
+    st.faces, st.uvs, st.uvfaces, st.atlas = st.faces_dyn, st.uvs_dyn, st.uvfaces_dyn, st.atlas_dyn[:1].clone()
+    st.faces_dyn, st.uvs_dyn, st.uvfaces_dyn = st.faces[:0].clone(), st.uvs[:0].clone(), st.uvfaces[:0].clone()
+    st.atlas_dyn = torch.zeros(1, 4, 1, 1)
+    g = torch.Generator().manual_seed(seed + 11)
+    atlas_mask = torch.randn((1, 1) + tuple(st.atlas.shape[-2:]), generator=g)
+    return st, atlas_mask
+
+
+def render_stage1(st: MPVState, H, W, tar_extrin, tar_intrin, near, far, dtype=torch.float64, atlas=None, atlas_dyn=None,
+                  atlas_mask=None, bg_color=None, normalize_blendweight_fordepth=False):
+    """Restates MPMesh.render (MPI.py:452-594) for rgb_mlp_type='direct', one view (the reference's own batching of views
+    does not run: MPI.py:472 broadcasts (B,3,3) against (1,N,3,1)).  Returns rgbl (1,H,W,3|4) and variables with `mpi`,
+    `blend_weight`, `alpha`, `disp_norm` (normalised disparity, MPI.py:552-553,566), `loopmask3d` (MPI.py:568-580)."""
+    atlas = st.atlas.to(dtype) if atlas is None else atlas
+    geo = geometry(st, H, W, tar_extrin, tar_intrin)
+    rgb, var = render(st, H, W, tar_extrin, tar_intrin, [0], dtype, atlas, atlas_dyn, geo=geo, bg_color=bg_color)
+    bw, alpha = var["blend_weight"], var["alpha"]
+    span = 1.0 / near - 1.0 / far
+    if normalize_blendweight_fordepth:                                          # MPI.py:564-566
+        bwn = bw / alpha.clamp_min(1e-10)[..., None]
+        disp = (_slot_inv_depth(st, geo, H, W, var["K"], dtype) * bwn).sum(-1)
+        disp = (disp - bwn.sum(-1) / far) / span
+        var["blend_weight"] = bwn
+    else:
+        disp = (var["disp_norm"] - alpha / far) / span                          # sum_k bw_k (1/z_k - 1/far) / span
+    var["disp_norm"] = disp
+    var["loopmask3d"] = None
+    rgbl = rgb
+    if atlas_mask is not None:                                                  # MPI.py:568-580
+        assert len(st.faces_dyn) == 0
+        fake = torch.cat([atlas_mask.to(dtype).expand(-1, 3, -1, -1), atlas[:, 3:4].detach()], 1)
+        lab, var_l = render(st, H, W, tar_extrin, tar_intrin, [0], dtype, fake, None, geo=geo)
+        var["loopmask3d"] = var_l["mpi"][..., :1]
+        rgbl = torch.cat([rgb, lab[..., :1]], -1)
+    return rgbl, var
+
+
+def _slot_inv_depth(st, geo, H, W, K, dtype):
+    """1 / view depth of each ray's hits, compacted into its K slots (0 for empty slots)."""
+    D, P = st.mpi_d, H * W
+    order = torch.arange(D) if geo["forward_order"] else torch.arange(D - 1, -1, -1)
+    hit_o = geo["hit"][:, order]
+    slot = torch.cumsum(hit_o.long(), 1) - 1
+    pidx = torch.arange(P)[:, None].expand(P, D)
+    inv_d = torch.zeros(P, max(K, 1), dtype=dtype)
+    inv_d = inv_d.index_put((pidx[hit_o], slot[hit_o]), 1.0 / geo["depth"][:, order].to(dtype)[hit_o])
+    return inv_d[:, :K].reshape(1, H, W, K)
+
+
+def forward_stage1(st: MPVState, h, w, tar_extrin, tar_intrin, near, far, *, sparsity=True, rgb_smooth=True, a_smooth=True,
+                   d_smooth=True, l_smooth=True, density=True, edge_scale=4.0, **render_kw):
+    """Restates MPMesh.forward, training branch (MPI.py:596-652).  Returns rgbl (1,C,h,w) and the dict of extra terms."""
+    rgbl, var = render_stage1(st, h, w, tar_extrin, tar_intrin, near, far, **render_kw)
+    rgbl = rgbl.permute(0, 3, 1, 2)
+    mpi, K, D = var["mpi"], var["K"], st.mpi_d
+    out = {}
+    if sparsity:                                                                # MPI.py:603-607 (1e-6, no gain)
+        al = mpi[..., -1]
+        out["sparsity"] = (al.norm(dim=-1, p=1) / al.norm(dim=-1, p=2).clamp_min(1e-6)).mean() / math.sqrt(D)
+    sm_mean = lambda t: (t[:, :, :-1] - t[:, :, 1:]).abs().mean() + (t[:, :-1] - t[:, 1:]).abs().mean()
+    if rgb_smooth:                                                              # MPI.py:609-615
+        out["rgb_smooth"] = sm_mean(mpi[..., :-1]) * (K / D)
+    if a_smooth:                                                                # MPI.py:617-623
+        out["a_smooth"] = sm_mean(mpi[..., -1]) * (K / D)
+    if d_smooth:                                                                # MPI.py:625-638 (edge-aware)
+        disp = var["disp_norm"]
+        dg = (disp[:, 1:, :-1] - disp[:, 1:, 1:]).abs() + (disp[:, :-1, 1:] - disp[:, 1:, 1:]).abs()
+        rgb = rgbl[:, :3]
+        edge = ((rgb[..., 1:, :-1] - rgb[..., 1:, 1:]).abs().sum(dim=1) + (rgb[..., :-1, 1:] - rgb[..., 1:, 1:]).abs().sum(dim=1))
+        out["d_smooth"] = (dg * (-edge * edge_scale + 1).clamp_min(0)).mean()
+    if l_smooth and var["loopmask3d"] is not None:                              # MPI.py:640-646
+        out["l_smooth"] = sm_mean(var["loopmask3d"][..., 0]) * (K / D)
+    if density:                                                                 # MPI.py:648-651
+        out["density"] = (var["alpha"] - 1).abs().mean()
+    return rgbl, out, var
+
+
 def total_loss(extra, rgb_smooth_w=0.2, a_smooth_w=0.2, **weights):
     """train_3dvid.py:230-240.  `weights`: sparsity= / density= / d_smooth= loss weights of the optional terms."""
     for k, wgt in weights.items():

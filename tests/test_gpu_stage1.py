@@ -1,0 +1,141 @@
+"""GPU: `MPMesh` (the reference's stage-1 model, MPI.py:38-124,452-652; SURVEY §8(f) N4, second half) through the CUDA
+path against golden vectors of the UNMODIFIED reference (oracle/make_golden.py::golden_stage1) and against the CPU
+oracle on other views.  Tolerances: 1e-4 relative on rendered values and loss terms (north_star), 5e-4 of the largest
+entry on gradients (the bar of the stage-2 golden tests)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mpv_oracle as MO
+from test_gpu_composite_sweep import VIEWS, _rot
+from util import load_golden, relerr, state_from_golden
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _model(g, **overrides):
+    from videoloop3d_b200 import MPMesh, default_args_stage1
+    H, W, D, hv, wv = int(g["H"]), int(g["W"]), int(g["mpi_d"]), int(g["hv"]), int(g["wv"])
+    weights = {k[2:] + "_loss_weight": float(g[k]) for k in g if k.startswith("w_")}
+    base = dict(sparsity_loss_weight=0.0, rgb_smooth_loss_weight=0.0, a_smooth_loss_weight=0.0, density_loss_weight=0.0,
+                d_smooth_loss_weight=0.0, l_smooth_loss_weight=0.0)
+    base.update(weights)
+    base.update(overrides)
+    args = default_args_stage1(mpi_d=D, mpi_h_verts=hv, mpi_w_verts=wv, atlas_grid_h=2, mpi_h_scale=1.2, mpi_w_scale=1.2,
+                               learn_loop_mask=bool(g["loop_mask"]), bg_color=str(g["bg_color"]), edge_scale=float(g["edge_scale"]),
+                               normalize_blendweight_fordepth=bool(g["normalize_blendweight_fordepth"]), **base)
+    f = 0.8 * W
+    m = MPMesh(args, H, W, np.eye(4, dtype=np.float32), np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32),
+               float(g["near"]), float(g["far"]))
+    m.atlas.data = torch.as_tensor(g["atlas"]).clone()
+    if bool(g["loop_mask"]):
+        m.atlas_mask.data = torch.as_tensor(g["atlas_mask"]).clone()
+    return m.to(dev())
+
+
+@pytest.mark.parametrize("name", ["stage1_loopmask", "stage1_bg_normdepth"])
+def test_stage1_forward_backward_matches_reference_golden(name):
+    g = load_golden(name)
+    m = _model(g)
+    H, W = int(g["H"]), int(g["W"])
+    ext, intr = torch.as_tensor(g["tar_extrin"]).to(dev()), torch.as_tensor(g["tar_intrin"]).to(dev())
+    m.train()
+    rgbl, extra = m(H, W, ext, intr)
+    assert tuple(rgbl.shape) == tuple(g["rgbl"].shape)
+    assert relerr(rgbl.detach().cpu(), g["rgbl"]) < RTOL
+    assert set(extra) == {k[6:] for k in g if k.startswith("extra_")}
+    loss = (rgbl * torch.as_tensor(g["g_up"]).to(dev())).mean()
+    for k, v in extra.items():
+        assert tuple(v.shape) == (1, 1)
+        ref = float(g["extra_" + k].reshape(-1)[0])
+        assert abs(float(v) - ref) < RTOL * abs(ref), (k, float(v), ref)
+        loss = loss + v.mean() * float(g["w_" + k])
+    assert abs(float(loss) - float(g["loss"])) < RTOL * abs(float(g["loss"]))
+    loss.backward()
+    assert m.uvs.grad is None and m._verts.grad is None
+    assert relerr(m.atlas.grad.cpu(), g["grad_atlas"]) < 5e-4
+    if bool(g["loop_mask"]):
+        assert relerr(m.atlas_mask.grad.cpu(), g["grad_atlas_mask"]) < 5e-4
+    # the variables of render (MPI.py:585-592)
+    m.eval()
+    with torch.no_grad():
+        rgbl2, var = m.render(H, W, (ext.cpu() @ torch.inverse(torch.as_tensor(g["ref_extrin"]))[None]), intr)
+        rgbl3, extra3 = m(H, W, ext, intr)
+    assert extra3 == {} and relerr(rgbl3.cpu(), g["rgbl"]) < RTOL
+    assert relerr(rgbl2.permute(0, 3, 1, 2).cpu(), g["rgbl"]) < RTOL
+    assert set(var.keys()) == {"pix_to_face", "blend_weight", "mpi", "loopmask3d", "disp_norm", "alpha"}
+    assert relerr(var["disp_norm"].cpu(), g["disp_norm"]) < RTOL
+    assert relerr(var["alpha"].cpu(), g["alpha"]) < RTOL
+    assert relerr(var["mpi"].cpu(), g["mpi"]) < RTOL
+    assert relerr(var["blend_weight"].cpu(), g["blend_weight"]) < RTOL
+    if bool(g["loop_mask"]):
+        assert relerr(var["loopmask3d"].cpu(), g["loopmask3d"]) < RTOL
+    else:
+        assert var["loopmask3d"] is None
+
+
+@pytest.mark.parametrize("vname", sorted(VIEWS))
+def test_stage1_matches_oracle_on_other_views(vname):
+    """Magnified / minified / rolled / oblique views of a D = 8 stage-1 model (image size off the tile grid)."""
+    from videoloop3d_b200 import MPMesh, default_args_stage1
+    H, W, D, hv, wv = 37, 70, 8, 6, 9
+    seed = 21 + sorted(VIEWS).index(vname)
+    st, atlas_mask = MO.stage1_state(H, W, D, hv, wv, 2, 1.0, 10.0, 1.6, 1.6, seed=seed)
+    v = VIEWS[vname]
+    ext = torch.eye(4)
+    ext[:3, :3] = _rot(*v["rot"])
+    ext[:3, 3] = torch.tensor(v["trans"])
+    f = 0.8 * W * v["fmul"]
+    intr = torch.tensor([[f, 0, W / 2 + 0.37], [0, f, H / 2 - 0.21], [0, 0, 1.]])
+    weights = dict(sparsity=0.3, rgb_smooth=0.2, a_smooth=0.5, density=0.2, d_smooth=0.4, l_smooth=0.1)
+    a = st.atlas.double().requires_grad_(True)
+    am = atlas_mask.double().requires_grad_(True)
+    rgbl_o, extra_o, var_o = MO.forward_stage1(st, H, W, ext[None], intr[None], 1.0, 10.0, edge_scale=0.5, atlas=a, atlas_mask=am)
+    gen = torch.Generator().manual_seed(seed)
+    g_up = torch.rand(rgbl_o.shape, generator=gen, dtype=torch.float64) - 0.4
+    loss_o = (rgbl_o * g_up).mean() + sum(extra_o[k] * w for k, w in weights.items())
+    loss_o.backward()
+    args = default_args_stage1(mpi_d=D, mpi_h_verts=hv, mpi_w_verts=wv, atlas_grid_h=2, mpi_h_scale=1.6, mpi_w_scale=1.6,
+                               edge_scale=0.5, **{k + "_loss_weight": w for k, w in weights.items()})
+    fr = 0.8 * W
+    m = MPMesh(args, H, W, np.eye(4, dtype=np.float32), np.array([[fr, 0, W / 2], [0, fr, H / 2], [0, 0, 1]], dtype=np.float32),
+               1.0, 10.0)
+    assert torch.equal(m.faces, st.faces) and torch.allclose(m._verts.data, st.verts) and torch.allclose(m.uvs.data, st.uvs, atol=1e-7)
+    m.atlas.data, m.atlas_mask.data = st.atlas.clone(), atlas_mask.clone()
+    m = m.to(dev()).train()
+    rgbl, extra = m(H, W, ext[None].to(dev()), intr[None].to(dev()))
+    assert float((rgbl.detach().cpu().double() - rgbl_o.detach()).abs().max()) < RTOL
+    for k in weights:
+        assert abs(float(extra[k]) - float(extra_o[k])) < RTOL * max(abs(float(extra_o[k])), 1e-3), k
+    loss = (rgbl * g_up.to(dev()).float()).mean() + sum(extra[k].mean() * w for k, w in weights.items())
+    loss.backward()
+    # The smoothness terms are sums of |differences| of neighbouring slot values: where two neighbours differ by less than
+    # the fp32 sampling noise (texel coordinates up to ~400 at eps 6e-8 => ~5e-6 on a value), the sign — the gradient of
+    # that pair, spread over the 2 x 4 texels it taps — is not defined by the inputs.  Such pairs are counted in the
+    # oracle's own values and only they may disagree (seen: one pair of the rolled view, |d alpha| = 1.1e-6).
+    n_ties = 0
+    for t in (var_o["mpi"].detach(), var_o["loopmask3d"].detach()):
+        for d in ((t[:, :, :-1] - t[:, :, 1:]).abs(), (t[:, :-1] - t[:, 1:]).abs()):
+            n_ties += int(((d > 0) & (d < 1e-5)).sum())
+    for name, got, ref in (("atlas", m.atlas.grad, a.grad), ("atlas_mask", m.atlas_mask.grad, am.grad)):
+        err = (got.cpu().double() - ref).abs()
+        bad = int((err > 5e-4 * float(ref.abs().max())).sum())
+        assert bad <= 8 * n_ties, (name, bad, n_ties, float(err.max()))
+        assert float(err.max()) < 0.5 * float(ref.abs().max()), (name, float(err.max()))
+
+
+def test_stage1_refuses_what_it_does_not_cover():
+    from videoloop3d_b200 import MPMesh, Vl3dError, default_args_stage1
+    g = load_golden("stage1_loopmask")
+    H, W = int(g["H"]), int(g["W"])
+    with pytest.raises(Vl3dError, match="rgb_mlp_type"):
+        MPMesh(default_args_stage1(rgb_mlp_type="rgb_sh"), H, W, np.eye(4, dtype=np.float32), np.eye(3, dtype=np.float32), 1.0, 10.0)
+    m = _model(g)
+    two = torch.eye(4)[None].repeat(2, 1, 1)
+    with pytest.raises(Vl3dError, match="one view"):
+        m.render(H, W, two, torch.as_tensor(g["tar_intrin"]).repeat(2, 1, 1))

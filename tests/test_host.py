@@ -388,6 +388,36 @@ def test_constructor_state_equals_reference_state():
         assert k in sd
 
 
+def test_stage1_constructor_state_equals_reference_state():
+    """`MPMesh.__init__` (second half) carries the tensors the unmodified reference's stage-1 constructor
+    produced for the same arguments (MPI.py:38-124; stored in tests/golden/stage1_loopmask.npz by
+    oracle/make_golden.py::golden_stage1, which asserts them against the reference's own)."""
+    from util import load_golden
+    from videoloop3d_b200 import MPMesh, default_args_stage1
+    g = load_golden("stage1_loopmask")
+    H, W, D, hv, wv = int(g["H"]), int(g["W"]), int(g["mpi_d"]), int(g["hv"]), int(g["wv"])
+    args = default_args_stage1(mpi_d=D, mpi_h_verts=hv, mpi_w_verts=wv, atlas_grid_h=2, mpi_h_scale=1.2, mpi_w_scale=1.2)
+    f = 0.8 * W
+    torch.manual_seed(0)
+    m = MPMesh(args, H, W, np.eye(4, dtype=np.float32), np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32),
+               1.0, 10.0)
+    assert {k for k, _ in m.named_parameters()} == {"_verts", "uvs", "atlas", "atlas_mask"}
+    assert {k for k, _ in m.named_buffers()} == {"ref_extrin", "ref_intrin", "planedepth", "uvfaces", "faces"}
+    assert torch.equal(m.faces, torch.as_tensor(g["faces"]).long()) and torch.equal(m.uvfaces, m.faces)
+    assert torch.equal(m.uvs.data, torch.as_tensor(g["uvs"]))                    # bit for bit
+    assert torch.equal(m._verts.data, torch.as_tensor(g["verts"]))
+    assert torch.equal(m.planedepth, torch.as_tensor(g["planedepth"]))
+    assert tuple(m.atlas.shape) == tuple(g["atlas"].shape) and tuple(m.atlas_mask.shape) == tuple(g["atlas_mask"].shape)
+    # the constructor's only RNG draw is the atlas (MPI.py:102), alpha / mask logits start at -3 (MPI.py:35,103,118)
+    torch.manual_seed(0)
+    assert torch.equal(m.atlas.data[:, :3], torch.rand((1, 4) + tuple(m.atlas.shape[-2:]))[:, :3])
+    assert float(m.atlas.data[:, 3].min()) == float(m.atlas.data[:, 3].max()) == -3.0 and float(m.atlas_mask.data.max()) == -3.0
+    assert not m.is_sparse and not m.has_dyn
+    m.eval()
+    with pytest.raises(Exception, match="CUDA"):                                 # no CPU fallback
+        m.render(H, W, np.eye(4)[None], torch.as_tensor(g["tar_intrin"]))
+
+
 def test_argument_validation_of_the_round2_entry_points():
     """vl3d_copy_boxes / vl3d_fused_bwd_adam_own / the sizing helpers reject bad arguments before touching the device."""
     lib = _lib.load()

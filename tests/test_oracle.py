@@ -88,6 +88,39 @@ def test_optional_terms_match_reference(name):
         assert relerr(a.grad, g["grad_atlas"]) < 1e-4
 
 
+@pytest.mark.parametrize("name", ["stage1_loopmask", "stage1_bg_normdepth"])
+def test_stage1_render_and_forward_match_reference(name):
+    """SURVEY §8(f) N4, second half: `MPI.MPMesh.render / forward` (MPI.py:452-652) of the unmodified reference —
+    rgb + loop-mask label, normalised disparity, every extra term and the gradients of atlas / atlas_mask."""
+    g = load_golden(name)
+    st = state_from_golden(g)
+    H, W = int(g["H"]), int(g["W"])
+    a = st.atlas.double().requires_grad_(True)
+    am = torch.as_tensor(g["atlas_mask"]).double().requires_grad_(True) if bool(g["loop_mask"]) else None
+    bg = MO.parse_bg_color(str(g["bg_color"])) if str(g["bg_color"]) else None
+    rgbl, extra, var = MO.forward_stage1(st, H, W, torch.as_tensor(g["tar_extrin"]), torch.as_tensor(g["tar_intrin"]),
+                                         float(g["near"]), float(g["far"]), edge_scale=float(g["edge_scale"]), atlas=a,
+                                         atlas_mask=am, bg_color=bg,
+                                         normalize_blendweight_fordepth=bool(g["normalize_blendweight_fordepth"]))
+    assert tuple(rgbl.shape) == tuple(g["rgbl"].shape)
+    assert relerr(rgbl.detach(), g["rgbl"]) < 2e-5
+    assert relerr(var["disp_norm"].detach(), g["disp_norm"]) < 2e-5
+    assert relerr(var["blend_weight"].detach(), g["blend_weight"]) < 2e-5
+    assert relerr(var["alpha"].detach(), g["alpha"]) < 2e-5
+    if am is not None:
+        assert relerr(var["loopmask3d"].detach(), g["loopmask3d"]) < 2e-5
+    assert set(extra) == {k[6:] for k in g if k.startswith("extra_")}
+    loss = (rgbl * torch.as_tensor(g["g_up"])).mean()
+    for k, v in extra.items():
+        assert abs(float(v) - float(g["extra_" + k].reshape(-1)[0])) < 2e-6 * max(1.0, abs(float(v))), k
+        loss = loss + v * float(g["w_" + k])
+    assert abs(float(loss) - float(g["loss"])) < 2e-6
+    loss.backward()
+    assert relerr(a.grad, g["grad_atlas"]) < 1e-4
+    if am is not None:
+        assert relerr(am.grad, g["grad_atlas_mask"]) < 1e-4
+
+
 @pytest.mark.parametrize("name", ["loss_lm_alpha0", "loss_lm_noalpha", "loss_direct_p7", "loss_lm_abs"])
 @pytest.mark.parametrize("mode", ["exact64", "ref32"])
 def test_loss_matches_reference(name, mode):

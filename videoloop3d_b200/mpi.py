@@ -1,0 +1,232 @@
+"""`MPMesh` — drop-in for the `render` / `forward` surface of the reference's stage-1 model (reference: MPI.py:38-124,
+452-652; SURVEY.md §8(f) N4, second half).
+
+Stage 1 fits ONE static multiplane image (plus a one-channel loop-mask atlas) to the averaged input views before
+stage 2 turns it into the looping video; it is the same composite as stage 2 with one frame: every quad samples the
+static atlas.  It is built from the stage-2 kernels, nothing new on the device:
+
+  * rgb / smoothness sums            `vl3d_composite_fwd / _bwd` (static tiles, T = 1),
+  * alpha, disparity, sparsity       `vl3d_composite_terms_fwd / _bwd` (csrc/terms.cu); MPI.py:553's normalisation of the
+                                     inverse depth is affine and is folded into the per-plane coefficients on the host,
+  * loop-mask label (MPI.py:568-580) a second composite over the texel tensor (mask, mask, mask, alpha.detach()): its
+                                     "rgb" is the label, its smoothness sums are 3x the l_smooth sums, and the detach
+                                     keeps the geometry independent of the mask exactly as the reference does.
+
+Supported: `rgb_mlp_type='direct'`, sigmoid activations, one view per call (the reference's own batching of views does
+not run: MPI.py:472 broadcasts (B,3,3) against (1,N,3,1)).  Not built here: the stage-1 trainer (`train_3d.py`) and
+`sparsify_faces` (MPI.py:289-442; its OUTPUT format is what `MPMeshVid.init_from_mpi` loads, pinned by tests/golden/ckpt.npz).
+There is no CPU fallback: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops, tiles
+from ._lib import Vl3dError
+from .mpv import LazyVariables, gen_mpi_vertices, get_new_intrin, make_depths
+
+ALPHA_INIT_VAL = -3.0                                               # MPI.py:35
+
+
+class Stage1Variables(LazyVariables):
+    """`variables` of MPMesh.render (MPI.py:585-592): `loopmask3d` joins the lazily materialised keys and
+    `blend_weight` honours `normalize_blendweight_fordepth` (MPI.py:564-565)."""
+
+    _LAZY = LazyVariables._LAZY + ("loopmask3d",)
+
+    def __init__(self, eager, make_mpi, make_mask_mpi=None, normalize_bw=False):
+        super().__init__(eager, make_mpi)
+        self._make_mask_mpi, self._normalize_bw = make_mask_mpi, normalize_bw
+
+    def _materialise(self):
+        if self._done:
+            return
+        super()._materialise()
+        K = dict.__getitem__(self, "mpi").shape[-2]
+        if self._normalize_bw:
+            bw = dict.__getitem__(self, "blend_weight")
+            dict.__setitem__(self, "blend_weight", bw / dict.__getitem__(self, "alpha").detach().clamp_min(1e-10)[..., None])
+        if self._make_mask_mpi is not None:
+            dict.__setitem__(self, "loopmask3d", self._make_mask_mpi()[..., :K, :1])
+
+
+class MPMesh(nn.Module):
+    """State contract (reference: MPI.py:38-124): parameters `atlas (1,4,Ha,Wa)`, `atlas_mask (1,1,Ha,Wa)` (with
+    `learn_loop_mask`), `uvs`, `_verts`; buffers `ref_extrin`, `ref_intrin`, `planedepth`, `faces`, `uvfaces`.  A fresh
+    model is dense: plane d occupies cell (d // grid_w, d % grid_w) of the atlas."""
+
+    def __init__(self, args, H, W, ref_extrin, ref_intrin, near, far):
+        super().__init__()
+        if getattr(args, "rgb_mlp_type", "direct") != "direct":
+            raise Vl3dError("rgb_mlp_type != 'direct' (view-dependent spherical harmonics) is not supported by the vl3d kernels")
+        if args.rgb_activate != "sigmoid" or args.alpha_activate != "sigmoid":
+            raise Vl3dError("non-sigmoid activations are not supported by the vl3d kernels")
+        if args.mpi_d > 32:
+            raise Vl3dError("mpi_d > 32 is not supported by the composite kernel")
+        assert args.mpi_d % args.atlas_grid_h == 0, "mpi_d and atlas_grid_h should match"
+        self.args = args
+        self.upsample_stage = getattr(args, "upsample_stage", "")
+        D, hv, wv = args.mpi_d, args.mpi_h_verts, args.mpi_w_verts
+        mpi_h, mpi_w = int(args.mpi_h_scale * H), int(args.mpi_w_scale * W)
+        self.mpi_d, self.near, self.far = D, near, far
+        self.mpi_h_verts, self.mpi_w_verts, self.mpi_h, self.mpi_w, self.H, self.W = hv, wv, mpi_h, mpi_w, H, W
+        self.atlas_grid_h, self.atlas_grid_w = args.atlas_grid_h, D // args.atlas_grid_h
+        self.is_sparse = self.has_dyn = False
+        self.atlas_full_h, self.atlas_full_w = int(self.atlas_grid_h * mpi_h), int(self.atlas_grid_w * mpi_w)
+        ref_extrin, ref_intrin = np.asarray(ref_extrin), np.asarray(ref_intrin)
+        assert ref_extrin.shape == (4, 4) and ref_intrin.shape == (3, 3)
+        self.register_buffer("ref_extrin", torch.tensor(ref_extrin))
+        self.register_buffer("ref_intrin", torch.tensor(ref_intrin).float())
+        self.register_buffer("planedepth", make_depths(D, near, far).float().flip(0))
+        self.H_start, self.W_start = (mpi_h - H) // 2, (mpi_w - W) // 2
+        verts = gen_mpi_vertices(mpi_h, mpi_w, get_new_intrin(self.ref_intrin, -self.H_start, -self.W_start), hv, wv,
+                                 self.planedepth)
+        if args.normalize_verts:
+            verts = (verts.reshape(D, -1) / self.planedepth[:, None]).reshape_as(verts)
+        quads = torch.from_numpy(tiles.quad_grid_faces(D, hv, wv))
+        self.register_buffer("uvfaces", quads.clone())
+        self._verts = nn.Parameter(verts, requires_grad=True)
+        self.register_buffer("faces", quads)
+        self.optimize_geometry = False
+        uv = tiles.dense_atlas_uvs(self.atlas_grid_h, self.atlas_grid_w, hv, wv)
+        self.register_parameter("uvs", nn.Parameter(uv, requires_grad=True))
+        self.rgb_mlp_type, self.use_viewdirs = "direct", False
+        atlas = torch.rand((1, 4, self.atlas_full_h, self.atlas_full_w))       # the constructor's only RNG draw (MPI.py:102)
+        atlas[:, -1] = ALPHA_INIT_VAL
+        self.register_parameter("atlas", nn.Parameter(ops.as_texels(atlas), requires_grad=True))
+        if args.learn_loop_mask:
+            self.register_parameter("atlas_mask", nn.Parameter(torch.ones_like(atlas[:, :1]) * ALPHA_INIT_VAL, requires_grad=True))
+        self._pack = self._pack_key = self._ref_inv = None
+
+    # ------------------------------------------------------------------ geometry cache
+    @property
+    def verts(self):
+        verts = self._verts
+        if self.args.normalize_verts:
+            verts = (verts.reshape(len(self.planedepth), -1) * self.planedepth[:, None]).reshape_as(verts)
+        return verts
+
+    def invalidate_geometry(self):
+        self._pack = self._ref_inv = None
+
+    def ref_extrin_inv_host(self):
+        key = (self.ref_extrin.data_ptr(), self.ref_extrin._version)
+        if self._ref_inv is None or self._ref_inv[0] != key:
+            self._ref_inv = (key, np.linalg.inv(self.ref_extrin.detach().double().cpu().numpy()))
+        return self._ref_inv[1]
+
+    def _texels(self):
+        t = ops.as_texels(self.atlas.data)
+        if t is not self.atlas.data:
+            self.atlas.data = t
+        return self.atlas
+
+    def mesh_pack(self):
+        key = (self.faces.data_ptr(), self.uvs.data_ptr(), self._verts.data_ptr(), tuple(self.atlas.shape), self.uvs._version,
+               self._verts._version, str(self.atlas.device))
+        if self._pack is None or key != self._pack_key:
+            if not self.atlas.is_cuda:
+                raise Vl3dError("MPMesh must be moved to a CUDA device before rendering (no CPU fallback)")
+            none3 = torch.zeros(0, 3, dtype=torch.long)
+            self._pack = ops.make_mesh_pack(
+                dict(verts=self.verts, faces=self.faces, uvs=self.uvs, uvfaces=self.uvfaces, atlas_hw=tuple(self.atlas.shape[-2:]),
+                     faces_dyn=none3, uvs_dyn=torch.zeros(0, 2), uvfaces_dyn=none3, atlas_dyn_hw=(1, 1)),
+                self.mpi_d, self.mpi_h_verts, self.mpi_w_verts, self.atlas.device)
+            self._pack_key = key
+            self._no_dyn = torch.zeros((1, 4, 1, 1), dtype=torch.float32, device=self.atlas.device)
+        return self._pack
+
+    def _bg_color(self):
+        bg = getattr(self.args, "bg_color", "")
+        if len(bg) == 0:
+            return None
+        if bg == "random":
+            return torch.rand(3)                                    # CPU generator, like the reference (MPI.py:555)
+        return torch.tensor([float(v) for v in bg.split('#')], dtype=torch.float32)
+
+    # ------------------------------------------------------------------ render / forward
+    def render(self, H, W, extrin, intrin):
+        """rgbl (1,H,W,3 or 4), variables  (reference: MPI.py:452-594).  `extrin`: ref -> target, (1,4,4)."""
+        if len(extrin) != 1:
+            raise Vl3dError("MPMesh.render takes one view per call (the reference's batching does not run either, MPI.py:472)")
+        if self.has_dyn:
+            raise Vl3dError("a sparsified stage-1 model with dynamic tiles is a stage-2 input: load it with MPMeshVid.init_from_mpi")
+        args = self.args
+        if getattr(args, "add_uv_noise", False) and self.training:
+            raise NotImplementedError("add_uv_noise is off in every shipped config and not supported")
+        atlas = self._texels()
+        pack = self.mesh_pack()
+        view = ops.make_view(pack, H, W, extrin, intrin, np.eye(4), (1, 1), tuple(atlas.shape[-2:]))
+        train = self.training
+        w_of = lambda k: getattr(args, f"{k}_loss_weight", 0) if train else 0
+        smooth = w_of("rgb_smooth") > 0 or w_of("a_smooth") > 0
+        rgb, _, sums = ops.CompositeFn.apply(self._no_dyn, atlas, view, pack, None, 1, 0, smooth)
+        span = 1.0 / self.near - 1.0 / self.far                     # MPI.py:552-553: (1/z - 1/far) / (1/near - 1/far)
+        inv_depth = ops.make_inv_depth(pack, H, W, extrin, intrin, np.eye(4), scale=1.0 / span, offset=-1.0 / (self.far * span))
+        alpha, disp, sp_sum = ops.CompositeTermsFn.apply(self._no_dyn, atlas, view, pack, None, 1, inv_depth, 1e-6, True,
+                                                         w_of("sparsity") > 0)
+        bg = self._bg_color()
+        if bg is not None:                                          # MPI.py:554-560
+            a = alpha[:, None]
+            rgb = rgb * a + bg.to(rgb)[None, :, None, None] * (-a + 1)
+        normalize_bw = bool(getattr(args, "normalize_blendweight_fordepth", False))
+        if normalize_bw:                                            # MPI.py:563-566
+            disp = disp / alpha.clamp_min(1e-10)
+        rgbl = rgb.permute(0, 2, 3, 1)
+        make_mask_mpi, lsums = None, None
+        if args.learn_loop_mask:                                    # MPI.py:568-580
+            mask_texels = self._mask_texels(atlas)
+            lab, _, lsums = ops.CompositeFn.apply(self._no_dyn, mask_texels, view, pack, None, 1, 0, w_of("l_smooth") > 0)
+            rgbl = torch.cat([rgbl, lab[:, :1].permute(0, 2, 3, 1)], dim=-1)
+
+            def make_mask_mpi():
+                with torch.no_grad():
+                    return ops.composite_fwd(view, pack, self._no_dyn, mask_texels.detach(), None, 1, 0, want_mpi=True)[2]
+
+        def make_mpi():
+            with torch.no_grad():
+                _, _, mpi, hits = ops.composite_fwd(view, pack, self._no_dyn, atlas.detach(), None, 1, 0, want_mpi=True, want_hits=True)
+            return mpi, hits
+
+        variables = Stage1Variables({"disp_norm": disp, "alpha": alpha}, make_mpi, make_mask_mpi, normalize_bw)
+        variables.train_sums = dict(smooth=sums, sparsity=sp_sum, l_smooth=lsums)   # consumed by forward()
+        return rgbl, variables
+
+    def _mask_texels(self, atlas):
+        """(mask, mask, mask, alpha.detach()) as an RGBA-interleaved texel tensor, differentiable w.r.t. `atlas_mask`."""
+        fake = torch.cat([self.atlas_mask.expand(-1, 3, -1, -1), atlas[:, 3:4].detach()], dim=1)
+        return ops.as_texels(fake.contiguous(memory_format=torch.channels_last))
+
+    def forward(self, h, w, tar_extrins, tar_intrins):
+        """(rgbl (1,C,h,w), extra) with extra = {sparsity, rgb_smooth, a_smooth, d_smooth, l_smooth, density}, each (1,1), in
+        training mode and {} otherwise (reference: MPI.py:596-652)."""
+        tar = tar_extrins.detach().double().cpu().numpy() if torch.is_tensor(tar_extrins) else np.asarray(tar_extrins, np.float64)
+        extrins = tar.reshape(-1, 4, 4) @ self.ref_extrin_inv_host()
+        rgbl, variables = self.render(h, w, extrins, tar_intrins)
+        rgbl = rgbl.permute(0, 3, 1, 2)
+        extra = {}
+        if not self.training:
+            return rgbl, extra
+        args, D = self.args, self.mpi_d
+        ts = variables.train_sums
+        nx, ny = max(h * (w - 1), 1) * D, max((h - 1) * w, 1) * D    # mean over (1,H,W-1,K,c) times K/D: K cancels
+        if args.sparsity_loss_weight > 0:                           # MPI.py:603-607
+            extra["sparsity"] = (ts["sparsity"] / (h * w) / np.sqrt(D)).float().reshape(1, -1)
+        if args.rgb_smooth_loss_weight > 0:                         # MPI.py:609-615
+            extra["rgb_smooth"] = (ts["smooth"][0] / (3 * nx) + ts["smooth"][1] / (3 * ny)).float().reshape(1, -1)
+        if args.a_smooth_loss_weight > 0:                           # MPI.py:617-623
+            extra["a_smooth"] = (ts["smooth"][2] / nx + ts["smooth"][3] / ny).float().reshape(1, -1)
+        if args.d_smooth_loss_weight > 0:                           # MPI.py:625-638
+            disp = variables["disp_norm"]
+            depth_grad = (disp[:, 1:, :-1] - disp[:, 1:, 1:]).abs() + (disp[:, :-1, 1:] - disp[:, 1:, 1:]).abs()
+            rgb = rgbl[:, :3]
+            edge = ((rgb[..., 1:, :-1] - rgb[..., 1:, 1:]).abs().sum(dim=1) + (rgb[..., :-1, 1:] - rgb[..., 1:, 1:]).abs().sum(dim=1))
+            weight = (-edge * args.edge_scale + 1).clamp_min(0)
+            extra["d_smooth"] = (depth_grad * weight).mean().reshape(1, -1)
+        if getattr(args, "l_smooth_loss_weight", 0) > 0 and ts["l_smooth"] is not None:   # MPI.py:640-646
+            extra["l_smooth"] = (ts["l_smooth"][0] / (3 * nx) + ts["l_smooth"][1] / (3 * ny)).float().reshape(1, -1)
+        if args.density_loss_weight > 0:                            # MPI.py:648-651
+            extra["density"] = (variables["alpha"] - 1).abs().mean().reshape(1, -1)
+        return rgbl, extra

@@ -50,6 +50,21 @@ def default_args(**overrides):
     return Namespace(**a)
 
 
+def default_args_stage1(**overrides):
+    """Namespace with the flags `MPMesh` reads; defaults = config_parser.py defaults overlaid with configs/mpi_base.txt."""
+    a = dict(
+        mpi_h_scale=1.6, mpi_w_scale=1.6, mpi_h_verts=36, mpi_w_verts=64, mpi_d=32, atlas_grid_h=4, atlas_size_scale=1,
+        normalize_verts=False, upsample_stage="", learn_loop_mask=True, rgb_mlp_type="direct", rgb_activate="sigmoid",
+        alpha_activate="sigmoid", bg_color="", add_uv_noise=False, normalize_blendweight_fordepth=False, edge_scale=4.0,
+        sparsity_loss_weight=0.004, rgb_smooth_loss_weight=0.2, a_smooth_loss_weight=0.5, density_loss_weight=0.02,
+        d_smooth_loss_weight=0.0, l_smooth_loss_weight=0.0, scale_invariant=True, add_intrin_noise=True,
+        optimizer="adam", lrate=0.05, lrate_decay=100, optimize_verts_gain=1.0,
+        patch_h_size=180, patch_w_size=320, patch_h_stride=90, patch_w_stride=160,
+    )
+    a.update(overrides)
+    return Namespace(**a)
+
+
 def loss_config(args, ref_view: bool):
     """The two per-view loss configs built in train_3dvid.py:163-190."""
     if ref_view:
