@@ -691,6 +691,66 @@ def measure_main(args, world, rank, local, dev, group, barrier, extras):
     return line
 
 
+def stage1_step(dev):
+    """SURVEY §8(f) N4, second half: one optimisation step of the stage-1 model at configs/mpi_base.txt's shape (D=32,
+    36x64 vertices, scale 1.6, 180x320 patch; loop mask, sparsity / smoothness / density terms on) through `MPMesh` +
+    `FusedAdam`, next to the oracle port of the same forward + backward on the host (one repetition, 90x160 patch x 4)."""
+    from oracle import mpv_oracle as MO
+    from videoloop3d_b200 import FusedAdam, MPMesh, default_args_stage1
+    H, W = 180, 320
+    args = default_args_stage1(d_smooth_loss_weight=0.0, l_smooth_loss_weight=0.05)
+    f = 0.8 * W
+    intr0 = np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32)
+    torch.manual_seed(2)
+    m = MPMesh(args, H, W, np.eye(4, dtype=np.float32), intr0, 1.0, 10.0).to(dev).train()
+    m.atlas.data[:, 3] = torch.randn(m.atlas.shape[-2:], device=dev) - 1.0
+    m.atlas_mask.data.normal_()
+    opt = FusedAdam([m.atlas, m.atlas_mask], lr=args.lrate, betas=(0.9, 0.999), eps=1e-8)
+    ext, intr = view_for(dict(H=H, W=W))
+    gen = torch.Generator(device=dev).manual_seed(3)
+    tar = torch.rand((1, 4, H, W), device=dev, generator=gen)
+    weights = {k: getattr(args, k + "_loss_weight") for k in ("sparsity", "rgb_smooth", "a_smooth", "density", "l_smooth")}
+
+    def step():
+        rgbl, extra = m(H, W, ext, intr)
+        loss = ((rgbl - tar) ** 2).mean()
+        for k, v in extra.items():
+            loss = loss + v.mean() * weights[k]
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = 20
+    for _ in range(n):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    gpu_ms = e0.elapsed_time(e1) / n
+    # CPU: the oracle restatement of the same forward + backward on a quarter-size patch (scaled by the pixel ratio)
+    hq, wq = H // 2, W // 2
+    st, mask = MO.stage1_state(hq, wq, 32, 36, 64, 4, 1.0, 10.0, 1.6, 1.6, seed=2)
+    extq, intrq = view_for(dict(H=hq, W=wq))
+    torch.set_num_threads(os.cpu_count() or 1)
+    a = st.atlas.float().requires_grad_(True)
+    am = mask.float().requires_grad_(True)
+    t0 = time.perf_counter()
+    rgbl_o, extra_o, _ = MO.forward_stage1(st, hq, wq, extq.cpu(), intrq.cpu(), 1.0, 10.0, d_smooth=False, atlas=a, atlas_mask=am,
+                                           dtype=torch.float32)
+    lo = (rgbl_o ** 2).mean() + sum(extra_o[k] * weights[k] for k in extra_o)
+    lo.backward()
+    cpu_ms = (time.perf_counter() - t0) * 1e3 * (H * W) / (hq * wq)
+    return {"workload": "stage-1 MPMesh step (configs/mpi_base.txt: D=32, 36x64 vertices, scale 1.6, 180x320 patch, loop mask, "
+                        "sparsity / rgb_smooth / a_smooth / density / l_smooth) through MPMesh.forward + backward + FusedAdam",
+            "ms_per_step": gpu_ms, "steps_per_s": 1000.0 / gpu_ms, "final_loss": float(loss),
+            "cpu_port_ms_per_step": cpu_ms, "cpu_sample": f"oracle forward + backward of one {hq}x{wq} patch x {H * W // (hq * wq)}, "
+                                                            f"{os.cpu_count() or 1} threads (no Adam)"}
+
+
 def measure_extras(args, world, rank, dev, group, barrier):
     """Further workloads of the same path (all ranks take part in the sharded ones; the rest is N = 1 only)."""
     from videoloop3d_b200 import FusedLoopStep
@@ -742,6 +802,9 @@ def measure_extras(args, world, rank, dev, group, barrier):
     more["loss_sweep_ms"].update(loss_sweep(dev, extents=((720, 1280),), Ts=(48,), n2s=(256,)))
     torch.cuda.empty_cache()
     more["config0"] = config0_static_render(dev)
+    torch.cuda.empty_cache()
+    more["stage1"] = stage1_step(dev)
+    torch.cuda.empty_cache()
     # ---- the reference's torch operator sequence on this same GPU (the north_star's ">= 10x" denominator)
     if not args.no_gpu_reference:
         torch.cuda.empty_cache()
