@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--alpha", type=float, default=0.0)
     ap.add_argument("--search", default="0")
     ap.add_argument("--vote", default="0")
+    ap.add_argument("--dump", default="", help="save the NN map here (A/B across processes: VL3D_LIB=... builds)")
+    ap.add_argument("--check", default="", help="compare the NN map with one saved by --dump")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(1)
@@ -63,6 +65,11 @@ def main():
         print(f"search variant {v}: {ms:8.3f} ms   indices differing from variant {a.search.split(',')[0]}: "
               f"{int((nn != ref).sum())} / {nn.numel()}", flush=True)
     os.environ.pop("VL3D_NN_VARIANT", None)
+    if a.dump:
+        torch.save(ref.cpu(), a.dump)
+    if a.check:
+        other = torch.load(a.check)
+        print(f"indices differing from {a.check}: {int((ref.cpu() != other).sum())} / {ref.numel()}", flush=True)
     gref = None
     for v in a.vote.split(","):
         os.environ["VL3D_VOTE_VARIANT"] = v
