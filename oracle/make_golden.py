@@ -439,6 +439,42 @@ def golden_stage1(name, H=24, W=40, D=4, hv=5, wv=7, seed=8, loop_mask=True, **a
     print(name, {k: float(v) for k, v in extra.items()}, "loss", float(loss))
 
 
+def golden_sparsify(name, H=32, W=48, D=4, hv=9, wv=13, seed=12):
+    """Tile culling (`MPI.MPMesh.sparsify_faces`, MPI.py:289-442) of the unmodified reference on a stage-1 model whose
+    alpha / loop-mask logits are blobs on the untouched initial value: the state dict after culling (what stage 2
+    loads) and a render of the culled model."""
+    import MPI  # reference
+    args = ref_env.make_args(config="configs/mpi_base.txt", mpi_d=D, mpi_h_verts=hv, mpi_w_verts=wv, atlas_grid_h=2,
+                             mpi_h_scale=1.0, mpi_w_scale=1.0)
+    f = 0.8 * W
+    ref_intrin = np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32)
+    torch.manual_seed(seed)
+    m = MPI.MPMesh(args, H, W, np.eye(4, dtype=np.float32), ref_intrin, 1.0, 10.0)
+    g = torch.Generator().manual_seed(seed)
+    Ha, Wa = m.atlas.shape[-2:]
+    atlas = m.atlas.data.clone()
+    mask = m.atlas_mask.data.clone()
+    for _ in range(40):                                             # blobs of real content on the -3 background
+        y, x = int(torch.randint(0, Ha - 6, (1,), generator=g)), int(torch.randint(0, Wa - 8, (1,), generator=g))
+        hh, ww = int(torch.randint(3, 7, (1,), generator=g)), int(torch.randint(4, 9, (1,), generator=g))
+        atlas[:, 3, y:y + hh, x:x + ww] = torch.randn((hh, ww), generator=g) + 1.0
+        if torch.rand(1, generator=g) < 0.5:
+            mask[:, 0, y:y + hh, x:x + ww] = torch.randn((hh, ww), generator=g) + 2.0
+    m.atlas.data, m.atlas_mask.data = atlas.clone(), mask.clone()
+    m.sparsify_faces(erode_num=1, alpha_thresh=0.05)
+    sd = m.state_dict()
+    ext, intr = _view(seed, H, W)
+    m.eval()
+    with torch.no_grad():
+        rgbl, _ = m(H, W, ext, intr)
+    key = lambda k: k.replace("self.", "self_")
+    out = {"sd_" + key(k): v for k, v in sd.items()}
+    out.update(H=H, W=W, D=D, hv=hv, wv=wv, atlas0=atlas, atlas_mask0=mask, erode_num=1, alpha_thresh=0.05, tar_extrin=ext,
+               tar_intrin=intr, rgbl=rgbl)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(out))
+    print(name, {k: (tuple(v.shape) if torch.is_tensor(v) else v) for k, v in sd.items() if "atlas" in k or "faces" in k})
+
+
 def main():
     assert ref_env.reference_available(), "needs /root/reference"
     ref_env.enable()
@@ -456,6 +492,7 @@ def main():
     terms = dict(sparsity_loss_weight=0.004, density_loss_weight=0.02, d_smooth_loss_weight=0.1)
     golden_step("step_dense_terms", "dense", LOSS_CFG_REF, seed=4, args=dict(bg_color="0.2#0.5#0.9", **terms))
     golden_step("step_sparse_terms", "sparse", LOSS_CFG_OTHER, seed=6, D=6, hv=6, wv=9, args=terms)   # (seed 5 has an NN near-tie)
+    golden_sparsify("stage1_sparsify")
     golden_stage1("stage1_loopmask", d_smooth_loss_weight=0.1, l_smooth_loss_weight=0.05, edge_scale=0.5)
     golden_stage1("stage1_bg_normdepth", seed=9, loop_mask=False, d_smooth_loss_weight=0.1, bg_color="0.9#0.1#0.4",
                   normalize_blendweight_fordepth=True, edge_scale=0.5)

@@ -129,6 +129,63 @@ def test_stage1_matches_oracle_on_other_views(vname):
         assert float(err.max()) < 0.5 * float(ref.abs().max()), (name, float(err.max()))
 
 
+def test_culled_stage1_model_renders_like_the_reference():
+    """After `sparsify_faces` (run on the GPU here) the stage-1 model carries static + one-frame dynamic tiles: its render
+    equals the unmodified reference's render of ITS culled model (golden), and value / gradients of a training forward
+    equal the oracle's on the culled state."""
+    from videoloop3d_b200 import MPMesh, default_args_stage1
+    g = load_golden("stage1_sparsify")
+    H, W, D, hv, wv = (int(g[k]) for k in ("H", "W", "D", "hv", "wv"))
+    args = default_args_stage1(mpi_d=D, mpi_h_verts=hv, mpi_w_verts=wv, atlas_grid_h=2, mpi_h_scale=1.0, mpi_w_scale=1.0,
+                               d_smooth_loss_weight=0.1)
+    f = 0.8 * W
+    m = MPMesh(args, H, W, np.eye(4, dtype=np.float32), np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32),
+               1.0, 10.0)
+    m.atlas.data = torch.as_tensor(g["atlas0"]).clone()
+    m.atlas_mask.data = torch.as_tensor(g["atlas_mask0"]).clone()
+    m = m.to(dev())
+    info = m.sparsify_faces(erode_num=int(g["erode_num"]), alpha_thresh=float(g["alpha_thresh"]))
+    assert info["kept"] == (len(g["sd_faces"]) + len(g["sd_faces_dyn"])) // 2 and info["dynamic"] == len(g["sd_faces_dyn"]) // 2
+    assert torch.equal(m.faces.cpu(), torch.as_tensor(g["sd_faces"]).long())
+    assert float((m.atlas_dyn.detach().cpu() - torch.as_tensor(g["sd_atlas_dyn"])).abs().max()) < 1e-5
+    ext, intr = torch.as_tensor(g["tar_extrin"]), torch.as_tensor(g["tar_intrin"])
+    m.eval()
+    with torch.no_grad():
+        rgbl, extra = m(H, W, ext.to(dev()), intr.to(dev()))
+    assert extra == {} and tuple(rgbl.shape) == tuple(g["rgbl"].shape)
+    assert relerr(rgbl.cpu(), g["rgbl"]) < RTOL
+    # training forward on the culled model against the oracle
+    sd = {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in m.state_dict().items()}
+    st = MO.MPVState.from_state_dict(sd, D, hv, wv)
+    a = st.atlas.double().requires_grad_(True)
+    ad = st.atlas_dyn.double().requires_grad_(True)
+    rgbl_o, extra_o, var_o = MO.forward_stage1(st, H, W, ext, intr, 1.0, 10.0, atlas=a, atlas_dyn=ad, l_smooth=False)
+    gen = torch.Generator().manual_seed(5)
+    g_up = torch.rand(rgbl_o.shape, generator=gen, dtype=torch.float64) - 0.4
+    # The golden's alpha logits are blobs on a CONSTANT background (the untouched -3 of a fresh stage-1 atlas) and its view
+    # only pans horizontally, so most neighbouring alphas — and vertically neighbouring disparities — are equal in exact
+    # arithmetic: the sign of their difference, i.e. the gradient of a_smooth / d_smooth, is rounding noise in the oracle
+    # (fp64) and in the kernel (fp32) alike (measured: scripts/debug_stage1_culled.py).  Those two are compared by value
+    # here; their gradients on static + dynamic tiles are pinned by tests/test_gpu_terms.py (step_sparse_terms golden).
+    weights = dict(sparsity=args.sparsity_loss_weight, rgb_smooth=args.rgb_smooth_loss_weight, a_smooth=0.0,
+                   density=args.density_loss_weight, d_smooth=0.0)
+    (rgbl_o * g_up).mean().add(sum(extra_o[k] * w for k, w in weights.items())).backward()
+    m.train()
+    rgbl_c, extra_c = m(H, W, ext.to(dev()), intr.to(dev()))
+    assert set(extra_c) == set(weights)
+    for k in weights:
+        assert abs(float(extra_c[k]) - float(extra_o[k])) < RTOL * max(abs(float(extra_o[k])), 1e-3), k
+    ((rgbl_c * g_up.to(dev()).float()).mean() + sum(extra_c[k].mean() * w for k, w in weights.items())).backward()
+    rgb_slots = var_o["mpi"].detach()[..., :3]
+    n_ties = sum(int(((d > 0) & (d < 1e-5)).sum()) for d in ((rgb_slots[:, :, :-1] - rgb_slots[:, :, 1:]).abs(),
+                                                             (rgb_slots[:, :-1] - rgb_slots[:, 1:]).abs()))
+    for name, got, ref in (("atlas", m.atlas.grad, a.grad), ("atlas_dyn", m.atlas_dyn.grad, ad.grad)):
+        err = (got.cpu().double() - ref).abs()
+        bad = int((err > 5e-4 * float(ref.abs().max())).sum())
+        assert bad <= 8 * n_ties, (name, bad, n_ties, float(err.max()))
+        assert float(err.max()) < 0.5 * float(ref.abs().max()), (name, float(err.max()))
+
+
 def test_stage1_refuses_what_it_does_not_cover():
     from videoloop3d_b200 import MPMesh, Vl3dError, default_args_stage1
     g = load_golden("stage1_loopmask")

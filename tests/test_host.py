@@ -418,6 +418,47 @@ def test_stage1_constructor_state_equals_reference_state():
         m.render(H, W, np.eye(4)[None], torch.as_tensor(g["tar_intrin"]))
 
 
+def test_stage1_tile_culling_matches_reference():
+    """`MPMesh.sparsify_faces` + `state_dict` (MPI.py:289-442, 207-221): the same quads kept / made dynamic, the same packed
+    atlases, uv corners and layout scalars as the unmodified reference (tests/golden/stage1_sparsify.npz), i.e. the
+    checkpoint stage 2 loads.  Pure host / torch logic: runs on the CPU here."""
+    from util import ckpt_dict, load_golden
+    from videoloop3d_b200 import MPMesh, default_args_stage1
+    g = load_golden("stage1_sparsify")
+    H, W, D, hv, wv = (int(g[k]) for k in ("H", "W", "D", "hv", "wv"))
+    args = default_args_stage1(mpi_d=D, mpi_h_verts=hv, mpi_w_verts=wv, atlas_grid_h=2, mpi_h_scale=1.0, mpi_w_scale=1.0)
+    f = 0.8 * W
+    m = MPMesh(args, H, W, np.eye(4, dtype=np.float32), np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32),
+               1.0, 10.0)
+    m.atlas.data = torch.as_tensor(g["atlas0"]).clone()
+    m.atlas_mask.data = torch.as_tensor(g["atlas_mask0"]).clone()
+    info = m.sparsify_faces(erode_num=int(g["erode_num"]), alpha_thresh=float(g["alpha_thresh"]))
+    ref = ckpt_dict(g, "sd_")
+    sd = m.state_dict()
+    assert set(sd) == set(ref)
+    assert info["kept"] == (len(ref["faces"]) + len(ref["faces_dyn"])) // 2 and info["dynamic"] == len(ref["faces_dyn"]) // 2
+    for k in ("faces", "faces_dyn", "uvfaces", "uvfaces_dyn"):
+        assert torch.equal(sd[k], ref[k].long()), k
+    for k in ("uvs", "uvs_dyn", "_verts", "planedepth", "ref_extrin", "ref_intrin"):
+        assert torch.allclose(sd[k], ref[k], rtol=0, atol=1e-6), k
+    for k in ("atlas", "atlas_dyn"):
+        assert tuple(sd[k].shape) == tuple(ref[k].shape) and float((sd[k] - ref[k]).abs().max()) < 1e-5, k
+    for k in sd:
+        if k.startswith("self."):
+            assert sd[k] == ref[k], k
+    assert m.has_dyn and m.is_sparse and not hasattr(m, "atlas_mask") and m.args.learn_loop_mask is False
+    with pytest.raises(Exception, match="culled already"):
+        m.sparsify_faces()
+    # ... and it is exactly what the stage-2 model loads (MPV.py:235-262)
+    from videoloop3d_b200 import MPMeshVid, default_args
+    args2 = default_args(mpi_d=D, mpi_h_verts=hv, mpi_w_verts=wv, atlas_grid_h=2, mpv_frm_num=3, mpi_h_scale=1.0, mpi_w_scale=1.0)
+    m2 = MPMeshVid(args2, H, W, np.eye(4, dtype=np.float32), np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32),
+                   1.0, 10.0)
+    m2.init_from_mpi(sd)
+    assert tuple(m2.atlas_dyn.shape) == (3,) + tuple(ref["atlas_dyn"].shape[1:]) and torch.equal(m2.faces_dyn, sd["faces_dyn"])
+    assert MPMesh._tile_grid(274 - 77) == (9, 22, 1) and MPMesh._tile_grid(77) == (6, 13, 1)
+
+
 def test_argument_validation_of_the_round2_entry_points():
     """vl3d_copy_boxes / vl3d_fused_bwd_adam_own / the sizing helpers reject bad arguments before touching the device."""
     lib = _lib.load()
