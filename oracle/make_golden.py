@@ -439,6 +439,51 @@ def golden_stage1(name, H=24, W=40, D=4, hv=5, wv=7, seed=8, loop_mask=True, **a
     print(name, {k: float(v) for k, v in extra.items()}, "loss", float(loss))
 
 
+def golden_stage1_step(name, H=24, W=40, D=4, hv=5, wv=7, seed=14, lr=0.05):
+    """One optimisation step of the stage-1 trainer: the body of `run_iter` (train_3d.py:189-236: scale-invariant MSE +
+    loop-mask cross-entropy + weighted extra terms, backward, Adam) executed on the unmodified reference model."""
+    import MPI  # reference
+    args = ref_env.make_args(config="configs/mpi_base.txt", mpi_d=D, mpi_h_verts=hv, mpi_w_verts=wv, atlas_grid_h=2,
+                             mpi_h_scale=1.2, mpi_w_scale=1.2, add_intrin_noise=False, lrate=lr)
+    f = 0.8 * W
+    ref_intrin = np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32)
+    torch.manual_seed(seed)
+    m = MPI.MPMesh(args, H, W, np.eye(4, dtype=np.float32), ref_intrin, 1.0, 10.0)
+    st, atlas_mask = MO.stage1_state(H, W, D, hv, wv, 2, 1.0, 10.0, 1.2, 1.2, seed=seed)
+    m.atlas.data, m.atlas_mask.data = st.atlas.clone(), atlas_mask.clone()
+    ext, intr = _view(seed, H, W)
+    pose = torch.inverse(ext)[:, :3, :]                                  # run_iter receives poses (train_3d.py:191)
+    g = torch.Generator().manual_seed(seed + 1)
+    b_rgbs = torch.rand(1, 3, H, W, generator=g)
+    b_loopmask = (torch.rand(1, H, W, generator=g) > 0.5).float()
+    opt = m.get_optimizer()
+    import utils  # reference
+    m.train()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rgb, extra = m(H, W, utils.pose2extrin_torch(pose), intr)
+    loop_mask = torch.clamp(rgb[:, -1], 0.001, 1 - 0.001)                # train_3d.py:201-212
+    loop_loss = -(b_loopmask * torch.log(loop_mask) + (1 - b_loopmask) * torch.log(1 - loop_mask)).mean()
+    rgb = rgb[:, :3]
+    scale = torch.exp(torch.log((b_rgbs + 0.01) / (rgb.detach() + 0.01)).mean())   # train_3d.py:217-220
+    rgb = rgb * ((scale + 3) / 4)
+    img_loss = utils.img2mse(rgb, b_rgbs)
+    loss = img_loss + loop_loss
+    for k, v in extra.items():
+        w = getattr(args, f"{k}_loss_weight")
+        if w > 0:
+            loss = loss + v.mean() * w
+    opt.zero_grad()
+    loss.backward()
+    g_atlas, g_mask = m.atlas.grad.clone(), m.atlas_mask.grad.clone()
+    opt.step()
+    out = dict(H=H, W=W, lr=lr, pose=pose, tar_intrin=intr, rgb=b_rgbs, loopmask=b_loopmask, loss=loss.detach(),
+               img_loss=img_loss.detach(), loop_loss=loop_loss.detach(), grad_atlas=g_atlas, grad_atlas_mask=g_mask,
+               new_atlas=m.atlas.data, new_atlas_mask=m.atlas_mask.data, atlas_mask=atlas_mask, **_state_arrays(st))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(out))
+    print(name, "loss", float(loss), "img", float(img_loss), "loop", float(loop_loss))
+
+
 def golden_sparsify(name, H=32, W=48, D=4, hv=9, wv=13, seed=12):
     """Tile culling (`MPI.MPMesh.sparsify_faces`, MPI.py:289-442) of the unmodified reference on a stage-1 model whose
     alpha / loop-mask logits are blobs on the untouched initial value: the state dict after culling (what stage 2
@@ -493,6 +538,7 @@ def main():
     golden_step("step_dense_terms", "dense", LOSS_CFG_REF, seed=4, args=dict(bg_color="0.2#0.5#0.9", **terms))
     golden_step("step_sparse_terms", "sparse", LOSS_CFG_OTHER, seed=6, D=6, hv=6, wv=9, args=terms)   # (seed 5 has an NN near-tie)
     golden_sparsify("stage1_sparsify")
+    golden_stage1_step("stage1_step")
     golden_stage1("stage1_loopmask", d_smooth_loss_weight=0.1, l_smooth_loss_weight=0.05, edge_scale=0.5)
     golden_stage1("stage1_bg_normdepth", seed=9, loop_mask=False, d_smooth_loss_weight=0.1, bg_color="0.9#0.1#0.4",
                   normalize_blendweight_fordepth=True, edge_scale=0.5)

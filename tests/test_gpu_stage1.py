@@ -186,6 +186,39 @@ def test_culled_stage1_model_renders_like_the_reference():
         assert float(err.max()) < 0.5 * float(ref.abs().max()), (name, float(err.max()))
 
 
+def test_stage1_run_iter_matches_reference_step():
+    """`make_run_iter_stage1` (train_3d.py:189-236) around MPMesh: loss and gradients of one step equal the unmodified
+    reference's (golden stage1_step); with torch's Adam, as `MPMesh.get_optimizer` returns it, the parameters after the
+    step agree as well."""
+    from videoloop3d_b200 import MPMesh, default_args_stage1, make_run_iter_stage1
+    g = load_golden("stage1_step")
+    H, W, D, hv, wv = int(g["H"]), int(g["W"]), int(g["mpi_d"]), int(g["hv"]), int(g["wv"])
+    args = default_args_stage1(mpi_d=D, mpi_h_verts=hv, mpi_w_verts=wv, atlas_grid_h=2, mpi_h_scale=1.2, mpi_w_scale=1.2,
+                               add_intrin_noise=False, lrate=float(g["lr"]))
+    f = 0.8 * W
+    m = MPMesh(args, H, W, np.eye(4, dtype=np.float32), np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32),
+               1.0, 10.0)
+    m.atlas.data, m.atlas_mask.data = torch.as_tensor(g["atlas"]).clone(), torch.as_tensor(g["atlas_mask"]).clone()
+    m = m.to(dev())
+    opt = m.get_optimizer()
+    assert [len(gr["params"]) for gr in opt.param_groups] == [3, 1] and opt.param_groups[0]["betas"] == (0.9, 0.999)
+    seen = {}
+    run_iter = make_run_iter_stage1(args, m, dev(), on_log=lambda i, loss, img, extra: seen.update(loss=loss, img=img, extra=extra))
+    datainfo = (0, 0, torch.as_tensor(g["pose"]), torch.as_tensor(g["tar_intrin"]), torch.as_tensor(g["rgb"]),
+                torch.as_tensor(g["loopmask"]))
+    loss = run_iter(0, opt, datainfo)
+    assert abs(float(loss) - float(g["loss"])) < RTOL * float(g["loss"])
+    assert abs(float(seen["img"]) - float(g["img_loss"])) < RTOL * float(g["img_loss"])
+    assert set(seen["extra"]) == {"sparsity", "rgb_smooth", "a_smooth", "density"}
+    assert relerr(m.atlas.grad.cpu(), g["grad_atlas"]) < 5e-4
+    assert relerr(m.atlas_mask.grad.cpu(), g["grad_atlas_mask"]) < 5e-4
+    # Adam's first step moves every parameter by lr * sign(g) (up to eps): all but the near-zero gradients agree
+    d = (m.atlas.detach().cpu() - torch.as_tensor(g["new_atlas"])).abs()
+    assert float((d > 1e-4).float().mean()) < 2e-3 and float(d.median()) < 1e-6
+    dm = (m.atlas_mask.detach().cpu() - torch.as_tensor(g["new_atlas_mask"])).abs()
+    assert float((dm > 1e-4).float().mean()) < 2e-3
+
+
 def test_stage1_refuses_what_it_does_not_cover():
     from videoloop3d_b200 import MPMesh, Vl3dError, default_args_stage1
     g = load_golden("stage1_loopmask")

@@ -16,6 +16,7 @@ from .mpv import MPMeshVid, get_new_intrin, make_depths, gen_mpi_vertices, pose2
 from .optim import FusedAdam  # noqa: F401
 from .evaluations import compute_nnerr, to8b  # noqa: F401
 from .dataset import MVVidPatchDataset, generate_patchinfo  # noqa: F401
-from .train_step import FusedLoopStep, make_run_iter, default_args, default_args_stage1  # noqa: F401
+from .train_step import (FusedLoopStep, make_run_iter, make_run_iter_stage1, default_args,  # noqa: F401
+                         default_args_stage1)
 
 __version__ = "0.1.0"

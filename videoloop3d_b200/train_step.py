@@ -112,6 +112,48 @@ def make_run_iter(args, nerf, device, writer=None, on_log=None):
     return run_iter
 
 
+def make_run_iter_stage1(args, nerf, device, on_log=None):
+    """Reference-shaped stage-1 `run_iter(stepi, optimizer_, datainfo_)` (train_3d.py:189-236) around an `MPMesh`:
+    `datainfo_ = (h_start, w_start, pose (1,3,4), intrin (1,3,3), rgb (1,3,h,w), loopmask (1,h,w))`; loss = scale-invariant
+    MSE + cross-entropy of the rendered loop-mask label + the weighted extra terms.  The render and every regulariser run
+    in libvl3d; the image / label losses are a handful of element-wise ops on one (1,4,h,w) image."""
+
+    def run_iter(stepi, optimizer_, datainfo_):
+        datainfo_ = [d.to(device) if torch.is_tensor(d) else d for d in datainfo_]
+        h_starts, w_starts, b_pose, b_intrin, b_rgbs, b_loopmask = datainfo_
+        b_extrin = pose2extrin_torch(b_pose)
+        patch_h, patch_w = b_rgbs.shape[-2:]
+        if args.add_intrin_noise:
+            dxy = torch.rand(2).type_as(b_intrin) - 0.5          # half pixel (train_3d.py:194-197)
+            b_intrin = b_intrin.clone()
+            b_intrin[:, :2, 2] += dxy
+        nerf.train()
+        rgb, extra = nerf(patch_h, patch_w, b_extrin, b_intrin)
+        loop_loss = 0
+        if args.learn_loop_mask:                                  # train_3d.py:201-212
+            label = torch.clamp(rgb[:, -1], 0.001, 1 - 0.001)
+            loop_loss = -(b_loopmask * torch.log(label) + (1 - b_loopmask) * torch.log(1 - label)).mean()
+            rgb = rgb[:, :3]
+        if args.scale_invariant:                                  # train_3d.py:217-220
+            scale = torch.exp(torch.log((b_rgbs + 0.01) / (rgb.detach() + 0.01)).mean())
+            rgb = rgb * ((scale + 3) / 4)
+        img_loss = torch.mean((rgb - b_rgbs) ** 2)
+        args_var = vars(args)
+        extra_losses = {k: v.mean() * args_var[f"{k}_loss_weight"] for k, v in extra.items()
+                        if args_var[f"{k}_loss_weight"] > 0}
+        loss = img_loss + loop_loss
+        for v in extra_losses.values():
+            loss = loss + v
+        optimizer_.zero_grad()
+        loss.backward()
+        optimizer_.step()
+        if on_log is not None:
+            on_log(stepi, loss, img_loss, extra_losses)
+        return loss.detach()
+
+    return run_iter
+
+
 def partition(n, world):
     """Contiguous blocks [b[r], b[r+1]) of n units over `world` ranks."""
     return [(n * r) // world for r in range(world + 1)]
