@@ -106,3 +106,80 @@ def test_reference_step_shape_matches_oracle(layout, cfg):
         n_off = int((err > 8 * w_max + 5e-4 * scale).sum())
         assert n_off <= max(64, 2e-4 * ref.numel()), f"{n_off} texel gradients off"
     assert torch.equal(m.atlas_dyn.data.cpu(), st.atlas_dyn.float())         # lr = 0
+
+
+def _tie_budget(*slot_tensors, thr=1e-5):
+    """Neighbouring slot values that tie to within the fp32 sampling noise: the gradient of |a - b| is undefined there; each
+    such pair may move the 2 x 4 texels it taps (see tests/test_gpu_stage1.py)."""
+    n = 0
+    for t in slot_tensors:
+        for d in ((t[:, :, :-1] - t[:, :, 1:]).abs(), (t[:, :-1] - t[:, 1:]).abs()):
+            n += int(((d > 0) & (d < thr)).sum())
+    return 8 * n
+
+
+def test_stage1_step_shape_matches_oracle():
+    """The stage-1 model at configs/mpi_base.txt's shape (D = 32, 36 x 64 vertices, scale 1.6, 180 x 320 patch; loop mask,
+    every extra term on) — forward values and the gradients of atlas / atlas_mask against the oracle's restatement of
+    MPI.py:452-652 (which tests/test_oracle.py pins to the unmodified reference)."""
+    from videoloop3d_b200 import MPMesh, default_args_stage1
+    dev = torch.device("cuda:0")
+    hv, wv = 36, 64
+    st, atlas_mask = MO.stage1_state(H, W, D, hv, wv, 4, 1.0, 10.0, 1.6, 1.6, seed=31, alpha_mean=-2.5)
+    ext, intr = _view()
+    weights = dict(sparsity=0.004, rgb_smooth=0.2, a_smooth=0.5, density=0.02, d_smooth=0.1, l_smooth=0.05)
+    a = st.atlas.double().requires_grad_(True)
+    am = atlas_mask.double().requires_grad_(True)
+    rgbl_o, extra_o, var_o = MO.forward_stage1(st, H, W, ext, intr, 1.0, 10.0, edge_scale=0.5, atlas=a, atlas_mask=am)
+    assert var_o["K"] == D
+    g_up = torch.rand(rgbl_o.shape, generator=torch.Generator().manual_seed(7), dtype=torch.float64) - 0.4
+    ((rgbl_o * g_up).mean() + sum(extra_o[k] * w for k, w in weights.items())).backward()
+    args = default_args_stage1(edge_scale=0.5, **{k + "_loss_weight": w for k, w in weights.items()})
+    f = 0.8 * W
+    m = MPMesh(args, H, W, np.eye(4, dtype=np.float32), np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32),
+               1.0, 10.0)
+    assert torch.equal(m.faces, st.faces) and torch.allclose(m.uvs.data, st.uvs, atol=1e-7) and tuple(m.atlas.shape) == tuple(st.atlas.shape)
+    m.atlas.data, m.atlas_mask.data = st.atlas.clone(), atlas_mask.clone()
+    m = m.to(dev).train()
+    rgbl, extra = m(H, W, ext.to(dev), intr.to(dev))
+    assert float((rgbl.detach().cpu().double() - rgbl_o.detach()).abs().max()) < 1e-4
+    for k in weights:
+        assert abs(float(extra[k]) - float(extra_o[k])) < 1e-4 * max(abs(float(extra_o[k])), 1e-3), k
+    ((rgbl * g_up.to(dev).float()).mean() + sum(extra[k].mean() * w for k, w in weights.items())).backward()
+    budget = _tie_budget(var_o["mpi"].detach(), var_o["loopmask3d"].detach())
+    for name, got, ref in (("atlas", m.atlas.grad, a.grad), ("atlas_mask", m.atlas_mask.grad, am.grad)):
+        err = (got.cpu().double() - ref).abs()
+        bad = int((err > 5e-4 * float(ref.abs().max())).sum())
+        assert bad <= budget, (name, bad, budget, float(err.max()))
+        assert float(err.max()) < 0.5 * float(ref.abs().max()), (name, float(err.max()))
+
+
+def test_optional_terms_at_step_shape_match_oracle():
+    """alpha / disparity / sparsity of the DENSE stage-2 model at the reference's step shape (D = 32, 180 x 320, 4 frames)
+    and the gradients of a random functional of them (csrc/terms.cu) against the oracle."""
+    from videoloop3d_b200.testing import model_from_tensors
+    dev = torch.device("cuda:0")
+    Tt = 4
+    st = MO.dense_state(H, W, D, 27, 48, 4, Tt, 1.0, 10.0, 1.1, 1.1, seed=33, alpha_mean=-2.5)
+    st.atlas = st.atlas[:, :, :1, :1].clone()
+    ext, intr = _view()
+    ts = list(range(Tt))
+    ad = st.atlas_dyn.double().requires_grad_(True)
+    _, var_o = MO.render(st, H, W, ext, intr, ts, atlas_dyn=ad)
+    al = var_o["mpi"][..., -1]
+    sp_o = (al.norm(dim=-1, p=1) / al.norm(dim=-1, p=2).clamp_min(1e-4)).sum()
+    gen = torch.Generator().manual_seed(9)
+    ga = torch.rand(var_o["alpha"].shape, generator=gen, dtype=torch.float64) - 0.3
+    gd = torch.rand(var_o["alpha"].shape, generator=gen, dtype=torch.float64) - 0.5
+    ((var_o["alpha"] * ga).sum() + (var_o["disp_norm"] * gd).sum() + 0.37 * sp_o).backward()
+    m = model_from_tensors(state_tensors(st), H, W, dev)
+    extrin = ext @ torch.inverse(st.ref_extrin)[None]
+    view = m.make_view(H, W, extrin, intr)
+    alpha, disp, sp = m._render_terms(view, m._ts_tensor(ts), Tt, H, W, extrin, intr, want_disp=True, want_sparsity=True)
+    assert float((alpha.detach().cpu().double() - var_o["alpha"].detach()).abs().max()) < 1e-4
+    assert float((disp.detach().cpu().double() - var_o["disp_norm"].detach()).abs().max()) < 1e-4 * float(var_o["disp_norm"].abs().max())
+    assert abs(float(sp) - float(sp_o)) < 1e-4 * float(sp_o)
+    ((alpha * ga.to(dev).float()).sum() + (disp * gd.to(dev).float()).sum() + 0.37 * sp.sum()).backward()
+    err = float((m.atlas_dyn.grad.cpu().double() - ad.grad).abs().max())
+    assert err < 3e-4 * float(ad.grad.abs().max()), err
+    assert float(m.atlas_dyn.grad[:, :3].abs().max()) == 0.0
