@@ -101,7 +101,7 @@ class MPMesh(nn.Module):
         self.register_parameter("atlas", nn.Parameter(ops.as_texels(atlas), requires_grad=True))
         if args.learn_loop_mask:
             self.register_parameter("atlas_mask", nn.Parameter(torch.ones_like(atlas[:, :1]) * ALPHA_INIT_VAL, requires_grad=True))
-        self._pack = self._pack_key = self._ref_inv = None
+        self._pack = self._pack_key = self._ref_inv = self._no_dyn = None
 
     # ------------------------------------------------------------------ geometry cache
     @property
@@ -128,7 +128,11 @@ class MPMesh(nn.Module):
                 t = ops.as_texels(p.data)
                 if t is not p.data:
                     p.data = t
-        return (self.atlas_dyn if self.has_dyn else self._no_dyn), self.atlas
+        if self.has_dyn:
+            return self.atlas_dyn, self.atlas
+        if getattr(self, "_no_dyn", None) is None or self._no_dyn.device != self.atlas.device:
+            self._no_dyn = torch.zeros((1, 4, 1, 1), dtype=torch.float32, device=self.atlas.device)
+        return self._no_dyn, self.atlas
 
     def mesh_pack(self):
         dyn = self.has_dyn
@@ -146,7 +150,6 @@ class MPMesh(nn.Module):
                      atlas_dyn_hw=tuple(self.atlas_dyn.shape[-2:]) if dyn else (1, 1)),
                 self.mpi_d, self.mpi_h_verts, self.mpi_w_verts, self.atlas.device)
             self._pack_key = key
-            self._no_dyn = torch.zeros((1, 4, 1, 1), dtype=torch.float32, device=self.atlas.device)
         return self._pack
 
     def _bg_color(self):
