@@ -154,6 +154,16 @@ def test_culled_stage1_model_renders_like_the_reference():
         rgbl, extra = m(H, W, ext.to(dev()), intr.to(dev()))
     assert extra == {} and tuple(rgbl.shape) == tuple(g["rgbl"].shape)
     assert relerr(rgbl.cpu(), g["rgbl"]) < RTOL
+    # a fresh model resumed from the REFERENCE's own checkpoint (MPI.py:173-205) renders the same frame
+    from util import ckpt_dict
+    m2 = MPMesh(default_args_stage1(mpi_d=D, mpi_h_verts=hv, mpi_w_verts=wv, atlas_grid_h=2, mpi_h_scale=1.0, mpi_w_scale=1.0),
+                H, W, np.eye(4, dtype=np.float32), np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32),
+                1.0, 10.0).to(dev())
+    m2.init_from_mpi(ckpt_dict(g, "sd_"))
+    m2.eval()
+    with torch.no_grad():
+        rgbl2, _ = m2(H, W, ext.to(dev()), intr.to(dev()))
+    assert relerr(rgbl2.cpu(), g["rgbl"]) < RTOL
     # training forward on the culled model against the oracle
     sd = {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in m.state_dict().items()}
     st = MO.MPVState.from_state_dict(sd, D, hv, wv)

@@ -457,6 +457,19 @@ def test_stage1_tile_culling_matches_reference():
     m2.init_from_mpi(sd)
     assert tuple(m2.atlas_dyn.shape) == (3,) + tuple(ref["atlas_dyn"].shape[1:]) and torch.equal(m2.faces_dyn, sd["faces_dyn"])
     assert MPMesh._tile_grid(274 - 77) == (9, 22, 1) and MPMesh._tile_grid(77) == (6, 13, 1)
+    # a fresh stage-1 model resumes from that checkpoint (MPI.py:173-205) ...
+    m3 = MPMesh(default_args_stage1(mpi_d=D, mpi_h_verts=hv, mpi_w_verts=wv, atlas_grid_h=2, mpi_h_scale=1.0, mpi_w_scale=1.0),
+                H, W, np.eye(4, dtype=np.float32), np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32), 1.0, 10.0)
+    m3.init_from_mpi({k: (v.clone() if torch.is_tensor(v) else v) for k, v in ref.items()})
+    sd3 = m3.state_dict()
+    assert set(sd3) == set(ref) and m3.has_dyn and not hasattr(m3, "atlas_mask")
+    for k, v in ref.items():
+        assert (torch.equal(sd3[k], v.to(sd3[k].dtype)) if torch.is_tensor(v) else sd3[k] == v), k
+    # ... and the trainer's per-step hooks exist (train_3d.py:298-301)
+    m3.update_step(1000)
+    assert [n for n, _ in m3.get_lrate(0)] == ["lr", "vertlr"] and abs(m3.get_lrate(100000)[0][1] - 0.1 * m3.args.lrate) < 1e-12
+    with pytest.raises(NotImplementedError):
+        m3.update_step(10 ** 7)
 
 
 def test_argument_validation_of_the_round2_entry_points():

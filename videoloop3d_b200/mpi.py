@@ -264,6 +264,44 @@ class MPMesh(nn.Module):
         scaling = 0.1 ** (step / (args.lrate_decay * 1000))
         return [("lr", args.lrate * scaling), ("vertlr", args.lrate * args.optimize_verts_gain * scaling)]
 
+    def update_step(self, step):
+        """MPI.py:154-157: geometry optimisation would start at `optimize_geo_start` (1e7 in every shipped config)."""
+        if step >= getattr(self.args, "optimize_geo_start", 10000000):
+            raise NotImplementedError("geometry optimisation (optimize_geo_start) is never reached by the shipped configs and is "
+                                      "not supported: the kernels assume fronto-parallel planes of axis-aligned quads")
+
+    def direct2sh(self):
+        raise NotImplementedError("direct2sh (view-dependent spherical harmonics, 'not well tested' in the reference) is not supported")
+
+    def init_from_mpi(self, state_dict):
+        """Load a stage-1 checkpoint written by `state_dict` — dense or culled (MPI.py:173-205)."""
+        sd = state_dict
+        dev = self.atlas.device
+        self._verts.data = sd['_verts'].to(self._verts)
+        self.uvs.data = sd['uvs'].to(self.uvs)
+        self.atlas.data = ops.as_texels(sd['atlas'].to(device=dev, dtype=torch.float32))
+        self.uvfaces.data = sd['uvfaces'].to(self.uvfaces)
+        self.faces.data = sd['faces'].to(self.faces)
+        self.ref_extrin.data = sd['ref_extrin'].to(self.ref_extrin)
+        self.ref_intrin.data = sd['ref_intrin'].to(self.ref_intrin)
+        self.planedepth.data = sd['planedepth'].to(self.planedepth)
+        for k in self._SCALARS:
+            setattr(self, k, sd["self." + k])
+        if "atlas_mask" in sd and hasattr(self, "atlas_mask"):
+            self.atlas_mask.data = sd["atlas_mask"].to(device=dev, dtype=torch.float32)
+        if "self.has_dyn" in sd.keys():
+            for k in self._SCALARS_DYN:
+                setattr(self, k, sd["self." + k])
+            self.register_parameter("uvs_dyn", nn.Parameter(sd['uvs_dyn'].to(self.uvs), requires_grad=True))
+            self.register_buffer("uvfaces_dyn", sd['uvfaces_dyn'].to(self.uvfaces))
+            self.register_buffer("faces_dyn", sd['faces_dyn'].to(self.faces))
+            self.register_parameter("atlas_dyn", nn.Parameter(ops.as_texels(sd['atlas_dyn'].to(device=dev, dtype=torch.float32)),
+                                                              requires_grad=True))
+            if hasattr(self, "atlas_mask"):                         # a culled model has no loop mask any more (MPI.py:440-441)
+                self.args.learn_loop_mask = False
+                del self.atlas_mask
+        self.invalidate_geometry()
+
     # ------------------------------------------------------------------ checkpoint format (MPI.py:207-221)
     _SCALARS = ("is_sparse", "atlas_full_w", "atlas_full_h", "atlas_grid_h", "atlas_grid_w")
     _SCALARS_DYN = ("has_dyn", "atlas_full_dyn_w", "atlas_full_dyn_h", "atlas_grid_dyn_h", "atlas_grid_dyn_w")
