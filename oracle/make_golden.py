@@ -112,6 +112,21 @@ def golden_render(name, kind, H=24, W=40, D=4, hv=5, wv=7, T=3, seed=0, **kw):
     print(name, "K =", var["mpi"].shape[-2], "rgb mean", float(rgb.mean()))
 
 
+def golden_render_bg_random(name, H=24, W=40, D=4, hv=5, wv=7, T=2, seed=16):
+    """`bg_color='random'` (MPV.py:456-457 draws `torch.rand(3)` from the global CPU generator on every render): the
+    eval forward of the unmodified reference under `torch.manual_seed(77)`."""
+    m, st, args = make_model("dense", H, W, D, hv, wv, T, seed, args=dict(bg_color="random"))
+    ext, intr = _view(seed, H, W)
+    m.eval()
+    torch.manual_seed(77)
+    with torch.no_grad():
+        rgb, _ = m(H, W, ext, intr)
+        rgb2, _ = m(H, W, ext, intr)                               # the generator advances: a second, different background
+    out = dict(H=H, W=W, T=T, tar_extrin=ext, tar_intrin=intr, rgb=rgb, rgb2=rgb2, seed=77, **_state_arrays(st))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(out))
+    print(name, "rgb mean", float(rgb.mean()), float(rgb2.mean()))
+
+
 LOSS_CFG_REF = dict(loss_name="gpnn_lm", loss_gain=3.5, patch_size=5, patcht_size=3, stride=2, stridet=1,
                     alpha=0.0, rou="-2", scaling=0.1, dist_fn="mse", macro_block=15, factor=1)
 LOSS_CFG_OTHER = dict(loss_name="gpnn_lm", patch_size=3, patcht_size=3, stride=2, stridet=1,
@@ -531,6 +546,7 @@ def main():
     golden_dataset("dataset")
     golden_render("render_dense", "dense", seed=0)
     golden_render("render_sparse", "sparse", seed=1, D=6, hv=6, wv=9, T=2)
+    golden_render_bg_random("render_bg_random")
     golden_step("step_dense_refcfg", "dense", LOSS_CFG_REF, seed=2)
     golden_step("step_sparse_othercfg", "sparse", LOSS_CFG_OTHER, seed=3, D=6, hv=6, wv=9)
     # the optional terms of MPV.py:455-466, 511-515, 533-551 (weight 0 / off in the shipped stage-2 configs)

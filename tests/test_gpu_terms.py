@@ -76,6 +76,22 @@ def test_eval_render_blends_background_like_the_reference():
     assert float((var_r["alpha"].cpu().double() - var_o["alpha"]).abs().max()) < RTOL
 
 
+def test_random_background_follows_the_reference_rng_stream():
+    """`bg_color='random'`: the background is `torch.rand(3)` from the global CPU generator, drawn once per render exactly as
+    MPV.py:456-457 does, so a seeded run blends the same colours as the reference (and a second render a different one)."""
+    g = load_golden("render_bg_random")
+    m = model_from_golden(g, bg_color="random")
+    H, W = int(g["H"]), int(g["W"])
+    ext, intr = torch.as_tensor(g["tar_extrin"]).to(dev()), torch.as_tensor(g["tar_intrin"]).to(dev())
+    m.eval()
+    torch.manual_seed(int(g["seed"]))
+    with torch.no_grad():
+        rgb, _ = m(H, W, ext, intr)
+        rgb2, _ = m(H, W, ext, intr)
+    assert relerr(rgb.cpu(), g["rgb"]) < RTOL and relerr(rgb2.cpu(), g["rgb2"]) < RTOL
+    assert float((rgb - rgb2).abs().max()) > 1e-3
+
+
 @pytest.mark.parametrize("vname", sorted(VIEWS))
 @pytest.mark.parametrize("mname", sorted(MODELS))
 def test_terms_and_their_backward_match_oracle(mname, vname):

@@ -332,6 +332,19 @@ def test_host_geometry_matches_oracle_on_random_views_and_layouts(seed):
         assert np.abs(ax[keep] - geo["ax"][:, d].numpy()[keep]).max(initial=0) < 1e-4
         assert np.abs(ay[keep] - geo["ay"][:, d].numpy()[keep]).max(initial=0) < 1e-4
     assert n_hit > H * W // 4
+    # the per-plane inverse view depth the terms kernels use (tiles.view_inv_depth): exactly linear in the pixel, equal to
+    # 1 / (the oracle's view depth = pytorch3d's zbuf); an affine normalisation folds into the coefficients
+    coef = tiles.view_inv_depth(grids, rel, intr[None], np.eye(4), H, W).astype(np.float64)
+    coef_n = tiles.view_inv_depth(grids, rel, intr[None], np.eye(4), H, W, scale=1.0 / 0.9, offset=-0.1 / 0.9).astype(np.float64)
+    rr, cc = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    u, v = (cc + 0.5 - W / 2.0).reshape(-1), (rr + 0.5 - H / 2.0).reshape(-1)
+    for d in range(D):
+        oh = geo["hit"][:, d].numpy()
+        inv_ref = 1.0 / geo["depth"][:, d].numpy()[oh]
+        got = coef[d, 0] * u[oh] + coef[d, 1] * v[oh] + coef[d, 2]
+        assert np.abs(got - inv_ref).max(initial=0) < 2e-6 * np.abs(inv_ref).max(initial=1)
+        got_n = coef_n[d, 0] * u[oh] + coef_n[d, 1] * v[oh] + coef_n[d, 2]
+        assert np.abs(got_n - (inv_ref - 0.1) / 0.9).max(initial=0) < 2e-6
 
 
 def test_argument_validation_of_the_data_entry_points():
