@@ -118,6 +118,27 @@ def test_argument_validation_happens_before_any_launch():
         _lib.call("vl3d_adam_step", ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16),
                   8, 0, 0.1, 0.9, 0.999, 6e-8, None)
     assert b"step" in lib.vl3d_last_error_string()
+    # the optional-terms entry points (csrc/terms.cu): every check precedes the launch, so no device is needed
+    P16 = ctypes.c_void_p(16)
+    v = _lib.View()
+    v.H, v.W, v.D, v.qh, v.qw = 8, 8, 2, 1, 1
+    coef = (ctypes.c_float * 6)()
+    with pytest.raises(_lib.Vl3dError, match="no output"):
+        _lib.call("vl3d_composite_terms_fwd", ctypes.byref(v), P16, None, None, None, 1, coef, 1e-4, None, None, None, None)
+    with pytest.raises(_lib.Vl3dError, match="inv_depth_host"):
+        _lib.call("vl3d_composite_terms_fwd", ctypes.byref(v), P16, None, None, None, 1, None, 1e-4, None, P16, None, None)
+    with pytest.raises(_lib.Vl3dError, match="sparsity_eps"):
+        _lib.call("vl3d_composite_terms_fwd", ctypes.byref(v), P16, None, None, None, 1, coef, 0.0, P16, None, None, None)
+    with pytest.raises(_lib.Vl3dError, match="bad T"):
+        _lib.call("vl3d_composite_terms_fwd", ctypes.byref(v), P16, None, None, None, 0, coef, 1e-4, P16, None, None, None)
+    with pytest.raises(_lib.Vl3dError, match="inv_depth_host"):
+        _lib.call("vl3d_composite_terms_bwd", ctypes.byref(v), P16, None, None, None, 1, None, 1e-4, None, P16, None, None, None, None)
+    with pytest.raises(_lib.Vl3dError, match="16-byte"):
+        _lib.call("vl3d_composite_terms_bwd", ctypes.byref(v), P16, None, None, None, 1, coef, 1e-4, P16, None, None,
+                  ctypes.c_void_p(8), None, None)
+    # nothing upstream: a no-op that returns success without a launch
+    assert _lib.call("vl3d_composite_terms_bwd", ctypes.byref(v), P16, None, None, None, 1, coef, 1e-4, None, None, None,
+                     None, None, None) == 0
 
 
 def test_product_refuses_cpu_tensors():

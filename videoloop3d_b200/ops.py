@@ -115,8 +115,14 @@ def make_inv_depth(pack: MeshPack, H, W, tar_extrin, tar_intrin, ref_extrin, sca
                                                      scale, offset))
 
 
-def _host_floats(a):
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+def _inv_depth_arg(view, a):
+    """(array kept alive by the caller, pointer) for the `inv_depth_host` argument: 3*D contiguous float32 on the host."""
+    if a is None:
+        return None, None
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.size < 3 * view.D:
+        raise _lib.Vl3dError(f"inv_depth needs 3 coefficients per plane ({3 * view.D} floats), got {a.size}")
+    return a, a.ctypes.data_as(C.c_void_p)
 
 
 def composite_terms_fwd(view, pack, atlas_dyn, atlas_sta, ts, T, inv_depth=None, sparsity_eps=1e-4, want_alpha=True,
@@ -130,17 +136,24 @@ def composite_terms_fwd(view, pack, atlas_dyn, atlas_sta, ts, T, inv_depth=None,
     alpha = torch.empty((T, H, W), dtype=torch.float32, device=dev) if want_alpha else None
     disp = torch.empty((T, H, W), dtype=torch.float32, device=dev) if want_disp else None
     sp = torch.zeros(1, dtype=torch.float64, device=dev) if want_sparsity else None
+    keep, inv_ptr = _inv_depth_arg(view, inv_depth)
     _lib.call("vl3d_composite_terms_fwd", C.byref(view), _lib.ptr(pack.quads), _lib.ptr(atlas_dyn), _lib.ptr(atlas_sta),
-              _lib.ptr(ts), int(T), _host_floats(inv_depth), float(sparsity_eps), _lib.ptr(alpha), _lib.ptr(disp), _lib.ptr(sp),
+              _lib.ptr(ts), int(T), inv_ptr, float(sparsity_eps), _lib.ptr(alpha), _lib.ptr(disp), _lib.ptr(sp),
               _lib.stream_ptr())
+    del keep
     return alpha, disp, sp
 
 
 def composite_terms_bwd(view, pack, atlas_dyn, atlas_sta, ts, T, inv_depth, sparsity_eps, g_alpha, g_disp, w_sparsity,
                         grad_dyn, grad_sta):
+    for name, g in (("g_alpha", g_alpha), ("g_disp", g_disp)):
+        if g is not None and (tuple(g.shape) != (T, view.H, view.W) or not g.is_contiguous() or g.dtype != torch.float32):
+            raise _lib.Vl3dError(f"composite_terms_bwd: {name} must be a contiguous float32 (T,H,W) tensor, got {tuple(g.shape)} {g.dtype}")
+    keep, inv_ptr = _inv_depth_arg(view, inv_depth)
     _lib.call("vl3d_composite_terms_bwd", C.byref(view), _lib.ptr(pack.quads), _lib.ptr(atlas_dyn), _lib.ptr(atlas_sta),
-              _lib.ptr(ts), int(T), _host_floats(inv_depth), float(sparsity_eps), _lib.ptr(g_alpha), _lib.ptr(g_disp),
+              _lib.ptr(ts), int(T), inv_ptr, float(sparsity_eps), _lib.ptr(g_alpha), _lib.ptr(g_disp),
               _lib.ptr(w_sparsity), _lib.ptr(grad_dyn), _lib.ptr(grad_sta), _lib.stream_ptr())
+    del keep
 
 
 def scale_invariant(rgb, T, res, out=None, partials=None):
