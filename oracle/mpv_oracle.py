@@ -21,6 +21,10 @@ What is restated (reference file:line):
   * compositing   utils_mpi.py:92-107 (overcompose), MPV.py:454 (alpha)
   * forward       MPV.py:477-556 (loop pad, scale-invariant gain, loss call, smoothness terms)
   * step          train_3dvid.py:214-244 (loss sum, backward, Adam eps=6e-8 MPV.py:213)
+  * optional      MPV.py:455-466 (background blend, disparity), 511-515 / 533-551 (sparsity, density, d_smooth) — pinned
+                  to `step_dense_terms` / `step_sparse_terms` / `render_bg_random`
+  * stage 1       MPI.py:452-652 (`MPMesh.render` / `forward`: loop-mask label, normalised disparity, six extra terms) —
+                  pinned to `stage1_loopmask` / `stage1_bg_normdepth`, and on a culled state to `stage1_sparsify`
 All maths is done with torch on the CPU in the dtype of `dtype` (float64 default for geometry).
 """
 from __future__ import annotations
