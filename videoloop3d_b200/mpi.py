@@ -302,6 +302,12 @@ class MPMesh(nn.Module):
                 del self.atlas_mask
         self.invalidate_geometry()
 
+    def _no_export(self, *a, **k):
+        raise NotImplementedError("mesh / texture / loop-mask export (MPI.py:223-271) is outside this package's scope: load "
+                                  "`state_dict()` into the reference's MPI.MPMesh (same keys) and export from there")
+
+    save_mesh = save_texture = save_loopmask = _no_export
+
     # ------------------------------------------------------------------ checkpoint format (MPI.py:207-221)
     _SCALARS = ("is_sparse", "atlas_full_w", "atlas_full_h", "atlas_grid_h", "atlas_grid_w")
     _SCALARS_DYN = ("has_dyn", "atlas_full_dyn_w", "atlas_full_dyn_h", "atlas_grid_dyn_h", "atlas_grid_dyn_w")
