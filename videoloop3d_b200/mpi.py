@@ -270,9 +270,6 @@ class MPMesh(nn.Module):
             raise NotImplementedError("geometry optimisation (optimize_geo_start) is never reached by the shipped configs and is "
                                       "not supported: the kernels assume fronto-parallel planes of axis-aligned quads")
 
-    def direct2sh(self):
-        raise NotImplementedError("direct2sh (view-dependent spherical harmonics, 'not well tested' in the reference) is not supported")
-
     def init_from_mpi(self, state_dict):
         """Load a stage-1 checkpoint written by `state_dict` — dense or culled (MPI.py:173-205)."""
         sd = state_dict
@@ -301,12 +298,6 @@ class MPMesh(nn.Module):
                 self.args.learn_loop_mask = False
                 del self.atlas_mask
         self.invalidate_geometry()
-
-    def _no_export(self, *a, **k):
-        raise NotImplementedError("mesh / texture / loop-mask export (MPI.py:223-271) is outside this package's scope: load "
-                                  "`state_dict()` into the reference's MPI.MPMesh (same keys) and export from there")
-
-    save_mesh = save_texture = save_loopmask = _no_export
 
     # ------------------------------------------------------------------ checkpoint format (MPI.py:207-221)
     _SCALARS = ("is_sparse", "atlas_full_w", "atlas_full_h", "atlas_grid_h", "atlas_grid_w")
