@@ -506,6 +506,31 @@ def test_stage1_tile_culling_matches_reference():
         m3.update_step(10 ** 7)
 
 
+def test_tile_culling_helpers():
+    """Host helpers of `MPMesh.sparsify_faces`: the atlas grid of MPI.py:367-381 (brute-force restatement) and the 3x3
+    erosion / dilation with zero padding of utils.py:298-317 (naive loops)."""
+    from videoloop3d_b200 import MPMesh
+    for n in list(range(16, 400)) + [777, 1024, 4099, 17532]:
+        h, w, filler = MPMesh._tile_grid(n)
+        cands = [r for r in range(int(np.sqrt(n / 4)), int(np.sqrt(n)))]
+        best = min(cands, key=lambda r: (r - n % r, cands.index(r)))          # first minimum of rows - n % rows
+        assert h == best and w == n // h + 1 and filler == h * w - n and 1 <= filler <= h
+        assert h * w > n and int(np.sqrt(n / 4)) <= h < int(np.sqrt(n))        # rows between sqrt(n / 4) and sqrt(n)
+    assert MPMesh._tile_grid(0) == (0, 0, 0)
+    with pytest.raises(ValueError):
+        MPMesh._tile_grid(3)
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(1, 1, 9, 11, generator=g)
+    xp = np.pad(x[0, 0].numpy(), 1)                                            # zero padding: the border erodes
+    ero = np.array([[xp[r:r + 3, c:c + 3].min() for c in range(11)] for r in range(9)])
+    dil = np.array([[xp[r:r + 3, c:c + 3].max() for c in range(11)] for r in range(9)])
+    assert np.array_equal(MPMesh._morph(x, 1, 0)[0, 0].numpy(), ero) and np.array_equal(MPMesh._morph(x, 0, 1)[0, 0].numpy(), dil)
+    ep = np.pad(ero, 1)
+    ero_dil = np.array([[ep[r:r + 3, c:c + 3].max() for c in range(11)] for r in range(9)])
+    assert np.array_equal(MPMesh._morph(x, 1, 1)[0, 0].numpy(), ero_dil)
+    assert float(MPMesh._morph(x, 1, 0)[0, 0, 0].max()) == 0.0                 # (first row touches the zero padding)
+
+
 def test_argument_validation_of_the_round2_entry_points():
     """vl3d_copy_boxes / vl3d_fused_bwd_adam_own / the sizing helpers reject bad arguments before touching the device."""
     lib = _lib.load()
