@@ -8,7 +8,7 @@ import torch
 
 from oracle import mpv_oracle as MO
 from test_gpu_composite_sweep import VIEWS, _rot
-from util import load_golden, relerr, state_from_golden
+from util import load_golden, relerr
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-4

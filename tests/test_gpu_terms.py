@@ -5,7 +5,6 @@ unmodified reference run with those terms ON, and against the CPU oracle across 
 Every shipped stage-2 config leaves them off; the CUDA path for them is csrc/terms.cu behind
 `vl3d_composite_terms_fwd / _bwd` (an autograd node next to the main composite).  Tolerance: 1e-4 relative on values
 (north_star), 5e-4 of the largest entry on gradients (the same bar as the main backward's golden test)."""
-import numpy as np
 import pytest
 import torch
 
@@ -148,7 +147,6 @@ def test_terms_and_their_backward_match_oracle(mname, vname):
 
 def test_terms_reject_bad_arguments():
     """C-ABI argument checks of the new entry points (error codes, no launch)."""
-    import ctypes as C
     from videoloop3d_b200 import _lib, ops
     g = load_golden("step_dense_terms")
     m = model_from_golden(g)
